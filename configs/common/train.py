@@ -1,0 +1,69 @@
+"""The ``train`` namespace shared by every recipe (keys: reference configs/common/train.py:8-150;
+additions are marked NEW)."""
+from libai_b200.config import DictConfig, LazyCall
+from libai_b200.evaluation import ClsEvaluator
+from libai_b200.scheduler import WarmupCosineLR
+
+train = dict(
+    # Directory where output files are written
+    output_dir="./output",
+    # `train_micro_batch_size` is the number of samples per batch on each GPU;
+    # train_mini_batch_size = train_micro_batch_size * num_accumulation_steps and
+    # global_batch_size = micro * num_accumulation_steps * data_parallel_size.
+    # Any one of the three can be left None and is derived.
+    train_micro_batch_size=32,
+    global_batch_size=None,
+    num_accumulation_steps=None,
+    # total training iterations (optimizer steps) / epochs; the larger one wins
+    train_iter=10000,
+    train_epoch=0,
+    consumed_train_samples=0,
+    consumed_valid_samples=0,
+    train_samples=None,
+    # fraction of warm-up iterations
+    warmup_ratio=0,
+    start_iter=0,
+    # mixed precision: bf16 parameters + fp32 master weights (NEW: dtype "bf16" | "fp16";
+    # fp16 enables the dynamic loss scaler)
+    amp=dict(enabled=False, dtype="bf16"),
+    # recompute each transformer layer in backward
+    activation_checkpoint=dict(enabled=False),
+    # gradient bucket size for data-parallel reduction (names kept from the reference)
+    nccl_fusion_threshold_mb=16,
+    nccl_fusion_max_ops=24,
+    # ZeRO: stage 1 = optimizer state, 2 = + gradients, 3 = + parameters partitioned over DP
+    zero_optimization=dict(enabled=False, stage=1),
+    checkpointer=dict(period=5000, max_to_keep=100, save_model_after_n_epoch=None),
+    test_micro_batch_size=32,
+    evaluation=dict(
+        enabled=True,
+        evaluator=LazyCall(ClsEvaluator)(topk=(1, 5)),
+        eval_period=5000,
+        eval_after_n_epoch=None,
+        eval_iter=1e5,  # running steps for validation/test
+        eval_metric="Acc@1",
+        eval_mode="max",
+    ),
+    # path of a checkpoint directory to load weights from (not a resume)
+    load_weight="",
+    log_period=20,
+    # lr scheduler; `max_iter` and `warmup_iter` are injected by the trainer
+    scheduler=LazyCall(WarmupCosineLR)(warmup_factor=0.001, alpha=0.01, warmup_method="linear"),
+    dist=dict(
+        data_parallel_size=1,
+        tensor_parallel_size=1,
+        pipeline_parallel_size=1,
+        # must be set for pipeline parallelism: number of layer indices to spread over stages
+        pipeline_num_layers=None,
+        # e.g. [0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3]
+        custom_pipeline_stage_id=None,
+        # NEW: Megatron-style sequence parallelism inside the TP region and fused comm+GEMM kernels
+        sequence_parallel=False,
+        fused_tp_comm=False,
+    ),
+    # "cuda" | "cpu": where batches are placed by get_batch
+    input_placement_device="cuda",
+    rdma_enabled=True,
+    seed=1234,
+)
+train = DictConfig(train)

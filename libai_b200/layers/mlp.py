@@ -1,0 +1,54 @@
+"""Transformer feed-forward block.
+
+Spec: reference libai/layers/mlp.py:22-114 — ``h→f`` column-parallel linear, bias+GELU, ``f→h``
+row-parallel linear, bias+dropout.  The bias+GELU runs in the epilogue of the first GEMM
+(``Linear1D.forward(act=...)``) and bias+dropout+residual is one fused op; ``bias_gelu_fusion``
+/ ``bias_dropout_fusion`` are accepted for config compatibility (both paths compute the same
+function).
+"""
+from torch import nn
+
+from libai_b200.ops import functional as OF
+
+from ._param import xavier_normal_
+from .linear import Linear
+
+
+class MLP(nn.Module):
+    def __init__(
+        self,
+        hidden_size,
+        ffn_hidden_size,
+        output_dropout_prob=0.0,
+        init_method=xavier_normal_,
+        output_layer_init_method=None,
+        bias_gelu_fusion=False,
+        bias_dropout_fusion=False,
+        *,
+        layer_idx=0,
+    ):
+        super().__init__()
+        self.output_dropout_prob = output_dropout_prob
+        self.bias_gelu_fusion = bias_gelu_fusion
+        self.bias_dropout_fusion = bias_dropout_fusion
+        if output_layer_init_method is None:
+            output_layer_init_method = init_method
+        self.dense_h_to_4h = Linear(
+            hidden_size, ffn_hidden_size, bias=True, parallel="col", skip_bias_add=False,
+            init_method=init_method, layer_idx=layer_idx,
+        )
+        self.dense_4h_to_h = Linear(
+            ffn_hidden_size, hidden_size, bias=True, parallel="row", skip_bias_add=True,
+            init_method=output_layer_init_method, layer_idx=layer_idx,
+        )
+
+    def forward(self, hidden_states, residual=None):
+        """Returns ``residual + dropout(mlp(x))`` when ``residual`` is given (fused epilogue)."""
+        inter = self.dense_h_to_4h(hidden_states, act="gelu")
+        out, bias = self.dense_4h_to_h(inter)
+        return OF.bias_dropout_add(out, bias, residual, self.output_dropout_prob, self.training)
+
+    def extra_repr(self) -> str:
+        return "bias_gelu_fusion={}, bias_dropout_fusion={}, dropout={}".format(
+            self.bias_gelu_fusion, self.bias_dropout_fusion, self.output_dropout_prob
+        )

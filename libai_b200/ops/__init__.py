@@ -1,0 +1,89 @@
+"""Hot operators.
+
+Every operator has two implementations:
+
+* ``native`` – hand-written sm_100a CUDA kernels in ``libai_b200/csrc`` (tcgen05/TMEM/TMA GEMMs,
+  fused norms, flash attention, fused optimizer, vocab-parallel cross entropy, in-kernel
+  NVLink collectives).  This is the product and the only path GPU training takes.
+* ``ref`` – plain PyTorch (+ ``torch.distributed``).  Test oracle, CPU/gloo plumbing path and the
+  honest "NCCL + library GEMM" baseline (select with ``LIBAI_B200_IMPL=ref``).
+
+The extension is built in-tree by ``__graft_entry__.build()`` / ``python -m libai_b200.ops.build``
+and loaded from ``libai_b200/_C.so``.  On a CUDA device a missing extension is a hard error, never
+a silent fallback.
+"""
+from __future__ import annotations
+
+import os
+import threading
+
+import torch
+
+_LOCK = threading.Lock()
+_EXT = None
+_EXT_ERR = None
+_SO_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_C.so")
+_LAUNCH_COUNT = 0
+
+
+def so_path() -> str:
+    return _SO_PATH
+
+
+def impl() -> str:
+    """'native' (default) or 'ref' (``LIBAI_B200_IMPL=ref`` forces the PyTorch path on GPU)."""
+    return os.environ.get("LIBAI_B200_IMPL", "native")
+
+
+def load_ext(required: bool = True):
+    """Load ``libai_b200/_C.so`` once and return ``torch.ops.libai_b200``."""
+    global _EXT, _EXT_ERR
+    if _EXT is not None:
+        return _EXT
+    with _LOCK:
+        if _EXT is not None:
+            return _EXT
+        try:
+            if not os.path.exists(_SO_PATH):
+                raise FileNotFoundError(
+                    f"{_SO_PATH} not found - build it with `python -m libai_b200.ops.build`"
+                )
+            torch.ops.load_library(_SO_PATH)
+            _EXT = torch.ops.libai_b200
+        except Exception as e:  # noqa
+            _EXT_ERR = e
+            if required:
+                raise RuntimeError(
+                    "libai_b200 native extension is required on CUDA devices but could not be "
+                    f"loaded: {e}"
+                ) from e
+            return None
+    return _EXT
+
+
+def use_native(*tensors) -> bool:
+    """True when the native sm_100a kernel must be used for these tensors."""
+    if impl() != "native":
+        return False
+    for t in tensors:
+        if isinstance(t, torch.Tensor):
+            if not t.is_cuda:
+                return False
+            load_ext(required=True)
+            return True
+    return False
+
+
+def count_launch(n: int = 1) -> None:
+    global _LAUNCH_COUNT
+    _LAUNCH_COUNT += n
+
+
+def launch_count() -> int:
+    """Number of native kernel launches issued through the python wrappers (bench bookkeeping)."""
+    return _LAUNCH_COUNT
+
+
+def reset_launch_count() -> None:
+    global _LAUNCH_COUNT
+    _LAUNCH_COUNT = 0
