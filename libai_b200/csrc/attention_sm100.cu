@@ -1,0 +1,720 @@
+// Flash attention for sm_100a on tcgen05 / TMEM / TMA (head dim 64 or 128, causal or full, bf16).
+//
+// Replaces the score GEMM + fused_scale_(tril_)softmax(_mask)_dropout + context GEMM sequence of the
+// reference (libai/layers/attention.py:211-253): no [b, a, s, s] tensor and no materialised mask.
+// Q/K/V are read straight out of the packed QKV projection through strided 4-D TMA tensor maps
+// ([B, A, S, D] views), O is written in [B, S, A, D] so the output projection consumes it as-is.
+//
+// Forward, one CTA per (batch, head, 128-query block), 192 threads:
+//   warp 0        TMA producer : Q once, then K/V tiles of 128 keys (double buffered)
+//   warp 1        MMA issuer   : S_j = Q·K_jᵀ (TMEM, double buffered)  and  O_j = P_j·V_j (TMEM)
+//   warps 2..5    softmax      : thread r owns query row r: tcgen05.ld S → online softmax (exp2) →
+//                                P (bf16) to swizzled smem as the A operand of the PV MMA; running
+//                                output kept in registers: O ← (O + O_{j-1}) · α_j
+// The QKᵀ MMA of block j+1 is issued before the softmax of block j, so tensor-core work hides behind
+// the (MUFU-bound) softmax.
+#include "common.cuh"
+
+namespace lb {
+
+constexpr int ATT_BM = 128;   // queries per CTA
+constexpr int ATT_BN = 128;   // keys per tile
+constexpr int ATT_THREADS = 192;
+
+template <int D>
+struct AttnCfg {
+  static constexpr int QK_CHUNKS = D / 64;                 // 64-element (128B) K-chunks of Q and K tiles
+  static constexpr int TILE_BYTES = ATT_BN * D * 2;        // one Q / K / V tile
+  static constexpr int P_BYTES = ATT_BM * ATT_BN * 2;      // 32 KB
+  static constexpr int P_STAGES = (D == 64) ? 2 : 1;
+  static constexpr int SMEM_BYTES = TILE_BYTES /*Q*/ + 4 * TILE_BYTES /*K,V x2*/ + P_STAGES * P_BYTES + 1024 + 256;
+  // TMEM columns: S0 [0,128) S1 [128,256) O [256, 256+D)
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr uint32_t O_COL = 256;
+};
+
+struct AttnFwdParams {
+  __nv_bfloat16* o;   // [B, S, A, D]
+  float* lse;         // [B, A, S]
+  int B, A, S;
+  int causal;
+  float scale_log2;   // scale * log2(e)
+  float scale;
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, AttnFwdParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int PST = Cfg::P_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::TILE_BYTES;            // 2 stages
+  uint8_t* sV = sK + 2 * Cfg::TILE_BYTES;        // 2 stages
+  uint8_t* sP = sV + 2 * Cfg::TILE_BYTES;        // PST stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + PST * Cfg::P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* v_full = bars + 5;        // 2
+  uint64_t* v_empty = bars + 7;       // 2
+  uint64_t* s_full = bars + 9;        // 2
+  uint64_t* s_empty = bars + 11;      // 2
+  uint64_t* p_full = bars + 13;       // 2
+  uint64_t* p_empty = bars + 15;      // 2
+  uint64_t* o_full = bars + 17;       // 1
+  uint64_t* o_empty = bars + 18;      // 1
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp_idx = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int q_blk = blockIdx.x;
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int q0 = q_blk * ATT_BM;
+  int nkv = (p.S + ATT_BN - 1) / ATT_BN;
+  if (p.causal) nkv = min(nkv, q_blk + 1);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 128);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp_idx == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, Cfg::TILE_BYTES);
+#pragma unroll
+      for (int c = 0; c < Cfg::QK_CHUNKS; ++c)
+        tma_load_4d(sQ + c * (ATT_BM * 128), &tmap_q, q_full, c * 64, q0, head, batch);
+      for (int j = 0; j < nkv; ++j) {
+        const int b = j & 1;
+        const uint32_t par = ((j >> 1) & 1) ^ 1;
+        mbar_wait(&k_empty[b], par);
+        mbar_arrive_expect_tx(&k_full[b], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < Cfg::QK_CHUNKS; ++c)
+          tma_load_4d(sK + b * Cfg::TILE_BYTES + c * (ATT_BN * 128), &tmap_k, &k_full[b], c * 64, j * ATT_BN, head, batch);
+        mbar_wait(&v_empty[b], par);
+        mbar_arrive_expect_tx(&v_full[b], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < Cfg::QK_CHUNKS; ++c)
+          tma_load_4d(sV + b * Cfg::TILE_BYTES + c * (ATT_BN * 128), &tmap_v, &v_full[b], c * 64, j * ATT_BN, head, batch);
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BM, ATT_BN, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, D, false, true);
+    const uint32_t q_addr = smem_u32(sQ);
+    auto issue_s = [&](int j) {
+      const int b = j & 1;
+      mbar_wait(&k_full[b], (j >> 1) & 1);
+      mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t k_addr = smem_u32(sK + b * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk / 4) * (ATT_BM * 128) + (kk % 4) * 32;
+          umma_f16_ss(tmem_base + b * ATT_BN, make_smem_desc_sw128(q_addr + off, 0, 1024),
+                      make_smem_desc_sw128(k_addr + off, 0, 1024), idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[b]);
+        umma_commit(&k_empty[b]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) issue_s(j + 1);
+      const int b = j & 1, pb = j % PST;
+      mbar_wait(&p_full[pb], (j / PST) & 1);
+      mbar_wait(&v_full[b], (j >> 1) & 1);
+      mbar_wait(o_empty, (j & 1) ^ 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t p_addr = smem_u32(sP + pb * Cfg::P_BYTES);
+        const uint32_t v_addr = smem_u32(sV + b * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(p_addr + (kk / 4) * (ATT_BM * 128) + (kk % 4) * 32, 0, 1024);
+          const uint64_t db = make_smem_desc_sw128(v_addr + kk * (16 * 128), ATT_BN * 128, 1024);
+          umma_f16_ss(tmem_base + Cfg::O_COL, da, db, idesc_pv, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&v_empty[b]);
+        umma_commit(&p_empty[pb]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= softmax / output (128 threads, thread <-> query row) =================
+    const int quad = warp_idx % 4;
+    const int r = quad * 32 + lane;          // row inside the tile
+    const int q_idx = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    float o_run[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o_run[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    auto add_o_block = [&](int jprev) {
+      mbar_wait(o_full, jprev & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::O_COL + c * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_run[c * 32 + i] += __uint_as_float(t[i]);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(o_empty);
+    };
+
+    for (int j = 0; j < nkv; ++j) {
+      const int b = j & 1, pb = j % PST;
+      mbar_wait(&s_full[b], (j >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t s_addr = tmem_base + lane_off + b * ATT_BN;
+      const int k0 = j * ATT_BN;
+      const bool need_mask = (p.causal && j == q_blk) || (k0 + ATT_BN > p.S);
+      // ---- pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < ATT_BN / 32; ++c) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(s_addr + c * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(t[i]);
+          if (need_mask) {
+            const int kidx = k0 + c * 32 + i;
+            if (kidx >= p.S || (p.causal && kidx > q_idx)) x = -INFINITY;
+          }
+          mx = fmaxf(mx, x);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = exp2f(m_run - m_use);   // m_run = -inf -> 0
+      // ---- wait for the P buffer to be free, then pass 2: p = exp2(s*scale - m), write bf16 to swizzled smem
+      mbar_wait(&p_empty[pb], ((j / PST) & 1) ^ 1);
+      uint8_t* prow = sP + pb * Cfg::P_BYTES + r * 128;
+      float rowsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < ATT_BN / 32; ++c) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(s_addr + c * 32, t);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float x0 = __uint_as_float(t[i]), x1 = __uint_as_float(t[i + 1]);
+          float e0 = exp2f(x0 * p.scale_log2 - m_use), e1 = exp2f(x1 * p.scale_log2 - m_use);
+          if (need_mask) {
+            const int kidx = k0 + c * 32 + i;
+            if (kidx >= p.S || (p.causal && kidx > q_idx)) e0 = 0.f;
+            if (kidx + 1 >= p.S || (p.causal && kidx + 1 > q_idx)) e1 = 0.f;
+          }
+          rowsum += e0 + e1;
+          packed[i / 2] = pack_bf16(e0, e1);
+        }
+        // 32 keys = 64 bytes = four 16-byte chunks; key chunk (c / 2) selects the 64-key half of the tile
+        uint8_t* half_base = prow + (c / 2) * (ATT_BM * 128);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int chunk16 = (c % 2) * 4 + q4;               // 16B chunk index inside the 128B row
+          const int phys = chunk16 ^ (r & 7);                 // 128B swizzle
+          *reinterpret_cast<uint4*>(half_base + phys * 16) =
+              make_uint4(packed[q4 * 4], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&s_empty[b]);      // S buffer b may be overwritten by QKᵀ of block j+2
+      fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&p_full[pb]);
+      l_run = l_run * alpha + rowsum;
+      // ---- fold the previous block's P·V into the running output, then rescale to the new max
+      if (j > 0) add_o_block(j - 1);
+      if (alpha != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) o_run[i] *= alpha;
+      }
+      m_run = m_new;
+    }
+    add_o_block(nkv - 1);
+    if (q_idx < p.S) {
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      __nv_bfloat16* orow = p.o + ((static_cast<size_t>(batch) * p.S + q_idx) * p.A + head) * D;
+#pragma unroll
+      for (int i = 0; i < D; i += 8) {
+        *reinterpret_cast<uint4*>(orow + i) =
+            make_uint4(pack_bf16(o_run[i] * inv, o_run[i + 1] * inv), pack_bf16(o_run[i + 2] * inv, o_run[i + 3] * inv),
+                       pack_bf16(o_run[i + 4] * inv, o_run[i + 5] * inv), pack_bf16(o_run[i + 6] * inv, o_run[i + 7] * inv));
+      }
+      // natural-log LSE of the scaled scores
+      p.lse[(static_cast<size_t>(batch) * p.A + head) * p.S + q_idx] =
+          (m_run == -INFINITY) ? -INFINITY : (m_run + log2f(l_run)) * 0.6931471805599453f;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace lb
+
+namespace {
+bool make_qkv_tmap(CUtensorMap* m, const void* ptr, int B, int A, int S, int D, const long* st) {
+  // dims innermost first: {D, S, A, B}; st = {batch, head, seq} strides in elements
+  uint64_t dims[4] = {(uint64_t)D, (uint64_t)S, (uint64_t)A, (uint64_t)B};
+  uint64_t strides[4] = {2, (uint64_t)st[2] * 2, (uint64_t)st[1] * 2, (uint64_t)st[0] * 2};
+  uint32_t box[4] = {64, 128, 1, 1};
+  return lb_host::make_tmap_bf16(m, ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int D>
+cudaError_t launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const lb::AttnFwdParams& p,
+                       cudaStream_t s) {
+  using Cfg = lb::AttnCfg<D>;
+  auto kern = lb::attn_fwd_kernel<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.S + lb::ATT_BM - 1) / lb::ATT_BM, p.A, p.B);
+  kern<<<grid, lb::ATT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, p);
+  return cudaGetLastError();
+}
+}  // namespace
+
+extern "C" int lb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int A, int S, int D,
+                           const long* q_strides, const long* k_strides, const long* v_strides, int causal, float scale,
+                           cudaStream_t s) {
+  if (D != 64 && D != 128) return -1;
+  for (int i = 0; i < 3; ++i)
+    if ((q_strides[i] % 8) || (k_strides[i] % 8) || (v_strides[i] % 8)) return -3;
+  CUtensorMap tq, tk, tv;
+  if (!make_qkv_tmap(&tq, q, B, A, S, D, q_strides)) return -2;
+  if (!make_qkv_tmap(&tk, k, B, A, S, D, k_strides)) return -2;
+  if (!make_qkv_tmap(&tv, v, B, A, S, D, v_strides)) return -2;
+  lb::AttnFwdParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.lse = lse;
+  p.B = B;
+  p.A = A;
+  p.S = S;
+  p.causal = causal;
+  p.scale = scale;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  cudaError_t e = (D == 64) ? launch_fwd<64>(tq, tk, tv, p, s) : launch_fwd<128>(tq, tk, tv, p, s);
+  return (int)e;
+}
+
+// =================================================================================================
+// Backward.  One CTA per (batch, head, 128-key block); loops over the query blocks that attend to it.
+//   S  = Q_i·Kᵀ , dP = dO_i·Vᵀ              (tcgen05, TMEM)
+//   P  = exp(S·scale − lse) , dS = P ∘ (dP − δ) · scale     (softmax threads → bf16 tiles in smem)
+//   dV += Pᵀ·dO_i , dK += dSᵀ·Q_i           (tcgen05, accumulators stay in TMEM for the whole CTA;
+//                                            Pᵀ / dSᵀ are the same smem tiles read as MN-major A operands)
+//   dQ_i += dS·K                            (tcgen05 → TMEM → fp32 red.add into dq_accum)
+// δ = rowsum(dO ∘ O) is produced by attn_delta_kernel, dq_accum is converted to bf16 afterwards.
+// =================================================================================================
+namespace lb {
+
+template <int D>
+struct AttnBwdCfg {
+  static constexpr int CHUNKS = D / 64;
+  static constexpr int TILE_BYTES = 128 * D * 2;
+  static constexpr int PS_BYTES = 128 * 128 * 2;
+  static constexpr int QST = (D == 64) ? 2 : 1;
+  static constexpr int SMEM_BYTES = 2 * TILE_BYTES /*K,V*/ + 2 * QST * TILE_BYTES /*Q,dO*/ + 2 * PS_BYTES + 1024 + 256;
+  static constexpr uint32_t S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + D;
+  static constexpr uint32_t DQ_COL = (D == 64) ? 384 : 0;  // D = 128: dQ aliases the S columns
+};
+
+struct AttnBwdParams {
+  const float* lse;     // [B, A, S]
+  const float* delta;   // [B, A, S]
+  float* dq_accum;      // [B, A, S, D] fp32
+  __nv_bfloat16* dk;    // strided [B, A, S, D] views
+  __nv_bfloat16* dv;
+  long g_strides[3];    // batch, head, seq strides (elements) of dk / dv
+  int B, A, S;
+  int causal;
+  float scale, scale_log2;
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                AttnBwdParams p) {
+  using Cfg = AttnBwdCfg<D>;
+  constexpr int QST = Cfg::QST;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + Cfg::TILE_BYTES;
+  uint8_t* sQ = sV + Cfg::TILE_BYTES;                 // QST stages
+  uint8_t* sDO = sQ + QST * Cfg::TILE_BYTES;          // QST stages
+  uint8_t* sP = sDO + QST * Cfg::TILE_BYTES;
+  uint8_t* sDS = sP + Cfg::PS_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + Cfg::PS_BYTES);
+  uint64_t* kv_full = bars;          // 1
+  uint64_t* qdo_full = bars + 1;     // 2
+  uint64_t* qdo_empty = bars + 3;    // 2
+  uint64_t* sdp_full = bars + 5;     // 1
+  uint64_t* pds_full = bars + 6;     // 1
+  uint64_t* pds_empty = bars + 7;    // 1
+  uint64_t* dq_full = bars + 8;      // 1
+  uint64_t* dq_empty = bars + 9;     // 1
+  uint64_t* acc_full = bars + 10;    // 1
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp_idx = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int kv_blk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+  const int k0 = kv_blk * 128;
+  const int nq = (p.S + 127) / 128;
+  const int i_begin = p.causal ? kv_blk : 0;
+  const int iters = nq - i_begin;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(pds_empty, 1);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 128);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
+#pragma unroll
+      for (int c = 0; c < Cfg::CHUNKS; ++c) {
+        tma_load_4d(sK + c * (128 * 128), &tmap_k, kv_full, c * 64, k0, head, batch);
+        tma_load_4d(sV + c * (128 * 128), &tmap_v, kv_full, c * 64, k0, head, batch);
+      }
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % QST;
+        const int q0 = (i_begin + it) * 128;
+        mbar_wait(&qdo_empty[st], ((it / QST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qdo_full[st], 2 * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < Cfg::CHUNKS; ++c) {
+          tma_load_4d(sQ + st * Cfg::TILE_BYTES + c * (128 * 128), &tmap_q, &qdo_full[st], c * 64, q0, head, batch);
+          tma_load_4d(sDO + st * Cfg::TILE_BYTES + c * (128 * 128), &tmap_do, &qdo_full[st], c * 64, q0, head, batch);
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);   // Q·Kᵀ, dO·Vᵀ
+    constexpr uint32_t idesc_t = make_idesc_bf16(128, D, true, true);       // Pᵀ·dO, dSᵀ·Q
+    constexpr uint32_t idesc_q = make_idesc_bf16(128, D, false, true);      // dS·K
+    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+    mbar_wait(kv_full, 0);
+    for (int it = 0; it < iters; ++it) {
+      const int st = it % QST;
+      mbar_wait(&qdo_full[st], (it / QST) & 1);
+      if (D == 128) mbar_wait(dq_empty, (it & 1) ^ 1);   // dQ aliases S
+      tc_fence_after_sync();
+      const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
+      const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk / 4) * (128 * 128) + (kk % 4) * 32;
+          umma_f16_ss(tmem_base + Cfg::S_COL, make_smem_desc_sw128(q_addr + off, 0, 1024),
+                      make_smem_desc_sw128(k_addr + off, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk / 4) * (128 * 128) + (kk % 4) * 32;
+          umma_f16_ss(tmem_base + Cfg::DP_COL, make_smem_desc_sw128(do_addr + off, 0, 1024),
+                      make_smem_desc_sw128(v_addr + off, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(sdp_full);
+      }
+      __syncwarp();
+      mbar_wait(pds_full, it & 1);
+      if (D == 64) mbar_wait(dq_empty, (it & 1) ^ 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        // K dimension of these three GEMMs = 128 (queries for dV/dK, keys for dQ): 8 steps of 16
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t a_pt = make_smem_desc_sw128(p_addr + kk * 2048, 128 * 128, 1024);       // Pᵀ  (MN-major A)
+          const uint64_t b_do = make_smem_desc_sw128(do_addr + kk * 2048, 128 * 128, 1024);      // dO  (MN-major B)
+          umma_f16_ss(tmem_base + Cfg::DV_COL, a_pt, b_do, idesc_t, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t a_dst = make_smem_desc_sw128(ds_addr + kk * 2048, 128 * 128, 1024);     // dSᵀ (MN-major A)
+          const uint64_t b_q = make_smem_desc_sw128(q_addr + kk * 2048, 128 * 128, 1024);        // Q   (MN-major B)
+          umma_f16_ss(tmem_base + Cfg::DK_COL, a_dst, b_q, idesc_t, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t a_ds = make_smem_desc_sw128(ds_addr + (kk / 4) * (128 * 128) + (kk % 4) * 32, 0, 1024);  // dS (K-major A)
+          const uint64_t b_k = make_smem_desc_sw128(k_addr + kk * 2048, 128 * 128, 1024);                          // K  (MN-major B)
+          umma_f16_ss(tmem_base + Cfg::DQ_COL, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(dq_full);
+        umma_commit(&qdo_empty[st]);
+        umma_commit(pds_empty);
+        if (it == iters - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp_idx % 4;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const size_t bh = static_cast<size_t>(batch) * p.A + head;
+    for (int it = 0; it < iters; ++it) {
+      const int q_blk = i_begin + it;
+      const int q_idx = q_blk * 128 + r;
+      const bool q_ok = q_idx < p.S;
+      const float lse2 = q_ok ? p.lse[bh * p.S + q_idx] * 1.4426950408889634f : 0.f;
+      const float delta = q_ok ? p.delta[bh * p.S + q_idx] : 0.f;
+      const bool need_mask = (p.causal && q_blk == kv_blk) || (k0 + 128 > p.S) || (q_blk * 128 + 128 > p.S);
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after_sync();
+      mbar_wait(pds_empty, (it & 1) ^ 1);
+      uint8_t* prow = sP + r * 128;
+      uint8_t* dsrow = sDS + r * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t ts[32], td[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::S_COL + c * 32, ts);
+        tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DP_COL + c * 32, td);
+        tmem_ld_wait();
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = exp2f(__uint_as_float(ts[i]) * p.scale_log2 - lse2);
+          float p1 = exp2f(__uint_as_float(ts[i + 1]) * p.scale_log2 - lse2);
+          if (need_mask) {
+            const int kidx = k0 + c * 32 + i;
+            if (!q_ok || kidx >= p.S || (p.causal && kidx > q_idx)) p0 = 0.f;
+            if (!q_ok || kidx + 1 >= p.S || (p.causal && kidx + 1 > q_idx)) p1 = 0.f;
+          }
+          const float d0 = p0 * (__uint_as_float(td[i]) - delta) * p.scale;
+          const float d1 = p1 * (__uint_as_float(td[i + 1]) - delta) * p.scale;
+          pp[i / 2] = pack_bf16(p0, p1);
+          dd[i / 2] = pack_bf16(d0, d1);
+        }
+        const int half_off = (c / 2) * (128 * 128);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int phys = ((c % 2) * 4 + q4) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + half_off + phys * 16) =
+              make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
+          *reinterpret_cast<uint4*>(dsrow + half_off + phys * 16) =
+              make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async();
+      mbar_arrive(pds_full);
+      // ---- dQ block: TMEM -> fp32 atomics
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after_sync();
+      float* dq_row = p.dq_accum + (bh * p.S + q_idx) * D;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DQ_COL + c * 32, t);
+        tmem_ld_wait();
+        if (q_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dq_row + c * 32 + i),
+                         "f"(__uint_as_float(t[i])), "f"(__uint_as_float(t[i + 1])), "f"(__uint_as_float(t[i + 2])),
+                         "f"(__uint_as_float(t[i + 3]))
+                         : "memory");
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(dq_empty);
+    }
+    // ---- dV / dK accumulators: thread r <-> key row r
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    const int k_idx = k0 + r;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
+      __nv_bfloat16* row = base + batch * p.g_strides[0] + head * p.g_strides[1] + static_cast<long>(k_idx) * p.g_strides[2];
+      const uint32_t col = which == 0 ? Cfg::DV_COL : Cfg::DK_COL;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + col + c * 32, t);
+        tmem_ld_wait();
+        if (k_idx < p.S) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            *reinterpret_cast<uint4*>(row + c * 32 + i) = make_uint4(
+                pack_bf16(__uint_as_float(t[i]), __uint_as_float(t[i + 1])),
+                pack_bf16(__uint_as_float(t[i + 2]), __uint_as_float(t[i + 3])),
+                pack_bf16(__uint_as_float(t[i + 4]), __uint_as_float(t[i + 5])),
+                pack_bf16(__uint_as_float(t[i + 6]), __uint_as_float(t[i + 7])));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// delta[b, a, s] = sum_d dO[b, a, s, d] * O[b, a, s, d]   (one warp per row)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o,
+                                  float* __restrict__ delta, int B, int A, int S, int D, long sb, long sa, long ss) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  const long total = static_cast<long>(B) * A * S;
+  if (warp >= total) return;
+  const int s = warp % S, a = (warp / S) % A, b = warp / (static_cast<long>(S) * A);
+  const long off = b * sb + a * sa + s * ss;
+  float acc = 0.f;
+  for (int d = lane * 2; d < D; d += 64) {
+    const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(dout + off + d));
+    const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(o + off + d));
+    acc += x.x * y.x + x.y * y.y;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) delta[warp] = acc;
+}
+
+// dq (strided bf16) = dq_accum (fp32 [B, A, S, D])
+__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int A,
+                                       int S, int D, long sb, long sa, long ss) {
+  const long nvec = static_cast<long>(B) * A * S * D / 4;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long e = i * 4;
+    const int d = e % D;
+    const long row = e / D;
+    const int s = row % S, a = (row / S) % A;
+    const long b = row / (static_cast<long>(S) * A);
+    const float4 v = reinterpret_cast<const float4*>(acc)[i];
+    *reinterpret_cast<uint2*>(dq + b * sb + a * sa + s * ss + d) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+}  // namespace lb
+
+namespace {
+template <int D>
+cudaError_t launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                       const lb::AttnBwdParams& p, cudaStream_t s) {
+  using Cfg = lb::AttnBwdCfg<D>;
+  auto kern = lb::attn_bwd_kernel<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.S + 127) / 128, p.A, p.B);
+  kern<<<grid, lb::ATT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+  return cudaGetLastError();
+}
+}  // namespace
+
+extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o,
+                           const float* lse, void* dq, void* dk, void* dv, float* delta, float* dq_accum, int B, int A,
+                           int S, int D, const long* q_strides, const long* k_strides, const long* v_strides,
+                           const long* do_strides, int causal, float scale, cudaStream_t s) {
+  if (D != 64 && D != 128) return -1;
+  for (int i = 0; i < 3; ++i)
+    if ((q_strides[i] % 8) || (k_strides[i] % 8) || (v_strides[i] % 8) || (do_strides[i] % 8)) return -3;
+  CUtensorMap tq, tk, tv, tdo;
+  if (!make_qkv_tmap(&tq, q, B, A, S, D, q_strides)) return -2;
+  if (!make_qkv_tmap(&tk, k, B, A, S, D, k_strides)) return -2;
+  if (!make_qkv_tmap(&tv, v, B, A, S, D, v_strides)) return -2;
+  if (!make_qkv_tmap(&tdo, dout, B, A, S, D, do_strides)) return -2;
+  const long rows = (long)B * A * S;
+  lb::attn_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(
+      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta, B, A, S, D, do_strides[0], do_strides[1], do_strides[2]);
+  lb::AttnBwdParams p;
+  p.lse = lse;
+  p.delta = delta;
+  p.dq_accum = dq_accum;
+  p.dk = (__nv_bfloat16*)dk;
+  p.dv = (__nv_bfloat16*)dv;
+  // dq / dk / dv are views of one packed [B, S, A, 3, D] tensor: same strides as the packed q view
+  p.g_strides[0] = (long)S * A * 3 * D;
+  p.g_strides[1] = 3L * D;
+  p.g_strides[2] = (long)A * 3 * D;
+  p.B = B;
+  p.A = A;
+  p.S = S;
+  p.causal = causal;
+  p.scale = scale;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  cudaError_t e = (D == 64) ? launch_bwd<64>(tq, tk, tv, tdo, p, s) : launch_bwd<128>(tq, tk, tv, tdo, p, s);
+  if (e != cudaSuccess) return (int)e;
+  const long nvec = rows * D / 4;
+  int blocks = (int)((nvec + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  lb::attn_dq_convert_kernel<<<blocks, 256, 0, s>>>(dq_accum, (__nv_bfloat16*)dq, B, A, S, D, p.g_strides[0],
+                                                    p.g_strides[1], p.g_strides[2]);
+  return (int)cudaGetLastError();
+}

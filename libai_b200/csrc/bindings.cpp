@@ -1,0 +1,354 @@
+// torch.ops.libai_b200.* : thin argument-checking wrappers around the extern "C" kernel launchers.
+// Registered with TORCH_LIBRARY so the in-tree `_C.so` is loaded by torch.ops.load_library (no
+// python ABI dependency).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+#include <torch/torch.h>
+
+#include <tuple>
+
+extern "C" {
+int lb_gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo, int layout,
+                 int epi, const void* bias, int act, void* pre_out, int force_bn, int force_splits, cudaStream_t s);
+int lb_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows, int H,
+                float eps, int rms, int dtype, int wdtype, cudaStream_t s);
+int lb_norm_bwd_workspace_rows(int rows);
+int lb_norm_bwd(const void* gy, const void* x, const void* gamma, const float* mean, const float* rstd, void* gx,
+                float* dgamma, float* dbeta, float* workspace, int rows, int H, int rms, int dtype, int wdtype,
+                cudaStream_t s);
+int lb_bias_act_fwd(const void* x, const void* bias, void* y, long rows, int N, int act, cudaStream_t s);
+int lb_bias_act_bwd(const void* gy, const void* x, const void* bias, void* gx, long rows, int N, int act,
+                    cudaStream_t s);
+int lb_bias_residual(const void* x, const void* bias, const void* res, void* y, long rows, int N, cudaStream_t s);
+int lb_swiglu_fwd(const void* gate, const void* up, void* y, long n, cudaStream_t s);
+int lb_swiglu_bwd(const void* gy, const void* gate, const void* up, void* dgate, void* dup, long n, cudaStream_t s);
+int lb_rope(const void* x, const float* cosv, const float* sinv, void* y, long rows, int S, int D, int backward,
+            cudaStream_t s);
+int lb_colsum(const void* x, float* out, int M, int N, cudaStream_t s);
+int lb_ce_stats(const void* logits, const int64_t* labels, float* mx, float* se, float* tgt, int T, int V,
+                long vocab_start, int dtype, cudaStream_t s);
+int lb_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* gloss, void* dlogits, int T,
+              int V, long vocab_start, int dtype, cudaStream_t s);
+int lb_adamw(float* master, const float* grad, float* m, float* v, void* lp_out, const float* scale, long n, float lr,
+             float b1, float b2, float eps, float wd, float bc1, float bc2, int decoupled, cudaStream_t s);
+int lb_sqnorm(const float* x, float* out, long n, cudaStream_t s);
+int lb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int A, int S, int D,
+                const long* q_strides, const long* k_strides, const long* v_strides, int causal, float scale,
+                cudaStream_t s);
+int lb_attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o, const float* lse,
+                void* dq, void* dk, void* dv, float* delta, float* dq_accum, int B, int A, int S, int D,
+                const long* q_strides, const long* k_strides, const long* v_strides, const long* do_strides, int causal,
+                float scale, cudaStream_t s);
+}
+
+namespace {
+
+using at::Tensor;
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+void check(int code, const char* what) {
+  TORCH_CHECK(code == 0, "libai_b200 kernel '", what, "' failed with code ", code,
+              code > 0 ? std::string(" (") + cudaGetErrorString(static_cast<cudaError_t>(code)) + ")" : std::string());
+}
+
+int dtype_code(const Tensor& t) {
+  if (t.scalar_type() == at::kBFloat16) return 0;
+  if (t.scalar_type() == at::kFloat) return 1;
+  TORCH_CHECK(false, "libai_b200: unsupported dtype ", t.scalar_type());
+}
+
+// ---- GEMM -----------------------------------------------------------------------------------------
+// layout 0: a[M,K] b[N,K]; 1: a[M,K] b[K,N]; 2: a[K,M] b[K,N].  Returns out (allocated when not given).
+Tensor gemm(const Tensor& a, const Tensor& b, int64_t layout, const c10::optional<Tensor>& bias,
+            const c10::optional<Tensor>& out_opt, bool accumulate, at::ScalarType out_dtype) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2, "gemm: 2-D CUDA tensors expected");
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm: bf16 operands expected");
+  TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1, "gemm: operands must be row-major");
+  c10::cuda::CUDAGuard guard(a.device());
+  int64_t M, N, K;
+  if (layout == 0) { M = a.size(0); K = a.size(1); N = b.size(0); TORCH_CHECK(b.size(1) == K, "gemm NT: K mismatch"); }
+  else if (layout == 1) { M = a.size(0); K = a.size(1); N = b.size(1); TORCH_CHECK(b.size(0) == K, "gemm NN: K mismatch"); }
+  else { K = a.size(0); M = a.size(1); N = b.size(1); TORCH_CHECK(b.size(0) == K, "gemm TN: K mismatch"); }
+  Tensor out;
+  int epi;
+  if (out_opt.has_value()) {
+    out = out_opt.value();
+    TORCH_CHECK(out.dim() == 2 && out.size(0) == M && out.size(1) == N && out.stride(1) == 1, "gemm: bad out shape");
+  } else {
+    auto opts = a.options().dtype(out_dtype);
+    out = (accumulate || (layout == 2 && out_dtype == at::kFloat)) ? at::zeros({M, N}, opts) : at::empty({M, N}, opts);
+  }
+  if (out.scalar_type() == at::kBFloat16) {
+    TORCH_CHECK(!accumulate, "gemm: accumulate needs an fp32 output");
+    epi = 0;
+  } else {
+    TORCH_CHECK(out.scalar_type() == at::kFloat, "gemm: out must be bf16 or fp32");
+    epi = (accumulate || layout == 2) ? 2 : 1;
+  }
+  const void* bias_ptr = nullptr;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(epi == 0 && bias->scalar_type() == at::kBFloat16 && bias->numel() == N, "gemm: bias must be bf16 [N]");
+    bias_ptr = bias->data_ptr();
+  }
+  check(lb_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, (int)a.stride(0),
+                     (int)b.stride(0), (int)out.stride(0), (int)layout, epi, bias_ptr, 0, nullptr, 0, 0, cur_stream()),
+        "gemm");
+  return out;
+}
+
+// y = act(x @ w^T + bias); optionally also returns the pre-activation (for backward)
+std::tuple<Tensor, Tensor> linear_fwd(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& bias, int64_t act,
+                                      bool need_pre) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1), "linear_fwd: shape mismatch");
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16, "linear_fwd: bf16 expected");
+  TORCH_CHECK(x.stride(1) == 1 && w.stride(1) == 1, "linear_fwd: row-major operands expected");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t M = x.size(0), K = x.size(1), N = w.size(0);
+  Tensor y = at::empty({M, N}, x.options());
+  Tensor pre;
+  if (need_pre && act != 0) pre = at::empty({M, N}, x.options());
+  const void* bias_ptr = nullptr;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->scalar_type() == at::kBFloat16 && bias->numel() == N, "linear_fwd: bias must be bf16 [N]");
+    bias_ptr = bias->data_ptr();
+  }
+  check(lb_gemm_bf16(x.data_ptr(), w.data_ptr(), y.data_ptr(), (int)M, (int)N, (int)K, (int)x.stride(0),
+                     (int)w.stride(0), (int)N, 0, 0, bias_ptr, (int)act, pre.defined() ? pre.data_ptr() : nullptr, 0, 0,
+                     cur_stream()),
+        "linear_fwd");
+  return std::make_tuple(y, pre.defined() ? pre : at::empty({0}, x.options()));
+}
+
+// raw entry used by tests / autotuning: explicit tile-N and split-K
+Tensor gemm_tuned(const Tensor& a, const Tensor& b, int64_t layout, int64_t bn, int64_t splits, bool fp32_out) {
+  c10::cuda::CUDAGuard guard(a.device());
+  int64_t M, N, K;
+  if (layout == 0) { M = a.size(0); K = a.size(1); N = b.size(0); }
+  else if (layout == 1) { M = a.size(0); K = a.size(1); N = b.size(1); }
+  else { K = a.size(0); M = a.size(1); N = b.size(1); }
+  const bool atomic = splits != 1;
+  Tensor out = atomic ? at::zeros({M, N}, a.options().dtype(at::kFloat))
+                      : at::empty({M, N}, a.options().dtype(fp32_out ? at::kFloat : at::kBFloat16));
+  const int epi = atomic ? 2 : (fp32_out ? 1 : 0);
+  check(lb_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, (int)a.stride(0),
+                     (int)b.stride(0), (int)N, (int)layout, epi, nullptr, 0, nullptr, (int)bn, (int)splits,
+                     cur_stream()),
+        "gemm_tuned");
+  return out;
+}
+
+// gx = gy * act'(pre)
+Tensor act_bwd(const Tensor& gy, const Tensor& pre, int64_t act) {
+  c10::cuda::CUDAGuard guard(gy.device());
+  Tensor gx = at::empty_like(gy);
+  check(lb_bias_act_bwd(gy.data_ptr(), pre.data_ptr(), nullptr, gx.data_ptr(), gy.size(0), (int)gy.size(1), (int)act,
+                        cur_stream()),
+        "act_bwd");
+  return gx;
+}
+
+Tensor colsum(const Tensor& x) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && x.scalar_type() == at::kBFloat16, "colsum: contiguous bf16 [M,N]");
+  Tensor out = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
+  check(lb_colsum(x.data_ptr(), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1), cur_stream()), "colsum");
+  return out.to(at::kBFloat16);
+}
+
+// ---- norms ----------------------------------------------------------------------------------------
+std::tuple<Tensor, Tensor, Tensor> norm_fwd(const Tensor& x, const Tensor& gamma, const c10::optional<Tensor>& beta,
+                                            double eps, bool rms) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 2 && x.is_contiguous(), "norm_fwd: contiguous [rows, H]");
+  const int rows = (int)x.size(0), H = (int)x.size(1);
+  Tensor y = at::empty_like(x);
+  Tensor mean = rms ? at::empty({0}, x.options().dtype(at::kFloat)) : at::empty({rows}, x.options().dtype(at::kFloat));
+  Tensor rstd = at::empty({rows}, x.options().dtype(at::kFloat));
+  const void* b = (beta.has_value() && beta->defined()) ? beta->data_ptr() : nullptr;
+  check(lb_norm_fwd(x.data_ptr(), gamma.data_ptr(), b, y.data_ptr(), rms ? nullptr : mean.data_ptr<float>(),
+                    rstd.data_ptr<float>(), rows, H, (float)eps, rms ? 1 : 0, dtype_code(x), dtype_code(gamma),
+                    cur_stream()),
+        "norm_fwd");
+  return std::make_tuple(y, mean, rstd);
+}
+
+std::tuple<Tensor, Tensor, Tensor> norm_bwd(const Tensor& gy, const Tensor& x, const Tensor& gamma, const Tensor& mean,
+                                            const Tensor& rstd, bool rms, bool has_bias) {
+  c10::cuda::CUDAGuard guard(x.device());
+  const int rows = (int)x.size(0), H = (int)x.size(1);
+  Tensor gx = at::empty_like(x);
+  auto fopt = x.options().dtype(at::kFloat);
+  Tensor dgamma = at::empty({H}, fopt);
+  Tensor dbeta = has_bias ? at::empty({H}, fopt) : at::empty({0}, fopt);
+  const int wrows = lb_norm_bwd_workspace_rows(rows);
+  Tensor ws = at::empty({2 * (int64_t)wrows * H}, fopt);
+  check(lb_norm_bwd(gy.data_ptr(), x.data_ptr(), gamma.data_ptr(), rms ? nullptr : mean.data_ptr<float>(),
+                    rstd.data_ptr<float>(), gx.data_ptr(), dgamma.data_ptr<float>(),
+                    has_bias ? dbeta.data_ptr<float>() : nullptr, ws.data_ptr<float>(), rows, H, rms ? 1 : 0,
+                    dtype_code(x), dtype_code(gamma), cur_stream()),
+        "norm_bwd");
+  return std::make_tuple(gx, dgamma, dbeta);
+}
+
+// ---- elementwise ------------------------------------------------------------------------------------
+Tensor bias_act_fwd(const Tensor& x, const c10::optional<Tensor>& bias, int64_t act) {
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = at::empty_like(x);
+  const void* b = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
+  check(lb_bias_act_fwd(x.data_ptr(), b, y.data_ptr(), x.size(0), (int)x.size(1), (int)act, cur_stream()), "bias_act_fwd");
+  return y;
+}
+Tensor bias_act_bwd(const Tensor& gy, const Tensor& x, const c10::optional<Tensor>& bias, int64_t act) {
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor gx = at::empty_like(x);
+  const void* b = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
+  check(lb_bias_act_bwd(gy.data_ptr(), x.data_ptr(), b, gx.data_ptr(), x.size(0), (int)x.size(1), (int)act, cur_stream()),
+        "bias_act_bwd");
+  return gx;
+}
+Tensor bias_residual_fwd(const Tensor& x, const c10::optional<Tensor>& bias, const c10::optional<Tensor>& res) {
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = at::empty_like(x);
+  const void* b = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
+  const void* r = (res.has_value() && res->defined()) ? res->data_ptr() : nullptr;
+  check(lb_bias_residual(x.data_ptr(), b, r, y.data_ptr(), x.size(0), (int)x.size(1), cur_stream()), "bias_residual");
+  return y;
+}
+Tensor swiglu_fwd(const Tensor& gate, const Tensor& up) {
+  c10::cuda::CUDAGuard guard(gate.device());
+  Tensor y = at::empty_like(gate);
+  check(lb_swiglu_fwd(gate.data_ptr(), up.data_ptr(), y.data_ptr(), gate.numel(), cur_stream()), "swiglu_fwd");
+  return y;
+}
+std::tuple<Tensor, Tensor> swiglu_bwd(const Tensor& gy, const Tensor& gate, const Tensor& up) {
+  c10::cuda::CUDAGuard guard(gate.device());
+  Tensor dg = at::empty_like(gate), du = at::empty_like(up);
+  check(lb_swiglu_bwd(gy.data_ptr(), gate.data_ptr(), up.data_ptr(), dg.data_ptr(), du.data_ptr(), gate.numel(),
+                      cur_stream()),
+        "swiglu_bwd");
+  return std::make_tuple(dg, du);
+}
+Tensor rope(const Tensor& x, const Tensor& cosv, const Tensor& sinv, bool backward) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 4 && x.is_contiguous() && x.scalar_type() == at::kBFloat16, "rope: contiguous bf16 [b,a,s,d]");
+  const int S = (int)x.size(2), D = (int)x.size(3);
+  TORCH_CHECK(cosv.is_contiguous() && sinv.is_contiguous() && cosv.size(0) >= S && cosv.size(1) == D, "rope: cos/sin [S,D]");
+  Tensor y = at::empty_like(x);
+  check(lb_rope(x.data_ptr(), cosv.data_ptr<float>(), sinv.data_ptr<float>(), y.data_ptr(), x.numel() / D, S, D,
+                backward ? 1 : 0, cur_stream()),
+        "rope");
+  return y;
+}
+
+// ---- cross entropy ------------------------------------------------------------------------------------
+std::tuple<Tensor, Tensor, Tensor> ce_stats(const Tensor& logits, const Tensor& labels, int64_t vocab_start) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  TORCH_CHECK(logits.dim() == 2 && logits.is_contiguous() && labels.scalar_type() == at::kLong, "ce_stats: bad args");
+  const int T = (int)logits.size(0), V = (int)logits.size(1);
+  auto fopt = logits.options().dtype(at::kFloat);
+  Tensor mx = at::empty({T}, fopt), se = at::empty({T}, fopt), tgt = at::empty({T}, fopt);
+  check(lb_ce_stats(logits.data_ptr(), labels.data_ptr<int64_t>(), mx.data_ptr<float>(), se.data_ptr<float>(),
+                    tgt.data_ptr<float>(), T, V, (long)vocab_start, dtype_code(logits), cur_stream()),
+        "ce_stats");
+  return std::make_tuple(mx, se, tgt);
+}
+Tensor ce_bwd(const Tensor& logits, const Tensor& labels, const Tensor& lse, const Tensor& gloss, int64_t vocab_start) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int T = (int)logits.size(0), V = (int)logits.size(1);
+  // in place: the saved logits buffer becomes dlogits (no second [T, V] allocation)
+  Tensor d = logits;
+  check(lb_ce_bwd(logits.data_ptr(), labels.data_ptr<int64_t>(), lse.data_ptr<float>(), gloss.data_ptr<float>(),
+                  d.data_ptr(), T, V, (long)vocab_start, dtype_code(logits), cur_stream()),
+        "ce_bwd");
+  return d;
+}
+
+// ---- optimizer ------------------------------------------------------------------------------------------
+void fused_adamw(Tensor master, const Tensor& grad, Tensor m, Tensor v, const c10::optional<Tensor>& lp_out,
+                 const Tensor& scale, double lr, double b1, double b2, double eps, double wd, double bc1, double bc2,
+                 bool decoupled) {
+  c10::cuda::CUDAGuard guard(master.device());
+  void* lp = (lp_out.has_value() && lp_out->defined()) ? lp_out->data_ptr() : nullptr;
+  check(lb_adamw(master.data_ptr<float>(), grad.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), lp,
+                 scale.data_ptr<float>(), master.numel(), (float)lr, (float)b1, (float)b2, (float)eps, (float)wd,
+                 (float)bc1, (float)bc2, decoupled ? 1 : 0, cur_stream()),
+        "fused_adamw");
+}
+Tensor sqnorm(const Tensor& x) {
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = at::zeros({1}, x.options().dtype(at::kFloat));
+  check(lb_sqnorm(x.data_ptr<float>(), out.data_ptr<float>(), x.numel(), cur_stream()), "sqnorm");
+  return out;
+}
+
+// ---- attention ----------------------------------------------------------------------------------------------
+// q, k, v: [B, A, S, D] views with arbitrary batch/head/seq strides (D contiguous). Output o is allocated as
+// [B, S, A, D] and returned as the [B, A, S, D] view, lse fp32 [B, A, S].
+std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, bool causal, double scale) {
+  c10::cuda::CUDAGuard guard(q.device());
+  TORCH_CHECK(q.dim() == 4 && q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1, "attn_fwd: [B,A,S,D], D contiguous");
+  const int B = (int)q.size(0), A = (int)q.size(1), S = (int)q.size(2), D = (int)q.size(3);
+  Tensor o = at::empty({B, S, A, D}, q.options());
+  Tensor lse = at::empty({B, A, S}, q.options().dtype(at::kFloat));
+  long qs[3] = {q.stride(0), q.stride(1), q.stride(2)};
+  long ks[3] = {k.stride(0), k.stride(1), k.stride(2)};
+  long vs[3] = {v.stride(0), v.stride(1), v.stride(2)};
+  check(lb_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), B, A, S, D, qs, ks,
+                    vs, causal ? 1 : 0, (float)scale, cur_stream()),
+        "attn_fwd");
+  return std::make_tuple(o.permute({0, 2, 1, 3}), lse);
+}
+
+std::tuple<Tensor, Tensor, Tensor> attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor& v,
+                                            const Tensor& o, const Tensor& lse, bool causal, double scale) {
+  c10::cuda::CUDAGuard guard(q.device());
+  const int B = (int)q.size(0), A = (int)q.size(1), S = (int)q.size(2), D = (int)q.size(3);
+  // gradients are produced in the packed [B, S, A, 3, D] layout so that the QKV dgrad/wgrad GEMMs read them directly
+  Tensor dqkv = at::empty({B, S, A, 3, D}, q.options());
+  Tensor dq = dqkv.select(3, 0).permute({0, 2, 1, 3});
+  Tensor dk = dqkv.select(3, 1).permute({0, 2, 1, 3});
+  Tensor dv = dqkv.select(3, 2).permute({0, 2, 1, 3});
+  Tensor delta = at::empty({B, A, S}, q.options().dtype(at::kFloat));
+  Tensor dq_acc = at::zeros({B, A, S, D}, q.options().dtype(at::kFloat));
+  TORCH_CHECK(o.stride(3) == 1, "attn_bwd: o must have contiguous D");
+  Tensor dout_c = dout;
+  if (dout.strides() != o.strides()) {  // bring dout into the [B, S, A, D]-backed layout of o
+    dout_c = at::empty_strided(o.sizes(), o.strides(), o.options());
+    dout_c.copy_(dout);
+  }
+  long qs[3] = {q.stride(0), q.stride(1), q.stride(2)};
+  long ks[3] = {k.stride(0), k.stride(1), k.stride(2)};
+  long vs[3] = {v.stride(0), v.stride(1), v.stride(2)};
+  long ds[3] = {dout_c.stride(0), dout_c.stride(1), dout_c.stride(2)};
+  check(lb_attn_bwd(dout_c.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(),
+                    dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr<float>(), dq_acc.data_ptr<float>(), B, A,
+                    S, D, qs, ks, vs, ds, causal ? 1 : 0, (float)scale, cur_stream()),
+        "attn_bwd");
+  return std::make_tuple(dq, dk, dv);
+}
+
+}  // namespace
+
+TORCH_LIBRARY(libai_b200, m) {
+  m.def("gemm(Tensor a, Tensor b, int layout, Tensor? bias, Tensor? out, bool accumulate, ScalarType out_dtype) -> Tensor", &gemm);
+  m.def("gemm_tuned(Tensor a, Tensor b, int layout, int bn, int splits, bool fp32_out) -> Tensor", &gemm_tuned);
+  m.def("linear_fwd(Tensor x, Tensor w, Tensor? bias, int act, bool need_pre) -> (Tensor, Tensor)", &linear_fwd);
+  m.def("act_bwd(Tensor gy, Tensor pre, int act) -> Tensor", &act_bwd);
+  m.def("colsum(Tensor x) -> Tensor", &colsum);
+  m.def("norm_fwd(Tensor x, Tensor gamma, Tensor? beta, float eps, bool rms) -> (Tensor, Tensor, Tensor)", &norm_fwd);
+  m.def("norm_bwd(Tensor gy, Tensor x, Tensor gamma, Tensor mean, Tensor rstd, bool rms, bool has_bias) -> (Tensor, Tensor, Tensor)", &norm_bwd);
+  m.def("bias_act_fwd(Tensor x, Tensor? bias, int act) -> Tensor", &bias_act_fwd);
+  m.def("bias_act_bwd(Tensor gy, Tensor x, Tensor? bias, int act) -> Tensor", &bias_act_bwd);
+  m.def("bias_residual_fwd(Tensor x, Tensor? bias, Tensor? res) -> Tensor", &bias_residual_fwd);
+  m.def("swiglu_fwd(Tensor gate, Tensor up) -> Tensor", &swiglu_fwd);
+  m.def("swiglu_bwd(Tensor gy, Tensor gate, Tensor up) -> (Tensor, Tensor)", &swiglu_bwd);
+  m.def("rope(Tensor x, Tensor cos, Tensor sin, bool backward) -> Tensor", &rope);
+  m.def("ce_stats(Tensor logits, Tensor labels, int vocab_start) -> (Tensor, Tensor, Tensor)", &ce_stats);
+  m.def("ce_bwd(Tensor(a!) logits, Tensor labels, Tensor lse, Tensor gloss, int vocab_start) -> Tensor(a!)", &ce_bwd);
+  m.def("fused_adamw(Tensor(a!) master, Tensor grad, Tensor(b!) m, Tensor(c!) v, Tensor? lp_out, Tensor scale, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, bool decoupled) -> ()", &fused_adamw);
+  m.def("sqnorm(Tensor x) -> Tensor", &sqnorm);
+  m.def("attn_fwd(Tensor q, Tensor k, Tensor v, bool causal, float scale) -> (Tensor, Tensor)", &attn_fwd);
+  m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor o, Tensor lse, bool causal, float scale) -> (Tensor, Tensor, Tensor)", &attn_bwd);
+}

@@ -1,0 +1,386 @@
+// Bandwidth-bound fused kernels for sm_100a: bias+activation (fwd/bwd), bias+residual, SwiGLU,
+// RoPE, column sums (bias gradients), vocab-parallel softmax cross entropy (stats + backward),
+// fused AdamW over flat buffers, squared-norm reduction.  All use 128-bit accesses and grid-stride
+// loops sized to the SM count.
+//
+// Reference call sites replaced: fused_bias_add_gelu (libai/layers/mlp.py:95), fused_bias_add_dropout
+// (mlp.py:104, attention.py:265; p = 0 path), silu(gate)*up (projects/Llama/llama.py:111-113),
+// apply_rotary_pos_emb (projects/Llama/llama.py:31-43), sparse_softmax_cross_entropy
+// (libai/layers/cross_entropy.py:44), flow.optim.AdamW multi-tensor update (configs/common/optim.py).
+#include "common.cuh"
+
+namespace lb {
+
+LB_DEVICE void ld8(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 q = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+LB_DEVICE void st8(__nv_bfloat16* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) =
+      make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+// y = act(x + bias)            (N % 8 == 0)
+__global__ void bias_act_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ bias,
+                                    __nv_bfloat16* __restrict__ y, size_t total_vec, int nvec_per_row, int act) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+    float v[8];
+    ld8(x + i * 8, v);
+    if (bias != nullptr) {
+      float b[8];
+      ld8(bias + (i % nvec_per_row) * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += b[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j], act);
+    st8(y + i * 8, v);
+  }
+}
+
+// gx = gy * act'(x + bias)
+__global__ void bias_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ x,
+                                    const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ gx,
+                                    size_t total_vec, int nvec_per_row, int act) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+    float v[8], g[8];
+    ld8(x + i * 8, v);
+    ld8(gy + i * 8, g);
+    if (bias != nullptr) {
+      float b[8];
+      ld8(bias + (i % nvec_per_row) * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += b[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= act_grad(v[j], act);
+    st8(gx + i * 8, g);
+  }
+}
+
+// y = x + bias + residual
+__global__ void bias_residual_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ bias,
+                                     const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y,
+                                     size_t total_vec, int nvec_per_row) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+    float v[8];
+    ld8(x + i * 8, v);
+    if (bias != nullptr) {
+      float b[8];
+      ld8(bias + (i % nvec_per_row) * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += b[j];
+    }
+    if (res != nullptr) {
+      float r[8];
+      ld8(res + i * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    st8(y + i * 8, v);
+  }
+}
+
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gate, const __nv_bfloat16* __restrict__ up,
+                                  __nv_bfloat16* __restrict__ y, size_t total_vec) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+    float g[8], u[8];
+    ld8(gate + i * 8, g);
+    ld8(up + i * 8, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = g[j] / (1.0f + __expf(-g[j])) * u[j];
+    st8(y + i * 8, g);
+  }
+}
+
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ gate,
+                                  const __nv_bfloat16* __restrict__ up, __nv_bfloat16* __restrict__ dgate,
+                                  __nv_bfloat16* __restrict__ dup, size_t total_vec) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+    float g[8], u[8], d[8], dg[8], du[8];
+    ld8(gate + i * 8, g);
+    ld8(up + i * 8, u);
+    ld8(gy + i * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = 1.0f / (1.0f + __expf(-g[j]));
+      du[j] = d[j] * g[j] * s;
+      dg[j] = d[j] * u[j] * s * (1.0f + g[j] * (1.0f - s));
+    }
+    st8(dgate + i * 8, dg);
+    st8(dup + i * 8, du);
+  }
+}
+
+// RoPE ("rotate_half" convention): x [B, A, S, D] contiguous, cos/sin fp32 [S, D]
+//   fwd: y = x*cos + rot(x)*sin, rot(x) = cat(-x2, x1);   bwd: gx = g*cos + rot^T(g*sin) = g*cos - rot(g*sin) ... (below)
+__global__ void rope_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cosv,
+                            const float* __restrict__ sinv, __nv_bfloat16* __restrict__ y, size_t rows, int S, int D,
+                            int backward) {
+  const int half = D / 2;
+  const size_t total = rows * half;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / half;
+    const int c = static_cast<int>(i % half);
+    const int s = static_cast<int>(row % S);
+    const float x1 = __bfloat162float(x[row * D + c]), x2 = __bfloat162float(x[row * D + c + half]);
+    const float c1 = cosv[s * D + c], c2 = cosv[s * D + c + half];
+    const float s1 = sinv[s * D + c], s2 = sinv[s * D + c + half];
+    float y1, y2;
+    if (!backward) {
+      y1 = x1 * c1 - x2 * s1;
+      y2 = x2 * c2 + x1 * s2;
+    } else {
+      y1 = x1 * c1 + x2 * s2;
+      y2 = x2 * c2 - x1 * s1;
+    }
+    y[row * D + c] = __float2bfloat16(y1);
+    y[row * D + c + half] = __float2bfloat16(y2);
+  }
+}
+
+// out[c] += sum_r x[r, c]   (out fp32, zero-initialised by the caller)
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int M, int N,
+                              int rows_per_block) {
+  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;  // pair of columns
+  if (c2 * 2 >= N) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float a0 = 0.f, a1 = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + static_cast<size_t>(r) * N + c2 * 2));
+    a0 += v.x;
+    a1 += v.y;
+  }
+  atomicAdd(out + c2 * 2, a0);
+  atomicAdd(out + c2 * 2 + 1, a1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// vocab-parallel cross entropy
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+LB_DEVICE float ld_logit(const T* p);
+template <>
+LB_DEVICE float ld_logit<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <>
+LB_DEVICE float ld_logit<float>(const float* p) { return *p; }
+
+// per row: local max, sum exp(x - max), target logit (0 if the label lives on another rank)
+template <typename T>
+__global__ void __launch_bounds__(256) ce_stats_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                       float* __restrict__ mx_out, float* __restrict__ se_out,
+                                                       float* __restrict__ tgt_out, int V, int64_t vocab_start) {
+  __shared__ float sm[8], ss[8];
+  const int row = blockIdx.x;
+  const T* lr = logits + static_cast<size_t>(row) * V;
+  float m = -INFINITY, s = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    const float x = ld_logit<T>(lr + c);
+    if (x > m) {
+      s = s * __expf(m - x) + 1.0f;
+      m = x;
+    } else {
+      s += __expf(x - m);
+    }
+  }
+  const float wm = warp_max(m);
+  s *= __expf(m - wm);
+  s = warp_sum(s);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (lane == 0) {
+    sm[warp] = wm;
+    ss[warp] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float m2 = lane < 8 ? sm[lane] : -INFINITY;
+    float s2 = lane < 8 ? ss[lane] : 0.f;
+    const float bm = warp_max(m2);
+    s2 = (m2 == -INFINITY) ? 0.f : s2 * __expf(m2 - bm);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      mx_out[row] = bm;
+      se_out[row] = s2;
+      const int64_t local = labels[row] - vocab_start;
+      tgt_out[row] = (local >= 0 && local < V) ? ld_logit<T>(lr + local) : 0.f;
+    }
+  }
+}
+
+// dlogits = (exp(x - lse) - onehot) * g[row]
+template <typename T>
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                     const float* __restrict__ lse, const float* __restrict__ gloss,
+                                                     T* __restrict__ dlogits, int V, int64_t vocab_start) {
+  const int row = blockIdx.x;
+  const T* lr = logits + static_cast<size_t>(row) * V;
+  T* dr = dlogits + static_cast<size_t>(row) * V;
+  const float l = lse[row], g = gloss[row];
+  const int64_t local = labels[row] - vocab_start;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    float p = __expf(ld_logit<T>(lr + c) - l);
+    if (c == local) p -= 1.0f;
+    dr[c] = static_cast<T>(p * g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused AdamW over flat fp32 buffers (+ optional low-precision parameter copy)
+// ------------------------------------------------------------------------------------------------
+__global__ void adamw_kernel(float* __restrict__ master, const float* __restrict__ grad, float* __restrict__ m,
+                             float* __restrict__ v, __nv_bfloat16* __restrict__ lp_out,
+                             const float* __restrict__ scale_ptr, size_t n, float lr, float b1, float b2, float eps,
+                             float wd, float bc1, float bc2, int decoupled) {
+  const float scale = scale_ptr != nullptr ? *scale_ptr : 1.0f;
+  const size_t nvec = n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float4 p4 = reinterpret_cast<float4*>(master)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(grad)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i];
+    float4 v4 = reinterpret_cast<float4*>(v)[i];
+    float pp[4] = {p4.x, p4.y, p4.z, p4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float g = gg[j] * scale;
+      if (!decoupled) g += wd * pp[j];
+      mm[j] = b1 * mm[j] + (1.0f - b1) * g;
+      vv[j] = b2 * vv[j] + (1.0f - b2) * g * g;
+      float upd = (mm[j] / bc1) / (sqrtf(vv[j] / bc2) + eps);
+      if (decoupled) upd += wd * pp[j];
+      pp[j] -= lr * upd;
+    }
+    reinterpret_cast<float4*>(master)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (lp_out != nullptr) {
+      reinterpret_cast<uint2*>(lp_out)[i] = make_uint2(pack_bf16(pp[0], pp[1]), pack_bf16(pp[2], pp[3]));
+    }
+  }
+}
+
+// out[0] += sum x^2
+__global__ void sqnorm_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  const size_t nvec = n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 q = reinterpret_cast<const float4*>(x)[i];
+    acc += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+  }
+  acc = warp_sum(acc);
+  if (threadIdx.x % 32 == 0) sm[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < blockDim.x / 32 ? sm[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+
+}  // namespace lb
+
+namespace {
+int ew_grid(size_t work, int block) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  size_t need = (work + block - 1) / block;
+  size_t cap = (size_t)sms * 8;
+  return (int)(need < cap ? (need == 0 ? 1 : need) : cap);
+}
+}  // namespace
+
+using bf16 = __nv_bfloat16;
+
+extern "C" int lb_bias_act_fwd(const void* x, const void* bias, void* y, long rows, int N, int act, cudaStream_t s) {
+  if (N % 8) return -1;
+  const size_t tv = (size_t)rows * N / 8;
+  if (tv == 0) return 0;
+  lb::bias_act_fwd_kernel<<<ew_grid(tv, 256), 256, 0, s>>>((const bf16*)x, (const bf16*)bias, (bf16*)y, tv, N / 8, act);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_bias_act_bwd(const void* gy, const void* x, const void* bias, void* gx, long rows, int N, int act,
+                               cudaStream_t s) {
+  if (N % 8) return -1;
+  const size_t tv = (size_t)rows * N / 8;
+  if (tv == 0) return 0;
+  lb::bias_act_bwd_kernel<<<ew_grid(tv, 256), 256, 0, s>>>((const bf16*)gy, (const bf16*)x, (const bf16*)bias,
+                                                           (bf16*)gx, tv, N / 8, act);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_bias_residual(const void* x, const void* bias, const void* res, void* y, long rows, int N,
+                                cudaStream_t s) {
+  if (N % 8) return -1;
+  const size_t tv = (size_t)rows * N / 8;
+  if (tv == 0) return 0;
+  lb::bias_residual_kernel<<<ew_grid(tv, 256), 256, 0, s>>>((const bf16*)x, (const bf16*)bias, (const bf16*)res,
+                                                            (bf16*)y, tv, N / 8);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_swiglu_fwd(const void* gate, const void* up, void* y, long n, cudaStream_t s) {
+  if (n % 8) return -1;
+  if (n == 0) return 0;
+  lb::swiglu_fwd_kernel<<<ew_grid(n / 8, 256), 256, 0, s>>>((const bf16*)gate, (const bf16*)up, (bf16*)y, n / 8);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_swiglu_bwd(const void* gy, const void* gate, const void* up, void* dgate, void* dup, long n,
+                             cudaStream_t s) {
+  if (n % 8) return -1;
+  if (n == 0) return 0;
+  lb::swiglu_bwd_kernel<<<ew_grid(n / 8, 256), 256, 0, s>>>((const bf16*)gy, (const bf16*)gate, (const bf16*)up,
+                                                            (bf16*)dgate, (bf16*)dup, n / 8);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_rope(const void* x, const float* cosv, const float* sinv, void* y, long rows, int S, int D,
+                       int backward, cudaStream_t s) {
+  if (rows == 0) return 0;
+  lb::rope_kernel<<<ew_grid((size_t)rows * D / 2, 256), 256, 0, s>>>((const bf16*)x, cosv, sinv, (bf16*)y,
+                                                                     (size_t)rows, S, D, backward);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_colsum(const void* x, float* out, int M, int N, cudaStream_t s) {
+  if (N % 2) return -1;
+  cudaMemsetAsync(out, 0, sizeof(float) * N, s);
+  if (M == 0) return 0;
+  const int rpb = 128;
+  dim3 grid((N / 2 + 127) / 128, (M + rpb - 1) / rpb);
+  lb::colsum_kernel<<<grid, 128, 0, s>>>((const bf16*)x, out, M, N, rpb);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_ce_stats(const void* logits, const int64_t* labels, float* mx, float* se, float* tgt, int T, int V,
+                           long vocab_start, int dtype, cudaStream_t s) {
+  if (T == 0) return 0;
+  if (dtype == 0)
+    lb::ce_stats_kernel<bf16><<<T, 256, 0, s>>>((const bf16*)logits, labels, mx, se, tgt, V, vocab_start);
+  else
+    lb::ce_stats_kernel<float><<<T, 256, 0, s>>>((const float*)logits, labels, mx, se, tgt, V, vocab_start);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* gloss, void* dlogits,
+                         int T, int V, long vocab_start, int dtype, cudaStream_t s) {
+  if (T == 0) return 0;
+  if (dtype == 0)
+    lb::ce_bwd_kernel<bf16><<<T, 256, 0, s>>>((const bf16*)logits, labels, lse, gloss, (bf16*)dlogits, V, vocab_start);
+  else
+    lb::ce_bwd_kernel<float><<<T, 256, 0, s>>>((const float*)logits, labels, lse, gloss, (float*)dlogits, V,
+                                               vocab_start);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_adamw(float* master, const float* grad, float* m, float* v, void* lp_out, const float* scale,
+                        long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, int decoupled,
+                        cudaStream_t s) {
+  if (n % 4) return -1;
+  if (n == 0) return 0;
+  lb::adamw_kernel<<<ew_grid(n / 4, 256), 256, 0, s>>>(master, grad, m, v, (bf16*)lp_out, scale, (size_t)n, lr, b1, b2,
+                                                       eps, wd, bc1, bc2, decoupled);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_sqnorm(const float* x, float* out, long n, cudaStream_t s) {
+  if (n % 4) return -1;
+  if (n == 0) return 0;
+  lb::sqnorm_kernel<<<ew_grid(n / 4, 256), 256, 0, s>>>(x, out, (size_t)n);
+  return (int)cudaGetLastError();
+}

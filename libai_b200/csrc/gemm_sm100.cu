@@ -1,0 +1,446 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> shared (128B swizzle) -> tcgen05.mma
+// (accumulators in TMEM, double buffered) -> tcgen05.ld epilogue with fused bias / activation.
+//
+//   D[M,N] = A · Bᵀ   with three operand layouts (all row-major tensors in global memory):
+//     NT: A[M,K], B[N,K]   (forward  : y  = x · Wᵀ)
+//     NN: A[M,K], B[K,N]   (dgrad    : dx = dy · W,   B is "MN-major")
+//     TN: A[K,M], B[K,N]   (wgrad    : dW = dyᵀ · x,  both "MN-major"; split-K + fp32 red.add)
+//
+// Replaces the cuBLAS matmuls behind libai/layers/linear.py:123-157 and the separate
+// fused_bias_add_gelu kernel (libai/layers/mlp.py:95) of the reference.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+// warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).  One CTA per SM, static
+// round-robin tile scheduler over (m_blk, n_blk, k_split).
+#include "common.cuh"
+
+#include <cstdio>
+#include <mutex>
+
+namespace lb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_THREADS = 128;
+
+enum Epi : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_ATOMIC_F32 = 2 };
+
+struct GemmParams {
+  int M, N, K;
+  int k_splits;        // number of K partitions (atomic epilogue only when > 1)
+  int k_per_split;     // in units of BLOCK_K blocks
+  const __nv_bfloat16* bias;  // [N] or nullptr
+  int act;                    // Act enum
+  void* out;                  // bf16 or fp32 [M, ldo]
+  __nv_bfloat16* pre_out;     // optional pre-activation copy (bf16)
+  int ldo;                    // leading dimension of out (elements)
+};
+
+template <int BLOCK_N>
+struct StageCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NUM_STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+  using Cfg = StageCfg<BLOCK_N>;
+  constexpr int NS = Cfg::NUM_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + NS;
+  uint64_t* tmem_full = empty_bar + NS;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp_idx = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+
+  const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int k_blocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_tiles = m_blocks * n_blocks * p.k_splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], NUM_EPI_THREADS);
+    mbar_init(&tmem_empty[1], NUM_EPI_THREADS);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ======================= TMA producer =======================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile % p.k_splits;
+        const int mn = tile / p.k_splits;
+        const int m_blk = mn / n_blocks, n_blk = mn % n_blocks;
+        const int kb0 = split * p.k_per_split;
+        const int kb1 = min(kb0 + p.k_per_split, k_blocks_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_M / 64; ++a)
+              tma_load_2d(sa + a * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_blk * BLOCK_M + a * 64, kb * BLOCK_K);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 64; ++a)
+              tma_load_2d(sb + a * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_blk * BLOCK_N + a * 64, kb * BLOCK_K);
+          }
+          if (++stage == NS) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ======================= MMA issuer =======================
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int split = tile % p.k_splits;
+      const int kb0 = split * p.k_per_split;
+      const int kb1 = min(kb0 + p.k_per_split, k_blocks_total);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: 8-row groups are 1024B apart (SBO), advance 32B per UMMA_K inside the swizzle row.
+            // MN-major: 64-element MN atoms are BLOCK_K*128B apart (LBO), 8-k-row groups 1024B apart (SBO),
+            //           advance 16 k-rows = 2048B per UMMA_K.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 0, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 0, 1024);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == NS) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ======================= epilogue (4 warps) =======================
+    const int quad = warp_idx % 4;  // TMEM lanes [32*quad, 32*quad+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mn = tile / p.k_splits;
+      const int m_blk = mn / n_blocks, n_blk = mn % n_blocks;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if constexpr (EPI == EPI_BF16) {
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                if (col0 + i < p.N) {
+                  const float2 b = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.bias + col0 + i));
+                  v[i] += b.x;
+                  v[i + 1] += b.y;
+                }
+              }
+            }
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+            if (p.pre_out != nullptr) {
+              __nv_bfloat16* prow = p.pre_out + static_cast<size_t>(row) * p.ldo + col0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (col0 + i < p.N) {
+                  uint4 q = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
+                                       pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
+                  *reinterpret_cast<uint4*>(prow + i) = q;
+                }
+              }
+            }
+            if (p.act != ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = act_fwd(v[i], p.act);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (col0 + i < p.N) {  // N % 8 == 0 is enforced on the host
+                uint4 q = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
+                                     pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
+                *reinterpret_cast<uint4*>(orow + i) = q;
+              }
+            }
+          } else if constexpr (EPI == EPI_F32) {
+            float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (col0 + i < p.N) *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+          } else {
+            float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (col0 + i < p.N) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(orow + i), "f"(v[i]), "f"(v[i + 1]),
+                             "f"(v[i + 2]), "f"(v[i + 3])
+                             : "memory");
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace lb
+
+// =================================================================================================
+// host side
+// =================================================================================================
+namespace lb_host {
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn fn = get_encode_tiled();
+  if (fn == nullptr) return false;
+  cuuint64_t gdim[5];
+  cuuint64_t gstride[5];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstride[i - 1] = strides_bytes[i];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstride, gbox, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace lb_host
+
+namespace {
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+// operand tensor map: K-major [rows, K] -> box {64, rows_box}; MN-major [K, cols] -> box {64, 64}
+bool operand_tmap(CUtensorMap* m, const void* ptr, bool mn_major, int rows_or_cols, int K, int ld, int block_mn) {
+  if (!mn_major) {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows_or_cols};
+    uint64_t strides[2] = {2, (uint64_t)ld * 2};
+    uint32_t box[2] = {(uint32_t)lb::BLOCK_K, (uint32_t)block_mn};
+    return lb_host::make_tmap_bf16(m, ptr, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  uint64_t dims[2] = {(uint64_t)rows_or_cols, (uint64_t)K};
+  uint64_t strides[2] = {2, (uint64_t)ld * 2};
+  uint32_t box[2] = {64u, (uint32_t)lb::BLOCK_K};
+  return lb_host::make_tmap_bf16(m, ptr, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int BN, bool AMN, bool BMN, int EPI>
+cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const lb::GemmParams& p, int grid,
+                       cudaStream_t stream) {
+  using Cfg = lb::StageCfg<BN>;
+  auto kern = lb::gemm_kernel<BN, AMN, BMN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, lb::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  return cudaGetLastError();
+}
+
+template <bool AMN, bool BMN, int EPI>
+cudaError_t launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const lb::GemmParams& p, int grid,
+                      cudaStream_t s) {
+  switch (bn) {
+    case 256:
+      return launch_cfg<256, AMN, BMN, EPI>(ta, tb, p, grid, s);
+    case 128:
+      return launch_cfg<128, AMN, BMN, EPI>(ta, tb, p, grid, s);
+    default:
+      return launch_cfg<64, AMN, BMN, EPI>(ta, tb, p, grid, s);
+  }
+}
+
+}  // namespace
+
+// layout: 0 = NT (A[M,K], B[N,K]); 1 = NN (A[M,K], B[K,N]); 2 = TN (A[K,M], B[K,N])
+// epi:    0 = bf16 store (+bias, act, optional pre-activation copy); 1 = fp32 store; 2 = fp32 atomic accumulate
+// Returns 0 on success, a negative code for unsupported arguments, or a cudaError_t (> 0).
+extern "C" int lb_gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo,
+                            int layout, int epi, const void* bias, int act, void* pre_out, int force_bn,
+                            int force_splits, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda % 8) || (ldb % 8) || (N % 8) || (ldo % 4)) return -1;
+  const bool a_mn = (layout == 2);
+  const bool b_mn = (layout != 0);
+  const int sms = num_sms();
+  const int m_blocks = (M + lb::BLOCK_M - 1) / lb::BLOCK_M;
+  // ---- tile-N heuristic: fewest waves, ties -> wider tile (less smem traffic per flop)
+  int bn = force_bn;
+  if (bn == 0) {
+    double best = 1e30;
+    const int cands[3] = {256, 128, 64};
+    for (int c : cands) {
+      if (c > 64 && N <= c / 2) continue;
+      const long tiles = (long)m_blocks * ((N + c - 1) / c);
+      const long waves = (tiles + sms - 1) / sms;
+      // cost ~ waves * per-tile time (proportional to c, with a small fixed overhead per tile)
+      const double cost = (double)waves * (c + 24.0);
+      if (cost < best - 1e-9) {
+        best = cost;
+        bn = c;
+      }
+    }
+  }
+  const int n_blocks = (N + bn - 1) / bn;
+  const int k_blocks = (K + lb::BLOCK_K - 1) / lb::BLOCK_K;
+  int splits = 1;
+  if (epi == 2) {
+    splits = force_splits;
+    if (splits <= 0) {
+      const long tiles = (long)m_blocks * n_blocks;
+      splits = (int)((sms + tiles - 1) / tiles);
+      if (tiles >= sms) splits = 1;
+      // keep at least 4 k-blocks per split so the pipeline fills
+      while (splits > 1 && k_blocks / splits < 4) --splits;
+    }
+    if (splits > k_blocks) splits = k_blocks;
+  }
+  lb::GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.k_splits = splits;
+  p.k_per_split = (k_blocks + splits - 1) / splits;
+  p.k_splits = (k_blocks + p.k_per_split - 1) / p.k_per_split;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.act = act;
+  p.out = out;
+  p.pre_out = reinterpret_cast<__nv_bfloat16*>(pre_out);
+  p.ldo = ldo;
+
+  CUtensorMap ta, tb;
+  if (!operand_tmap(&ta, a, a_mn, M, K, lda, lb::BLOCK_M)) return -2;
+  if (!operand_tmap(&tb, b, b_mn, N, K, ldb, bn)) return -2;
+  const long num_tiles = (long)m_blocks * n_blocks * p.k_splits;
+  const int grid = (int)(num_tiles < sms ? num_tiles : sms);
+
+  cudaError_t e;
+  if (layout == 0) {
+    if (epi == 0) e = launch_bn<false, false, lb::EPI_BF16>(bn, ta, tb, p, grid, stream);
+    else if (epi == 1) e = launch_bn<false, false, lb::EPI_F32>(bn, ta, tb, p, grid, stream);
+    else e = launch_bn<false, false, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, grid, stream);
+  } else if (layout == 1) {
+    if (epi == 0) e = launch_bn<false, true, lb::EPI_BF16>(bn, ta, tb, p, grid, stream);
+    else if (epi == 1) e = launch_bn<false, true, lb::EPI_F32>(bn, ta, tb, p, grid, stream);
+    else e = launch_bn<false, true, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, grid, stream);
+  } else {
+    if (epi == 0) e = launch_bn<true, true, lb::EPI_BF16>(bn, ta, tb, p, grid, stream);
+    else if (epi == 1) e = launch_bn<true, true, lb::EPI_F32>(bn, ta, tb, p, grid, stream);
+    else e = launch_bn<true, true, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, grid, stream);
+  }
+  return (int)e;
+}

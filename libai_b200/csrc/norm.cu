@@ -1,0 +1,347 @@
+// Fused LayerNorm / RMSNorm forward + backward for sm_100a (bandwidth-bound: one warp per row,
+// 128-bit vector accesses, statistics in fp32, row cached in registers between the passes).
+// Replaces flow._C.layer_norm_affine / rms_norm (reference libai/layers/layer_norm.py:78-131).
+//
+//   fwd : y = (x - mean) * rstd * gamma + beta          (rms: y = x * rstd * gamma, mean := 0)
+//   bwd : dx = rstd * (g·γ - mean_h(g·γ) - x̂ · mean_h(g·γ·x̂))   (rms: no mean_h(g·γ) term)
+//         dγ = Σ_rows g·x̂ ,  dβ = Σ_rows g        (two-stage: per-CTA partials, then column reduce)
+#include "common.cuh"
+
+namespace lb {
+
+constexpr int NORM_WARPS = 8;
+
+template <typename T>
+struct Vec8;
+template <>
+struct Vec8<__nv_bfloat16> {
+  static LB_DEVICE void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 q = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+  static LB_DEVICE void store(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+};
+template <>
+struct Vec8<float> {
+  static LB_DEVICE void load(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static LB_DEVICE void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+
+// H = VPL * 256 elements per row (each lane owns VPL vectors of 8, interleaved for coalescing)
+template <typename T, typename W, int VPL, bool RMS>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+norm_fwd_kernel(const T* __restrict__ x, const W* __restrict__ gamma, const W* __restrict__ beta, T* __restrict__ y,
+                float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, float eps) {
+  constexpr int H = VPL * 256;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int row = blockIdx.x * NORM_WARPS + warp; row < rows; row += gridDim.x * NORM_WARPS) {
+    const T* xr = x + static_cast<size_t>(row) * H;
+    float v[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      Vec8<T>::load(xr + (i * 32 + lane) * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+    float mean = 0.f;
+    if (!RMS) mean = warp_sum(s) * (1.0f / H);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / H) + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+    T* yr = y + static_cast<size_t>(row) * H;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float g[8], b[8], o[8];
+      Vec8<W>::load(gamma + (i * 32 + lane) * 8, g);
+      if (beta != nullptr) Vec8<W>::load(beta + (i * 32 + lane) * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = (v[i][j] - mean) * rstd * g[j];
+        if (beta != nullptr) o[j] += b[j];
+      }
+      Vec8<T>::store(yr + (i * 32 + lane) * 8, o);
+    }
+  }
+}
+
+template <typename T, typename W, int VPL, bool RMS>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+norm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, const W* __restrict__ gamma,
+                const float* __restrict__ mean_in, const float* __restrict__ rstd_in, T* __restrict__ gx,
+                float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, int rows) {
+  constexpr int H = VPL * 256;
+  __shared__ float red[NORM_WARPS][32 * 8 + 8];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  float dg[VPL][8], db[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+  float gam[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) Vec8<W>::load(gamma + (i * 32 + lane) * 8, gam[i]);
+
+  for (int row = blockIdx.x * NORM_WARPS + warp; row < rows; row += gridDim.x * NORM_WARPS) {
+    const float mean = RMS ? 0.f : mean_in[row];
+    const float rstd = rstd_in[row];
+    const T* xr = x + static_cast<size_t>(row) * H;
+    const T* gr = gy + static_cast<size_t>(row) * H;
+    float xh[VPL][8], gw[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float xv[8], gv[8];
+      Vec8<T>::load(xr + (i * 32 + lane) * 8, xv);
+      Vec8<T>::load(gr + (i * 32 + lane) * 8, gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[i][j] = (xv[j] - mean) * rstd;
+        gw[i][j] = gv[j] * gam[i][j];
+        s1 += gw[i][j];
+        s2 += gw[i][j] * xh[i][j];
+        dg[i][j] += gv[j] * xh[i][j];
+        db[i][j] += gv[j];
+      }
+    }
+    s1 = RMS ? 0.f : warp_sum(s1) * (1.0f / H);
+    s2 = warp_sum(s2) * (1.0f / H);
+    T* gxr = gx + static_cast<size_t>(row) * H;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (gw[i][j] - s1 - xh[i][j] * s2);
+      Vec8<T>::store(gxr + (i * 32 + lane) * 8, o);
+    }
+  }
+  // block-level reduction of the per-warp column partials, one vector slot at a time
+  for (int i = 0; i < VPL; ++i) {
+    for (int which = 0; which < (part_dbeta != nullptr ? 2 : 1); ++which) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = which == 0 ? dg[i][j] : db[i][j];
+      __syncthreads();
+      for (int c = threadIdx.x; c < 256; c += NORM_WARPS * 32) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < NORM_WARPS; ++w) acc += red[w][c];
+        float* dst = (which == 0 ? part_dgamma : part_dbeta) + static_cast<size_t>(blockIdx.x) * H + i * 256 + c;
+        *dst = acc;
+      }
+    }
+  }
+}
+
+// out[c] = sum_r part[r, c]
+__global__ void colreduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nrows, int H) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  float acc = 0.f;
+  for (int r = 0; r < nrows; ++r) acc += part[static_cast<size_t>(r) * H + c];
+  out[c] = acc;
+}
+
+// ---------------- generic (any H) fallbacks: one warp per row, strided scalar access ----------------
+template <typename T, typename W, bool RMS>
+__global__ void norm_fwd_generic(const T* __restrict__ x, const W* __restrict__ gamma, const W* __restrict__ beta,
+                                 T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                 int rows, int H, float eps) {
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row = blockIdx.x * (blockDim.x / 32) + warp;
+  if (row >= rows) return;
+  const T* xr = x + static_cast<size_t>(row) * H;
+  float s = 0.f;
+  for (int c = lane; c < H; c += 32) s += static_cast<float>(xr[c]);
+  const float mean = RMS ? 0.f : warp_sum(s) / H;
+  float sq = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    const float d = static_cast<float>(xr[c]) - mean;
+    sq += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / H + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  T* yr = y + static_cast<size_t>(row) * H;
+  for (int c = lane; c < H; c += 32) {
+    float o = (static_cast<float>(xr[c]) - mean) * rstd * static_cast<float>(gamma[c]);
+    if (beta != nullptr) o += static_cast<float>(beta[c]);
+    yr[c] = static_cast<T>(o);
+  }
+}
+
+template <typename T, typename W, bool RMS>
+__global__ void norm_bwd_generic(const T* __restrict__ gy, const T* __restrict__ x, const W* __restrict__ gamma,
+                                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                 T* __restrict__ gx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
+                                 int H) {
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row = blockIdx.x * (blockDim.x / 32) + warp;
+  if (row >= rows) return;
+  const float mean = RMS ? 0.f : mean_in[row], rstd = rstd_in[row];
+  const T* xr = x + static_cast<size_t>(row) * H;
+  const T* gr = gy + static_cast<size_t>(row) * H;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    const float xh = (static_cast<float>(xr[c]) - mean) * rstd;
+    const float g = static_cast<float>(gr[c]);
+    const float gw = g * static_cast<float>(gamma[c]);
+    s1 += gw;
+    s2 += gw * xh;
+    atomicAdd(&dgamma[c], g * xh);
+    if (dbeta != nullptr) atomicAdd(&dbeta[c], g);
+  }
+  s1 = RMS ? 0.f : warp_sum(s1) / H;
+  s2 = warp_sum(s2) / H;
+  T* gxr = gx + static_cast<size_t>(row) * H;
+  for (int c = lane; c < H; c += 32) {
+    const float xh = (static_cast<float>(xr[c]) - mean) * rstd;
+    const float gw = static_cast<float>(gr[c]) * static_cast<float>(gamma[c]);
+    gxr[c] = static_cast<T>(rstd * (gw - s1 - xh * s2));
+  }
+}
+
+}  // namespace lb
+
+namespace {
+int norm_grid(int rows) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int need = (rows + lb::NORM_WARPS - 1) / lb::NORM_WARPS;
+  const int cap = sms * 4;
+  return need < cap ? need : cap;
+}
+
+template <typename T, typename W, bool RMS>
+bool fwd_dispatch(int vpl, const T* x, const W* g, const W* b, T* y, float* mean, float* rstd, int rows, float eps,
+                  cudaStream_t s) {
+  const int grid = norm_grid(rows);
+#define LB_CASE(V)                                                                                             \
+  case V:                                                                                                      \
+    lb::norm_fwd_kernel<T, W, V, RMS><<<grid, lb::NORM_WARPS * 32, 0, s>>>(x, g, b, y, mean, rstd, rows, eps); \
+    return true;
+  switch (vpl) {
+    LB_CASE(1) LB_CASE(2) LB_CASE(3) LB_CASE(4) LB_CASE(5) LB_CASE(6) LB_CASE(8) LB_CASE(10) LB_CASE(12) LB_CASE(16)
+    LB_CASE(20) LB_CASE(32)
+    default:
+      return false;
+  }
+#undef LB_CASE
+}
+
+template <typename T, typename W, bool RMS>
+bool bwd_dispatch(int vpl, const T* gy, const T* x, const W* g, const float* mean, const float* rstd, T* gx, float* pdg,
+                  float* pdb, int rows, int grid, cudaStream_t s) {
+#define LB_CASE(V)                                                                                                   \
+  case V:                                                                                                            \
+    lb::norm_bwd_kernel<T, W, V, RMS><<<grid, lb::NORM_WARPS * 32, 0, s>>>(gy, x, g, mean, rstd, gx, pdg, pdb, rows); \
+    return true;
+  switch (vpl) {
+    LB_CASE(1) LB_CASE(2) LB_CASE(3) LB_CASE(4) LB_CASE(5) LB_CASE(6) LB_CASE(8) LB_CASE(10) LB_CASE(12) LB_CASE(16)
+    default:
+      return false;
+  }
+#undef LB_CASE
+}
+}  // namespace
+
+// dtype codes: 0 = bf16 activations, 1 = fp32 activations; wdtype: 0 = bf16 params, 1 = fp32 params
+extern "C" int lb_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                           int rows, int H, float eps, int rms, int dtype, int wdtype, cudaStream_t s) {
+  if (rows == 0) return 0;
+  const bool fast = (H % 256 == 0);
+  bool done = false;
+#define LB_GO(T, W)                                                                                                   \
+  {                                                                                                                   \
+    if (fast) {                                                                                                       \
+      done = rms ? fwd_dispatch<T, W, true>(H / 256, (const T*)x, (const W*)gamma, (const W*)beta, (T*)y, mean, rstd, \
+                                            rows, eps, s)                                                             \
+                 : fwd_dispatch<T, W, false>(H / 256, (const T*)x, (const W*)gamma, (const W*)beta, (T*)y, mean,      \
+                                             rstd, rows, eps, s);                                                     \
+    }                                                                                                                 \
+    if (!done) {                                                                                                      \
+      const int wpb = 8;                                                                                              \
+      const int grid = (rows + wpb - 1) / wpb;                                                                        \
+      if (rms)                                                                                                        \
+        lb::norm_fwd_generic<T, W, true><<<grid, wpb * 32, 0, s>>>((const T*)x, (const W*)gamma, (const W*)beta,      \
+                                                                   (T*)y, mean, rstd, rows, H, eps);                  \
+      else                                                                                                            \
+        lb::norm_fwd_generic<T, W, false><<<grid, wpb * 32, 0, s>>>((const T*)x, (const W*)gamma, (const W*)beta,     \
+                                                                    (T*)y, mean, rstd, rows, H, eps);                 \
+    }                                                                                                                 \
+  }
+  if (dtype == 0 && wdtype == 0) LB_GO(__nv_bfloat16, __nv_bfloat16)
+  else if (dtype == 0 && wdtype == 1) LB_GO(__nv_bfloat16, float)
+  else if (dtype == 1 && wdtype == 1) LB_GO(float, float)
+  else return -1;
+#undef LB_GO
+  return (int)cudaGetLastError();
+}
+
+// workspace: float[2 * grid_cap * H] where grid_cap = lb_norm_bwd_workspace_rows(); dgamma/dbeta fp32 [H]
+extern "C" int lb_norm_bwd_workspace_rows(int rows) { return norm_grid(rows); }
+
+extern "C" int lb_norm_bwd(const void* gy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                           void* gx, float* dgamma, float* dbeta, float* workspace, int rows, int H, int rms, int dtype,
+                           int wdtype, cudaStream_t s) {
+  if (rows == 0) return 0;
+  const bool fast = (H % 256 == 0) && (H / 256 <= 16);
+  const int grid = norm_grid(rows);
+  bool done = false;
+  float* pdg = workspace;
+  float* pdb = dbeta != nullptr ? workspace + static_cast<size_t>(grid) * H : nullptr;
+#define LB_GO(T, W)                                                                                                  \
+  {                                                                                                                  \
+    if (fast) {                                                                                                      \
+      done = rms ? bwd_dispatch<T, W, true>(H / 256, (const T*)gy, (const T*)x, (const W*)gamma, mean, rstd, (T*)gx, \
+                                            pdg, pdb, rows, grid, s)                                                 \
+                 : bwd_dispatch<T, W, false>(H / 256, (const T*)gy, (const T*)x, (const W*)gamma, mean, rstd,        \
+                                             (T*)gx, pdg, pdb, rows, grid, s);                                       \
+      if (done) {                                                                                                    \
+        lb::colreduce_kernel<<<(H + 255) / 256, 256, 0, s>>>(pdg, dgamma, grid, H);                                  \
+        if (dbeta != nullptr) lb::colreduce_kernel<<<(H + 255) / 256, 256, 0, s>>>(pdb, dbeta, grid, H);             \
+      }                                                                                                              \
+    }                                                                                                                \
+    if (!done) {                                                                                                     \
+      cudaMemsetAsync(dgamma, 0, sizeof(float) * H, s);                                                              \
+      if (dbeta != nullptr) cudaMemsetAsync(dbeta, 0, sizeof(float) * H, s);                                         \
+      const int wpb = 8;                                                                                             \
+      const int g2 = (rows + wpb - 1) / wpb;                                                                         \
+      if (rms)                                                                                                       \
+        lb::norm_bwd_generic<T, W, true><<<g2, wpb * 32, 0, s>>>((const T*)gy, (const T*)x, (const W*)gamma, mean,   \
+                                                                 rstd, (T*)gx, dgamma, dbeta, rows, H);              \
+      else                                                                                                           \
+        lb::norm_bwd_generic<T, W, false><<<g2, wpb * 32, 0, s>>>((const T*)gy, (const T*)x, (const W*)gamma, mean,  \
+                                                                  rstd, (T*)gx, dgamma, dbeta, rows, H);             \
+    }                                                                                                                \
+  }
+  if (dtype == 0 && wdtype == 0) LB_GO(__nv_bfloat16, __nv_bfloat16)
+  else if (dtype == 0 && wdtype == 1) LB_GO(__nv_bfloat16, float)
+  else if (dtype == 1 && wdtype == 1) LB_GO(float, float)
+  else return -1;
+#undef LB_GO
+  return (int)cudaGetLastError();
+}

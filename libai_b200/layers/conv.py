@@ -41,6 +41,8 @@ class Conv1D(nn.Module):
             if bias
             else None
         )
+        if parallel == "row" and self.bias is not None:
+            self.bias.sequence_parallel = dutil.get_dist_util().sequence_parallel
 
     def forward(self, x):
         sp = dutil.get_dist_util().sequence_parallel

@@ -57,6 +57,9 @@ class Linear1D(nn.Module):
             if bias
             else None
         )
+        if parallel == "row" and self.bias is not None:
+            # added after the reduce-scatter, i.e. on token shards: its gradient is partial per TP rank
+            self.bias.sequence_parallel = dutil.get_dist_util().sequence_parallel
 
     def forward(self, x, act=None):
         """``act`` (optional activation name) is fused into the GEMM epilogue when the bias is

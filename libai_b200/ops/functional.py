@@ -283,7 +283,7 @@ class _FlashAttnFn(torch.autograd.Function):
     def backward(ctx, go):
         ext = load_ext()
         q, k, v, o, lse = ctx.saved_tensors
-        dq, dk, dv = ext.attn_bwd(go.contiguous(), q, k, v, o, lse, ctx.causal, ctx.scale)
+        dq, dk, dv = ext.attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale)
         count_launch(3)
         return dq, dk, dv, None, None
 

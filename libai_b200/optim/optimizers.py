@@ -181,27 +181,36 @@ class FlatOptimizer(torch.optim.Optimizer):
         topo = dutil.get_dist_util()
         dev = None
         total = None
+        def _acc(seg):
+            if math.isinf(norm_type):
+                return seg.abs().max() if seg.numel() else torch.zeros((), device=seg.device)
+            return seg.pow(2).sum() if norm_type == 2.0 else seg.abs().pow(norm_type).sum()
+
         for fg in self._groups:
             if fg is None:
                 continue
             dev = fg.device
-            # parameters replicated over TP are counted on tp_rank 0 only
-            if topo.tensor_parallel_size > 1:
-                acc = torch.zeros((), dtype=torch.float32, device=dev)
-                for p, off in zip(fg.params, fg.offsets):
+            # every logical element once: skip TP-replicated parameters on tp_rank != 0 and the
+            # last-stage copy of tied weights (their gradients are identical duplicates)
+            skip = []
+            for p, off in zip(fg.params, fg.offsets):
+                dup_tp = topo.tensor_parallel_size > 1 and getattr(p, "tp_dim", None) is None and topo.tp_rank != 0
+                dup_tied = getattr(p, "shared_from", None) is not None
+                if dup_tp or dup_tied:
                     lo, hi = max(off, fg.lo), min(off + p.numel(), fg.hi)
-                    if lo >= hi:
-                        continue
-                    dup = getattr(p, "tp_dim", None) is None
-                    if dup and topo.tp_rank != 0:
-                        continue
-                    seg = fg.grad_flat[lo:hi]
-                    acc = acc + (seg.abs().max() if math.isinf(norm_type) else seg.float().abs().pow(norm_type).sum())
+                    if lo < hi:
+                        skip.append((lo, hi))
+            if math.isinf(norm_type) and skip:
+                acc = torch.zeros((), dtype=torch.float32, device=dev)
+                cur = fg.lo
+                for lo, hi in skip + [(fg.hi, fg.hi)]:
+                    if cur < lo:
+                        acc = torch.maximum(acc, _acc(fg.grad_flat[cur:lo]))
+                    cur = max(cur, hi)
             else:
-                seg = fg.grad_shard()
-                acc = seg.abs().max() if math.isinf(norm_type) else (
-                    seg.pow(2).sum() if norm_type == 2.0 else seg.abs().pow(norm_type).sum()
-                )
+                acc = _acc(fg.grad_shard())
+                for lo, hi in skip:
+                    acc = acc - _acc(fg.grad_flat[lo:hi])
             total = acc if total is None else (torch.maximum(total, acc) if math.isinf(norm_type) else total + acc)
         if total is None:
             total = torch.zeros((), dtype=torch.float32, device=dutil.get_device())

@@ -1,0 +1,242 @@
+"""Pipeline parallelism: non-interleaved 1F1B schedule in user space.
+
+The reference gets 1F1B from OneFlow's graph compiler (``set_stage`` per block,
+``set_gradient_accumulation_steps`` = number of micro-batches; libai/models/gpt_model.py:359-401,
+libai/models/utils/graph_base.py:63-64, docs customize_parallel.md:171-185).  Here the schedule is
+explicit:
+
+    stage s of p, M micro-batches:   warm-up  = min(p - s - 1, M) forwards
+                                      steady   = M - warm-up  × (forward, backward)
+                                      cooldown = warm-up backwards
+
+Activations / activation-gradients travel between neighbouring stages (same dp, tp coordinates) with
+NCCL ``isend/irecv`` (gloo on CPU).  Under sequence parallelism the payload is the token shard
+``[b·s/t, h]`` – t× smaller than the reference's replicated ``[b, s, h]`` hand-off.  Models implement
+``forward_stage(batch, hidden_in)`` (see models/utils/pipeline_model.py).  Tied embeddings: the
+first and last stage hold separate copies whose gradients are summed over ``embedding_group`` by
+the optimizer's ``sync_gradients``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.distributed as dist
+
+from libai_b200.layers.embedding import set_sp_shape
+from libai_b200.utils import distributed as dutil
+
+_DTYPES = [torch.float32, torch.bfloat16, torch.float16, torch.int64, torch.int32]
+TensorOrTuple = Union[torch.Tensor, Tuple[torch.Tensor, ...]]
+
+
+def _as_tuple(x) -> Tuple[torch.Tensor, ...]:
+    return tuple(x) if isinstance(x, (tuple, list)) else (x,)
+
+
+class _P2P:
+    """Shape-aware send/recv between pipeline neighbours (shape/dtype handshake on first use)."""
+
+    def __init__(self):
+        self.topo = dutil.get_dist_util()
+        self.group = self.topo.pp_group
+        self.prev = self.topo.pp_ranks[self.topo.pp_rank - 1] if not self.topo.is_first_stage else None
+        self.next = self.topo.pp_ranks[self.topo.pp_rank + 1] if not self.topo.is_last_stage else None
+        self.meta_fwd: Optional[List[Tuple[Tuple[int, ...], torch.dtype]]] = None  # what we receive from prev
+        self.sent_meta = False
+        self.dev = self.topo.device
+
+    # -- meta ------------------------------------------------------------------------------------
+    def _send_meta(self, tensors: Sequence[torch.Tensor]):
+        buf = torch.full((1 + 10 * len(tensors),), -1, dtype=torch.int64)
+        buf[0] = len(tensors)
+        for i, t in enumerate(tensors):
+            buf[1 + i * 10] = _DTYPES.index(t.dtype)
+            buf[2 + i * 10] = t.dim()
+            for d, n in enumerate(t.shape):
+                buf[3 + i * 10 + d] = n
+        head = torch.tensor([buf.numel()], dtype=torch.int64, device=self.dev)
+        dist.send(head, self.next, group=self.group)
+        dist.send(buf.to(self.dev), self.next, group=self.group)
+
+    def _recv_meta(self):
+        head = torch.empty(1, dtype=torch.int64, device=self.dev)
+        dist.recv(head, self.prev, group=self.group)
+        buf = torch.empty(int(head.item()), dtype=torch.int64, device=self.dev)
+        dist.recv(buf, self.prev, group=self.group)
+        buf = buf.cpu()
+        metas = []
+        for i in range(int(buf[0])):
+            dt = _DTYPES[int(buf[1 + i * 10])]
+            nd = int(buf[2 + i * 10])
+            metas.append((tuple(int(x) for x in buf[3 + i * 10 : 3 + i * 10 + nd]), dt))
+        self.meta_fwd = metas
+
+    # -- low level ----------------------------------------------------------------------------------
+    def _exchange(self, sends, recvs):
+        """``sends``/``recvs``: lists of (tensor, peer). Issued as one batch so that opposite
+        directions between two neighbours progress concurrently (no send/send deadlock)."""
+        ops = [dist.P2POp(dist.isend, t, peer, self.group) for t, peer in sends]
+        ops += [dist.P2POp(dist.irecv, t, peer, self.group) for t, peer in recvs]
+        if not ops:
+            return
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def _fwd_buffers(self):
+        if self.meta_fwd is None:
+            self._recv_meta()
+        return [torch.empty(shape, dtype=dt, device=self.dev) for shape, dt in self.meta_fwd]
+
+    @staticmethod
+    def _wrap_inputs(bufs):
+        for t in bufs:
+            if t.dtype.is_floating_point:
+                t.requires_grad_(True)
+        return bufs[0] if len(bufs) == 1 else tuple(bufs)
+
+    def _fwd_payload(self, out):
+        ts = [t.detach().contiguous() for t in _as_tuple(out)]
+        if not self.sent_meta:
+            self._send_meta(ts)
+            self.sent_meta = True
+        return ts
+
+    @staticmethod
+    def _grad_payload(hidden_in):
+        return [
+            (t.grad if t.grad is not None else torch.zeros_like(t)).contiguous()
+            for t in _as_tuple(hidden_in)
+            if t.dtype.is_floating_point
+        ]
+
+    @staticmethod
+    def _grad_buffers(out):
+        return [torch.empty_like(t) if t.dtype.is_floating_point else None for t in _as_tuple(out)]
+
+    # -- single direction ----------------------------------------------------------------------------
+    def recv_forward(self):
+        if self.prev is None:
+            return None
+        bufs = self._fwd_buffers()
+        self._exchange([], [(b, self.prev) for b in bufs])
+        return self._wrap_inputs(bufs)
+
+    def send_forward(self, out):
+        if self.next is None:
+            return
+        self._exchange([(t, self.next) for t in self._fwd_payload(out)], [])
+
+    def recv_backward(self, out):
+        if self.next is None:
+            return None
+        bufs = self._grad_buffers(out)
+        self._exchange([], [(b, self.next) for b in bufs if b is not None])
+        return tuple(bufs)
+
+    def send_backward(self, hidden_in):
+        if self.prev is None or hidden_in is None:
+            return
+        self._exchange([(g, self.prev) for g in self._grad_payload(hidden_in)], [])
+
+    # -- fused directions (steady state of 1F1B) -----------------------------------------------------------
+    def send_forward_recv_backward(self, out):
+        if self.next is None:
+            return None
+        bufs = self._grad_buffers(out)
+        self._exchange([(t, self.next) for t in self._fwd_payload(out)], [(b, self.next) for b in bufs if b is not None])
+        return tuple(bufs)
+
+    def send_backward_recv_forward(self, hidden_in):
+        if self.prev is None:
+            return None
+        bufs = self._fwd_buffers()
+        self._exchange([(g, self.prev) for g in self._grad_payload(hidden_in)], [(b, self.prev) for b in bufs])
+        return self._wrap_inputs(bufs)
+
+
+class PipelineSchedule1F1B:
+    """Runs one optimizer step's worth of micro-batches through the local pipeline stage."""
+
+    def __init__(self, model, loss_scaler=None):
+        self.model = model
+        self.topo = dutil.get_dist_util()
+        self.p2p = _P2P()
+        self.loss_scaler = loss_scaler
+
+    def _forward(self, batch: Dict[str, torch.Tensor], hidden_in, n_micro: int):
+        """Returns ``(out, metrics)``: ``out`` is the scaled scalar loss on the last stage, the stage
+        output tensors otherwise."""
+        if self.topo.sequence_parallel:
+            first = next(iter(batch.values()))
+            set_sp_shape(first.shape[0], first.shape[1] if first.dim() > 1 else 1)
+        out = self.model.forward_stage(batch, hidden_in)
+        if self.topo.is_last_stage:
+            loss = sum(v for k, v in out.items() if "loss" in k) / n_micro
+            if self.loss_scaler is not None:
+                loss = self.loss_scaler.scale_loss(loss)
+            return loss, {k: v.detach() / n_micro for k, v in out.items()}
+        return out, None
+
+    def _backward(self, out, out_grads):
+        if self.topo.is_last_stage:
+            out.backward()
+            return
+        pairs = [(t, g) for t, g in zip(_as_tuple(out), out_grads) if g is not None and t.requires_grad]
+        torch.autograd.backward([t for t, _ in pairs], [g for _, g in pairs])
+
+    def run(self, batches: List[Dict[str, torch.Tensor]]) -> Optional[Dict[str, torch.Tensor]]:
+        """Returns the (micro-batch averaged) loss dict on the last stage, ``None`` elsewhere."""
+        M = len(batches)
+        p, s = self.topo.pipeline_parallel_size, self.topo.pp_rank
+        warm = min(p - s - 1, M)
+        steady = M - warm
+        p2p = self.p2p
+        inflight: List[Tuple] = []  # (hidden_in, out) awaiting backward, FIFO
+        metrics: Optional[Dict[str, torch.Tensor]] = None
+
+        def track(m):
+            nonlocal metrics
+            if m is not None:
+                metrics = m if metrics is None else {k: metrics[k] + m[k] for k in m}
+
+        it = iter(batches)
+        # ---- warm-up forwards
+        for _ in range(warm):
+            hidden_in = p2p.recv_forward()
+            out, m = self._forward(next(it), hidden_in, M)
+            track(m)
+            p2p.send_forward(out)
+            inflight.append((hidden_in, out))
+        # ---- steady 1F1B
+        hidden_in = p2p.recv_forward() if steady > 0 else None
+        for i in range(steady):
+            out, m = self._forward(next(it), hidden_in, M)
+            track(m)
+            inflight.append((hidden_in, out))
+            grads = p2p.send_forward_recv_backward(out)
+            h_old, o_old = inflight.pop(0)
+            self._backward(o_old, grads)
+            if i == steady - 1:
+                p2p.send_backward(h_old)
+            else:
+                hidden_in = p2p.send_backward_recv_forward(h_old)
+                if self.topo.is_first_stage:
+                    hidden_in = None
+        # ---- cool-down backwards
+        for _ in range(warm):
+            h_old, o_old = inflight.pop(0)
+            grads = p2p.recv_backward(o_old)
+            self._backward(o_old, grads)
+            p2p.send_backward(h_old)
+        return metrics
+
+    @torch.no_grad()
+    def forward_only(self, batch: Dict[str, torch.Tensor]):
+        """Inference / evaluation through the pipeline; the result lives on the last stage."""
+        hidden_in = self.p2p.recv_forward()
+        out = self.model.forward_stage(batch, hidden_in)
+        if not self.topo.is_last_stage:
+            self.p2p.send_forward(out)
+            return None
+        return out

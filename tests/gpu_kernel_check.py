@@ -1,0 +1,324 @@
+"""Numerics + timing report of every native kernel against fp32 PyTorch references.
+
+Run on a B200:  python tests/gpu_kernel_check.py [--out gpurun_out/kernel_check.json]
+Never aborts on the first failure: every case is recorded (ok / max error / device time / achieved
+TFLOP/s or GB/s) so one GPU call yields the full picture.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import traceback
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from libai_b200 import ops  # noqa: E402
+
+RESULTS = []
+
+
+def timeit(fn, iters=20, warmup=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    times = []
+    for _ in range(iters):
+        flush.zero_()  # evict L2 (126 MB)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    times.sort()
+    return times[len(times) // 2]
+
+
+ONLY = None
+OUT_PATH = None
+
+
+def record(name, fn):
+    if ONLY and not any(name.startswith(o) for o in ONLY):
+        return
+    try:
+        info = fn() or {}
+        info.setdefault("ok", True)
+    except Exception as e:  # noqa
+        info = {"ok": False, "error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1500:]}
+        try:
+            torch.cuda.synchronize()
+        except Exception as e2:  # a sticky CUDA error poisons the context: stop here
+            info["fatal"] = str(e2)
+            RESULTS.append({"name": name, **info})
+            print(json.dumps(RESULTS[-1]), flush=True)
+            raise SystemExit(3)
+    RESULTS.append({"name": name, **info})
+    print(json.dumps({k: v for k, v in RESULTS[-1].items() if k != "trace"}), flush=True)
+    if OUT_PATH:
+        with open(OUT_PATH, "w") as f:
+            json.dump(RESULTS, f, indent=1)
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-6))
+
+
+def check_gemm(ext, layout, M, N, K, bn=0, splits=1, fp32_out=False, time_it=False):
+    def run():
+        g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + layout)
+        if layout == 0:
+            a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+            b = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+            ref = a.float() @ b.float().t()
+        elif layout == 1:
+            a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+            b = torch.randn(K, N, device="cuda", generator=g).bfloat16()
+            ref = a.float() @ b.float()
+        else:
+            a = torch.randn(K, M, device="cuda", generator=g).bfloat16()
+            b = torch.randn(K, N, device="cuda", generator=g).bfloat16()
+            ref = a.float().t() @ b.float()
+        out = ext.gemm_tuned(a, b, layout, bn, splits, fp32_out)
+        torch.cuda.synchronize()
+        err = rel_err(out, ref)
+        tol = 2e-2 if out.dtype == torch.bfloat16 else 2e-3
+        info = {"ok": err < tol, "rel_err": err, "shape": [M, N, K], "layout": layout, "bn": bn, "splits": splits}
+        if time_it:
+            ms = timeit(lambda: ext.gemm_tuned(a, b, layout, bn, splits, fp32_out))
+            lib = timeit(lambda: (a @ b.t()) if layout == 0 else ((a @ b) if layout == 1 else (a.t() @ b)))
+            info.update(ms=ms, tflops=2.0 * M * N * K / ms / 1e9, cublas_ms=lib, cublas_tflops=2.0 * M * N * K / lib / 1e9)
+        return info
+
+    record(f"gemm L{layout} {M}x{N}x{K} bn{bn} s{splits}{' f32' if fp32_out else ''}", run)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/kernel_check.json")
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="comma separated name prefixes")
+    args = ap.parse_args()
+    global ONLY, OUT_PATH
+    ONLY = [o for o in args.only.split(",") if o] or None
+    OUT_PATH = args.out
+    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+    ext = ops.load_ext()
+    torch.manual_seed(0)
+    print("device:", torch.cuda.get_device_name(0), flush=True)
+
+    # ------------------------------------------------------------------ GEMM correctness
+    for layout in (0, 1, 2):
+        for bn in (64, 128, 256):
+            check_gemm(ext, layout, 256, 512, 256, bn=bn)
+    check_gemm(ext, 0, 1000, 1304, 1032)          # ragged M, N, K tails
+    check_gemm(ext, 1, 1000, 1304, 1032)
+    check_gemm(ext, 2, 1000, 1304, 1032, splits=3)
+    check_gemm(ext, 0, 384, 256, 4096, fp32_out=True)
+    check_gemm(ext, 2, 1024, 1024, 8192, splits=0)  # heuristic split-K with atomics
+    # ------------------------------------------------------------------ GEMM speed (GPT-2 / BERT shapes)
+    if not args.quick:
+        for (M, N, K) in [(8192, 3072, 1024), (8192, 1024, 1024), (8192, 4096, 1024), (8192, 1024, 4096),
+                          (8192, 50304, 1024), (8192, 8192, 8192)]:
+            check_gemm(ext, 0, M, N, K, time_it=True)
+        check_gemm(ext, 1, 8192, 1024, 4096, time_it=True)   # dgrad
+        check_gemm(ext, 1, 8192, 1024, 50304, time_it=True)  # LM-head dgrad
+        check_gemm(ext, 2, 4096, 1024, 8192, splits=0, time_it=True)  # wgrad [f, h]
+        check_gemm(ext, 2, 1024, 1024, 8192, splits=0, time_it=True)
+        check_gemm(ext, 2, 50304, 1024, 8192, splits=0, time_it=True)
+
+    # ------------------------------------------------------------------ fused linear fwd (bias + gelu, pre-activation)
+    def lin():
+        x = torch.randn(512, 1024, device="cuda").bfloat16()
+        w = (torch.randn(4096, 1024, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(4096, device="cuda").bfloat16()
+        y, pre = ext.linear_fwd(x, w, b, 1, True)
+        ref_pre = x.float() @ w.float().t() + b.float()
+        ref = torch.nn.functional.gelu(ref_pre)
+        return {"ok": rel_err(y, ref) < 2e-2 and rel_err(pre, ref_pre) < 2e-2, "rel_err": rel_err(y, ref)}
+
+    record("linear_fwd bias+gelu", lin)
+
+    # ------------------------------------------------------------------ norms
+    for rms in (False, True):
+        for H in (1024, 768, 4096, 200):
+            for wdt in (torch.bfloat16, torch.float32):
+                def norm(rms=rms, H=H, wdt=wdt):
+                    x = torch.randn(777, H, device="cuda").bfloat16()
+                    g = (1 + 0.1 * torch.randn(H, device="cuda")).to(wdt)
+                    b = None if rms else (0.1 * torch.randn(H, device="cuda")).to(wdt)
+                    y, mean, rstd = ext.norm_fwd(x, g, b, 1e-5, rms)
+                    xf = x.float().requires_grad_(True)
+                    gf = g.float().requires_grad_(True)
+                    bf = None if b is None else b.float().requires_grad_(True)
+                    if rms:
+                        ref = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * gf
+                    else:
+                        ref = torch.nn.functional.layer_norm(xf, (H,), gf, bf, 1e-5)
+                    gy = torch.randn_like(ref)
+                    ref.backward(gy)
+                    gx, dg, db = ext.norm_bwd(gy.bfloat16(), x, g, mean, rstd, rms, b is not None)
+                    e = [rel_err(y, ref), rel_err(gx, xf.grad), rel_err(dg, gf.grad)]
+                    if b is not None:
+                        e.append(rel_err(db, bf.grad))
+                    return {"ok": max(e) < 3e-2, "errs": e}
+
+                record(f"norm rms={rms} H={H} w={str(wdt)[6:]}", norm)
+
+    def norm_speed():
+        x = torch.randn(8192, 1024, device="cuda").bfloat16()
+        g = torch.ones(1024, device="cuda").bfloat16()
+        b = torch.zeros(1024, device="cuda").bfloat16()
+        ms = timeit(lambda: ext.norm_fwd(x, g, b, 1e-5, False))
+        y, mean, rstd = ext.norm_fwd(x, g, b, 1e-5, False)
+        msb = timeit(lambda: ext.norm_bwd(x, x, g, mean, rstd, False, True))
+        nbytes = x.numel() * 2
+        return {"fwd_ms": ms, "fwd_GBs": 2 * nbytes / ms / 1e6, "bwd_ms": msb, "bwd_GBs": 3 * nbytes / msb / 1e6}
+
+    record("layernorm speed 8192x1024", norm_speed)
+
+    # ------------------------------------------------------------------ elementwise
+    def ew():
+        x = torch.randn(1000, 4096, device="cuda").bfloat16()
+        b = torch.randn(4096, device="cuda").bfloat16()
+        r = torch.randn(1000, 4096, device="cuda").bfloat16()
+        errs = []
+        for act, name in ((1, "gelu"), (2, "gelu_tanh"), (3, "relu"), (4, "silu"), (5, "quick")):
+            y = ext.bias_act_fwd(x, b, act)
+            xf = (x.float() + b.float()).requires_grad_(True)
+            ref = {1: torch.nn.functional.gelu(xf), 2: torch.nn.functional.gelu(xf, approximate="tanh"),
+                   3: torch.relu(xf), 4: torch.nn.functional.silu(xf), 5: xf * torch.sigmoid(1.702 * xf)}[act]
+            gy = torch.randn_like(ref)
+            ref.backward(gy)
+            gx = ext.bias_act_bwd(gy.bfloat16(), x, b, act)
+            errs += [rel_err(y, ref), rel_err(gx, xf.grad)]
+        y = ext.bias_residual_fwd(x, b, r)
+        errs.append(rel_err(y, x.float() + b.float() + r.float()))
+        cs = ext.colsum(x)
+        errs.append(rel_err(cs, x.float().sum(0)))
+        g, u = x, r
+        y = ext.swiglu_fwd(g, u)
+        gf, uf = g.float().requires_grad_(True), u.float().requires_grad_(True)
+        ref = torch.nn.functional.silu(gf) * uf
+        gy = torch.randn_like(ref)
+        ref.backward(gy)
+        dg, du = ext.swiglu_bwd(gy.bfloat16(), g, u)
+        errs += [rel_err(y, ref), rel_err(dg, gf.grad), rel_err(du, uf.grad)]
+        return {"ok": max(errs) < 3e-2, "errs": errs}
+
+    record("elementwise", ew)
+
+    def rope():
+        from libai_b200.ops.functional import rotate_half
+
+        x = torch.randn(2, 4, 128, 64, device="cuda").bfloat16()
+        pos = torch.arange(128, device="cuda").float()
+        inv = 1.0 / (10000 ** (torch.arange(0, 64, 2, device="cuda").float() / 64))
+        fr = torch.outer(pos, inv)
+        emb = torch.cat([fr, fr], -1)
+        cos, sin = emb.cos().contiguous(), emb.sin().contiguous()
+        y = ext.rope(x, cos, sin, False)
+        xf = x.float().requires_grad_(True)
+        ref = xf * cos + rotate_half(xf) * sin
+        gy = torch.randn_like(ref)
+        ref.backward(gy)
+        gx = ext.rope(gy.bfloat16(), cos, sin, True)
+        e = [rel_err(y, ref), rel_err(gx, xf.grad)]
+        return {"ok": max(e) < 2e-2, "errs": e}
+
+    record("rope", rope)
+
+    # ------------------------------------------------------------------ cross entropy
+    def ce():
+        T, V = 513, 50304
+        logits = (torch.randn(T, V, device="cuda") * 2).bfloat16()
+        labels = torch.randint(0, V, (T,), device="cuda")
+        mx, se, tgt = ext.ce_stats(logits, labels, 0)
+        lf = logits.float().requires_grad_(True)
+        ref = torch.nn.functional.cross_entropy(lf, labels, reduction="none")
+        loss = mx + torch.log(se) - tgt
+        gl = torch.rand(T, device="cuda")
+        ref.backward(gl)
+        d = ext.ce_bwd(logits.clone(), labels, mx + torch.log(se), gl, 0)
+        e = [rel_err(loss, ref), rel_err(d, lf.grad)]
+        ms = timeit(lambda: ext.ce_stats(logits, labels, 0))
+        return {"ok": max(e) < 2e-2, "errs": e, "stats_ms": ms, "GBs": T * V * 2 / ms / 1e6}
+
+    record("cross entropy", ce)
+
+    # ------------------------------------------------------------------ adam
+    def adam():
+        n = 1 << 20
+        p = torch.randn(n, device="cuda")
+        g = torch.randn(n, device="cuda")
+        m = torch.zeros(n, device="cuda")
+        v = torch.zeros(n, device="cuda")
+        lp = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+        pr = p.clone().requires_grad_(True)
+        opt = torch.optim.AdamW([pr], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+        for step in (1, 2, 3):
+            pr.grad = g.clone()
+            opt.step()
+            ext.fused_adamw(p, g, m, v, lp, torch.ones(1, device="cuda"), 1e-2, 0.9, 0.999, 1e-8, 0.01,
+                            1 - 0.9 ** step, 1 - 0.999 ** step, True)
+        e = [rel_err(p, pr.detach()), rel_err(lp, pr.detach())]
+        sq = ext.sqnorm(g)
+        e.append(abs(float(sq) - float((g * g).sum())) / float((g * g).sum()))
+        ms = timeit(lambda: ext.fused_adamw(p, g, m, v, lp, torch.ones(1, device="cuda"), 1e-2, 0.9, 0.999, 1e-8, 0.01, 0.5, 0.5, True))
+        return {"ok": e[0] < 1e-4 and e[1] < 1e-2 and e[2] < 1e-3, "errs": e, "ms": ms, "GBs": n * (4 * 7 + 2) / ms / 1e6}
+
+    record("fused adamw + sqnorm", adam)
+
+    # ------------------------------------------------------------------ attention
+    from libai_b200.ops.functional import attention_ref
+
+    for (B, A, S, D, causal) in [(2, 4, 256, 64, True), (2, 4, 256, 64, False), (1, 2, 384, 128, True),
+                                 (2, 3, 200, 64, True), (1, 2, 1024, 64, True), (1, 2, 512, 128, False)]:
+        def att(B=B, A=A, S=S, D=D, causal=causal):
+            qkv = torch.randn(B, S, A, 3 * D, device="cuda").bfloat16()
+            v4 = qkv.view(B, S, A, 3 * D).permute(0, 2, 1, 3)
+            q, k, v = v4[..., :D], v4[..., D:2 * D], v4[..., 2 * D:]
+            scale = 1.0 / math.sqrt(D)
+            o, lse = ext.attn_fwd(q, k, v, causal, scale)
+            qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+            ref = attention_ref(qf, kf, vf, causal=causal, scale=scale, fill=-1e30)
+            e = [rel_err(o, ref)]
+            go = torch.randn(B, S, A, D, device="cuda").bfloat16().permute(0, 2, 1, 3)
+            ref.backward(go.float())
+            dq, dk, dv = ext.attn_bwd(go, q, k, v, o, lse, causal, scale)
+            e += [rel_err(dq, qf.grad), rel_err(dk, kf.grad), rel_err(dv, vf.grad)]
+            return {"ok": max(e) < 3e-2, "errs": e}
+
+        record(f"attention B{B} A{A} S{S} D{D} causal={causal}", att)
+
+    if not args.quick:
+        def att_speed():
+            B, A, S, D = 8, 16, 1024, 64
+            qkv = torch.randn(B, S, A, 3 * D, device="cuda").bfloat16()
+            v4 = qkv.permute(0, 2, 1, 3)
+            q, k, v = v4[..., :D], v4[..., D:2 * D], v4[..., 2 * D:]
+            scale = 0.125
+            ms = timeit(lambda: ext.attn_fwd(q, k, v, True, scale))
+            o, lse = ext.attn_fwd(q, k, v, True, scale)
+            go = torch.randn(B, S, A, D, device="cuda").bfloat16().permute(0, 2, 1, 3)
+            msb = timeit(lambda: ext.attn_bwd(go, q, k, v, o, lse, True, scale))
+            flops = 4.0 * B * A * S * S * D / 2
+            qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
+            sd = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qc, kc, vc, is_causal=True))
+            return {"fwd_ms": ms, "fwd_tflops": flops / ms / 1e9, "bwd_ms": msb, "bwd_tflops": 2.5 * flops / msb / 1e9,
+                    "sdpa_fwd_ms": sd}
+
+        record("attention speed B8 A16 S1024 D64 causal", att_speed)
+
+    with open(args.out, "w") as f:
+        json.dump(RESULTS, f, indent=1)
+    bad = [r["name"] for r in RESULTS if not r.get("ok", False)]
+    print(f"SUMMARY: {len(RESULTS) - len(bad)}/{len(RESULTS)} ok; failed: {bad}")
+
+
+if __name__ == "__main__":
+    main()
