@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--tp", type=int, default=1)
     ap.add_argument("--pp", type=int, default=1)
-    ap.add_argument("--zero", type=int, default=0)
+    ap.add_argument("--zero", type=int, default=-1, help="ZeRO stage; -1 = auto (stage 1 with the fused NVLink kernels when dp > 1)")
     ap.add_argument("--acc", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -145,6 +145,8 @@ class ClockSampler:
 def build_cfg(args, world):
     from libai_b200.config import LazyConfig
 
+    if args.zero < 0:
+        args.zero = 1 if world // (args.tp * args.pp) > 1 else 0
     cfg = LazyConfig.load(os.path.join(REPO, "configs", "gpt2_synthetic.py"))
     m = cfg.model.cfg
     m.hidden_layers, m.hidden_size, m.num_attention_heads = args.layers, args.hidden, args.heads

@@ -33,6 +33,19 @@ int lb_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const
 int lb_adamw(float* master, const float* grad, float* m, float* v, void* lp_out, const float* scale, long n, float lr,
              float b1, float b2, float eps, float wd, float bc1, float bc2, int decoupled, cudaStream_t s);
 int lb_sqnorm(const float* x, float* out, long n, cudaStream_t s);
+int lb_gemm_bf16_comm(const void* a, const void* b, void* out, int M, int N, int K, int layout, const void* bias, int act,
+                      void* pre_out, int mode, int world, int rank, unsigned epoch, unsigned target,
+                      const long* peer_buf, const long* peer_flags, void* chunk_flags, const void* residual,
+                      void* rs_out, long staging_parity_off, int n_comm, cudaStream_t stream);
+int lb_zero_reduce_scatter(const long* grad_ptrs, const long* flag_ptrs, float* red, float* sqnorm, long lo, long n,
+                           float scale, int world, int rank, unsigned epoch, cudaStream_t s);
+int lb_zero_adam_allgather(float* master, const float* red, float* m, float* v, const long* param_ptrs,
+                           const long* flag_ptrs, unsigned* done_counter, const float* clip, long lo, long n, float lr,
+                           float b1, float b2, float eps, float wd, float bc1, float bc2, int decoupled, int world,
+                           int rank, unsigned epoch, cudaStream_t s);
+int lb_device_barrier(const long* flag_ptrs, int world, int rank, int slot, unsigned epoch, cudaStream_t s);
+int lb_p2p_allgather(const void* shard, const long* out_ptrs, const long* flag_ptrs, unsigned* done_counter,
+                     long nbytes, int world, int rank, unsigned epoch, cudaStream_t s);
 int lb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int A, int S, int D,
                 const long* q_strides, const long* k_strides, const long* v_strides, int causal, float scale,
                 cudaStream_t s);
@@ -301,7 +314,7 @@ std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tens
   return std::make_tuple(o.permute({0, 2, 1, 3}), lse);
 }
 
-std::tuple<Tensor, Tensor, Tensor> attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor& v,
+std::tuple<Tensor, Tensor, Tensor, Tensor> attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor& v,
                                             const Tensor& o, const Tensor& lse, bool causal, double scale) {
   c10::cuda::CUDAGuard guard(q.device());
   const int B = (int)q.size(0), A = (int)q.size(1), S = (int)q.size(2), D = (int)q.size(3);
@@ -326,12 +339,79 @@ std::tuple<Tensor, Tensor, Tensor> attn_bwd(const Tensor& dout, const Tensor& q,
                     dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr<float>(), dq_acc.data_ptr<float>(), B, A,
                     S, D, qs, ks, vs, ds, causal ? 1 : 0, (float)scale, cur_stream()),
         "attn_bwd");
-  return std::make_tuple(dq, dk, dv);
+  return std::make_tuple(dq, dk, dv, dqkv);
+}
+
+// ---- fused collectives ---------------------------------------------------------------------------------------
+std::vector<long> to_longs(at::IntArrayRef v) { return std::vector<long>(v.begin(), v.end()); }
+
+// mode 1: AG->GEMM (returns y [M, N]); mode 2: GEMM->RS (returns rs_out [M/world, N])
+Tensor gemm_comm(const Tensor& a, const Tensor& w, int64_t layout, const c10::optional<Tensor>& bias, int64_t act, int64_t mode,
+                 int64_t world, int64_t rank, int64_t epoch, int64_t target, at::IntArrayRef peer_buf,
+                 at::IntArrayRef peer_flags, const c10::optional<Tensor>& chunk_flags,
+                 const c10::optional<Tensor>& residual, int64_t staging_parity_off, int64_t n_comm) {
+  c10::cuda::CUDAGuard guard(a.device());
+  TORCH_CHECK(a.dim() == 2 && w.dim() == 2 && a.is_contiguous() && w.is_contiguous(), "gemm_comm: contiguous 2-D operands");
+  const int64_t M = a.size(0), K = a.size(1), N = layout == 0 ? w.size(0) : w.size(1);
+  TORCH_CHECK((layout == 0 ? w.size(1) : w.size(0)) == K, "gemm_comm: K mismatch");
+  auto pb = to_longs(peer_buf), pf = to_longs(peer_flags);
+  Tensor out = mode == 1 ? at::empty({M, N}, a.options()) : at::empty({M / world, N}, a.options());
+  const void* bias_ptr = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
+  const void* res_ptr = (residual.has_value() && residual->defined()) ? residual->data_ptr() : nullptr;
+  void* cf = (chunk_flags.has_value() && chunk_flags->defined()) ? chunk_flags->data_ptr() : nullptr;
+  check(lb_gemm_bf16_comm(a.data_ptr(), w.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, (int)layout, bias_ptr, (int)act, nullptr,
+                          (int)mode, (int)world, (int)rank, (unsigned)epoch, (unsigned)target, pb.data(), pf.data(), cf,
+                          res_ptr, out.data_ptr(), (long)staging_parity_off, (int)n_comm, cur_stream()),
+        "gemm_comm");
+  return out;
+}
+
+void zero_reduce_scatter(at::IntArrayRef grad_ptrs, at::IntArrayRef flag_ptrs, Tensor red, Tensor sqnorm, int64_t lo,
+                         int64_t n, double scale, int64_t world, int64_t rank, int64_t epoch) {
+  c10::cuda::CUDAGuard guard(red.device());
+  auto g = to_longs(grad_ptrs), f = to_longs(flag_ptrs);
+  check(lb_zero_reduce_scatter(g.data(), f.data(), red.data_ptr<float>(), sqnorm.data_ptr<float>(), (long)lo, (long)n,
+                               (float)scale, (int)world, (int)rank, (unsigned)epoch, cur_stream()),
+        "zero_reduce_scatter");
+}
+
+void zero_adam_allgather(Tensor master, const Tensor& red, Tensor m, Tensor v, at::IntArrayRef param_ptrs,
+                         at::IntArrayRef flag_ptrs, Tensor done_counter, const Tensor& clip, int64_t lo, int64_t n,
+                         double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, bool decoupled,
+                         int64_t world, int64_t rank, int64_t epoch) {
+  c10::cuda::CUDAGuard guard(master.device());
+  auto pp = to_longs(param_ptrs), f = to_longs(flag_ptrs);
+  check(lb_zero_adam_allgather(master.data_ptr<float>(), red.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
+                               pp.data(), f.data(), reinterpret_cast<unsigned*>(done_counter.data_ptr()),
+                               clip.data_ptr<float>(), (long)lo, (long)n, (float)lr, (float)b1, (float)b2, (float)eps,
+                               (float)wd, (float)bc1, (float)bc2, decoupled ? 1 : 0, (int)world, (int)rank,
+                               (unsigned)epoch, cur_stream()),
+        "zero_adam_allgather");
+}
+
+void device_barrier(at::IntArrayRef flag_ptrs, int64_t world, int64_t rank, int64_t slot, int64_t epoch) {
+  auto f = to_longs(flag_ptrs);
+  check(lb_device_barrier(f.data(), (int)world, (int)rank, (int)slot, (unsigned)epoch, cur_stream()), "device_barrier");
+}
+
+void p2p_allgather(const Tensor& shard, at::IntArrayRef out_ptrs, at::IntArrayRef flag_ptrs, Tensor done_counter,
+                   int64_t world, int64_t rank, int64_t epoch) {
+  c10::cuda::CUDAGuard guard(shard.device());
+  auto o = to_longs(out_ptrs), f = to_longs(flag_ptrs);
+  check(lb_p2p_allgather(shard.data_ptr(), o.data(), f.data(), reinterpret_cast<unsigned*>(done_counter.data_ptr()),
+                         (long)(shard.numel() * shard.element_size()), (int)world, (int)rank, (unsigned)epoch,
+                         cur_stream()),
+        "p2p_allgather");
 }
 
 }  // namespace
 
 TORCH_LIBRARY(libai_b200, m) {
+  m.def("gemm_comm(Tensor a, Tensor w, int layout, Tensor? bias, int act, int mode, int world, int rank, int epoch, int target, int[] peer_buf, int[] peer_flags, Tensor? chunk_flags, Tensor? residual, int staging_parity_off, int n_comm) -> Tensor", &gemm_comm);
+  m.def("zero_reduce_scatter(int[] grad_ptrs, int[] flag_ptrs, Tensor(a!) red, Tensor(b!) sqnorm, int lo, int n, float scale, int world, int rank, int epoch) -> ()", &zero_reduce_scatter);
+  m.def("zero_adam_allgather(Tensor(a!) master, Tensor red, Tensor(b!) m, Tensor(c!) v, int[] param_ptrs, int[] flag_ptrs, Tensor(d!) done_counter, Tensor clip, int lo, int n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, bool decoupled, int world, int rank, int epoch) -> ()", &zero_adam_allgather);
+  m.def("device_barrier(int[] flag_ptrs, int world, int rank, int slot, int epoch) -> ()", &device_barrier);
+  m.def("p2p_allgather(Tensor shard, int[] out_ptrs, int[] flag_ptrs, Tensor(a!) done_counter, int world, int rank, int epoch) -> ()", &p2p_allgather);
   m.def("gemm(Tensor a, Tensor b, int layout, Tensor? bias, Tensor? out, bool accumulate, ScalarType out_dtype) -> Tensor", &gemm);
   m.def("gemm_tuned(Tensor a, Tensor b, int layout, int bn, int splits, bool fp32_out) -> Tensor", &gemm_tuned);
   m.def("linear_fwd(Tensor x, Tensor w, Tensor? bias, int act, bool need_pre) -> (Tensor, Tensor)", &linear_fwd);
@@ -350,5 +430,5 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("fused_adamw(Tensor(a!) master, Tensor grad, Tensor(b!) m, Tensor(c!) v, Tensor? lp_out, Tensor scale, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, bool decoupled) -> ()", &fused_adamw);
   m.def("sqnorm(Tensor x) -> Tensor", &sqnorm);
   m.def("attn_fwd(Tensor q, Tensor k, Tensor v, bool causal, float scale) -> (Tensor, Tensor)", &attn_fwd);
-  m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor o, Tensor lse, bool causal, float scale) -> (Tensor, Tensor, Tensor)", &attn_bwd);
+  m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor o, Tensor lse, bool causal, float scale) -> (Tensor, Tensor, Tensor, Tensor)", &attn_bwd);
 }

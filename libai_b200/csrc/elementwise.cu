@@ -167,6 +167,26 @@ LB_DEVICE float ld_logit<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloa
 template <>
 LB_DEVICE float ld_logit<float>(const float* p) { return *p; }
 
+// load 8 consecutive logits as floats (16-byte / 32-byte vector access)
+template <typename T>
+LB_DEVICE void ld_logits8(const T* p, float (&v)[8]);
+template <>
+LB_DEVICE void ld_logits8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) { ld8(p, v); }
+template <>
+LB_DEVICE void ld_logits8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename T>
+LB_DEVICE void st_logits8(T* p, const float (&v)[8]);
+template <>
+LB_DEVICE void st_logits8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) { st8(p, v); }
+template <>
+LB_DEVICE void st_logits8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 // per row: local max, sum exp(x - max), target logit (0 if the label lives on another rank)
 template <typename T>
 __global__ void __launch_bounds__(256) ce_stats_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels,
@@ -176,17 +196,33 @@ __global__ void __launch_bounds__(256) ce_stats_kernel(const T* __restrict__ log
   const int row = blockIdx.x;
   const T* lr = logits + static_cast<size_t>(row) * V;
   float m = -INFINITY, s = 0.f;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) {
-    const float x = ld_logit<T>(lr + c);
-    if (x > m) {
-      s = s * __expf(m - x) + 1.0f;
-      m = x;
-    } else {
-      s += __expf(x - m);
+  if (V % 8 == 0) {
+    for (int c = threadIdx.x * 8; c < V; c += blockDim.x * 8) {
+      float x[8];
+      ld_logits8<T>(lr + c, x);
+      float cm = x[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) cm = fmaxf(cm, x[j]);
+      if (cm > m) {
+        s *= __expf(m - cm);
+        m = cm;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += __expf(x[j] - m);
+    }
+  } else {
+    for (int c = threadIdx.x; c < V; c += blockDim.x) {
+      const float x = ld_logit<T>(lr + c);
+      if (x > m) {
+        s = s * __expf(m - x) + 1.0f;
+        m = x;
+      } else {
+        s += __expf(x - m);
+      }
     }
   }
   const float wm = warp_max(m);
-  s *= __expf(m - wm);
+  s = (m == -INFINITY) ? 0.f : s * __expf(m - wm);
   s = warp_sum(s);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (lane == 0) {
@@ -219,10 +255,24 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ logit
   T* dr = dlogits + static_cast<size_t>(row) * V;
   const float l = lse[row], g = gloss[row];
   const int64_t local = labels[row] - vocab_start;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) {
-    float p = __expf(ld_logit<T>(lr + c) - l);
-    if (c == local) p -= 1.0f;
-    dr[c] = static_cast<T>(p * g);
+  if (V % 8 == 0) {
+    for (int c = threadIdx.x * 8; c < V; c += blockDim.x * 8) {
+      float x[8];
+      ld_logits8<T>(lr + c, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float p = __expf(x[j] - l);
+        if (c + j == local) p -= 1.0f;
+        x[j] = p * g;
+      }
+      st_logits8<T>(dr + c, x);
+    }
+  } else {
+    for (int c = threadIdx.x; c < V; c += blockDim.x) {
+      float p = __expf(ld_logit<T>(lr + c) - l);
+      if (c == local) p -= 1.0f;
+      dr[c] = static_cast<T>(p * g);
+    }
   }
 }
 

@@ -15,6 +15,7 @@
 #include "common.cuh"
 
 #include <cstdio>
+#include <cstring>
 #include <mutex>
 
 namespace lb {
@@ -38,6 +39,47 @@ struct GemmParams {
   int ldo;                    // leading dimension of out (elements)
 };
 
+// Fused collective modes (tensor parallel): peer pointers refer to NVLink peer-mapped symmetric memory.
+//   COMM_AG : all-gather -> GEMM.  A = [M, K] "gathered" buffer; rank r produced rows [r*rpr, (r+1)*rpr) of its own
+//             buffer, the other rows are pulled from the owners by `n_comm` dedicated CTAs while the GEMM CTAs
+//             already work on the local rows; per-row-block arrival counters gate the TMA loads.
+//   COMM_RS : GEMM -> reduce-scatter.  Each rank computes the full [M, N] partial product; the epilogue stores
+//             row block tiles straight into the owner's staging slot (P2P stores) and bumps the owner's arrival
+//             counter; after its tiles every CTA helps reducing the local rows (sum over sources + bias + residual).
+enum CommMode : int { COMM_NONE = 0, COMM_AG = 1, COMM_RS = 2 };
+struct CommParams {
+  int mode, world, rank;
+  int rows_per_rank;            // M / world, multiple of BLOCK_M
+  int n_comm;                   // COMM_AG: number of copy CTAs
+  uint32_t epoch;               // call counter (>= 1) for the "shard ready" handshake
+  uint32_t target;              // cumulative arrival count expected by this call (per row block)
+  __nv_bfloat16* peer_buf[8];   // AG: gathered buffers of all ranks; RS: staging buffers of all ranks
+  uint32_t* peer_flags[8];      // AG: handshake flag rows of all ranks; RS: arrival counters of all ranks
+  uint32_t* chunk_flags;        // AG: local per-row-block arrival counters
+  const __nv_bfloat16* residual;  // RS: optional [rows_per_rank, N]
+  __nv_bfloat16* rs_out;        // RS: [rows_per_rank, N]
+  long staging_parity_off;      // RS: element offset of the staging half used by this call
+};
+
+// streaming (non-volatile, L1 no-allocate) 128-bit load: many of these stay in flight per thread over NVLink
+LB_DEVICE uint4 ld_stream_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+LB_DEVICE uint32_t ld_acquire_sys_u32(const uint32_t* a) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(a) : "memory");
+  return v;
+}
+LB_DEVICE uint32_t ld_acquire_gpu_u32(const uint32_t* a) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(a) : "memory");
+  return v;
+}
+
 template <int BLOCK_N>
 struct StageCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -50,7 +92,8 @@ struct StageCfg {
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p,
+            CommParams cp) {
   using Cfg = StageCfg<BLOCK_N>;
   constexpr int NS = Cfg::NUM_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -68,6 +111,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int k_blocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_tiles = m_blocks * n_blocks * p.k_splits;
+  // CTAs [0, n_comm) are copy CTAs in COMM_AG mode; the rest run the GEMM roles
+  const int n_comm = (cp.mode == COMM_AG) ? cp.n_comm : 0;
+  const int cta = static_cast<int>(blockIdx.x) - n_comm;
+  const int cta_stride = static_cast<int>(gridDim.x) - n_comm;
+  const int mbpr = cp.mode != COMM_NONE ? cp.rows_per_rank / BLOCK_M : m_blocks;
+  // row blocks are visited owner by owner: AG starts with the local rows (already resident), RS ends with them
+  auto map_m = [&](int m_seq) -> int {
+    if (cp.mode == COMM_NONE) return m_seq;
+    const int shift = (cp.mode == COMM_AG) ? 0 : 1;
+    const int owner = (cp.rank + shift + m_seq / mbpr) % cp.world;
+    return owner * mbpr + m_seq % mbpr;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -92,15 +147,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp_idx == 0) {
+  if (n_comm > 0 && static_cast<int>(blockIdx.x) < n_comm) {
+    // ======================= COMM_AG copy CTA: pull the peers' row blocks over NVLink =======================
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      __threadfence_system();
+      for (int q = 0; q < cp.world; ++q)
+        asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(cp.peer_flags[q] + cp.rank), "r"(cp.epoch) : "memory");
+    }
+    const size_t nv_blk = static_cast<size_t>(BLOCK_M) * p.K / 8;  // uint4 vectors per row block
+    const size_t v_lo = nv_blk * blockIdx.x / n_comm, v_hi = nv_blk * (blockIdx.x + 1) / n_comm;
+    for (int s = 1; s < cp.world; ++s) {
+      const int src = (cp.rank + s) % cp.world;
+      if (threadIdx.x == 0) {
+        while (static_cast<int32_t>(ld_acquire_sys_u32(cp.peer_flags[cp.rank] + src) - cp.epoch) < 0) {
+        }
+      }
+      __syncthreads();
+      for (int lm = 0; lm < mbpr; ++lm) {
+        const int m_blk = src * mbpr + lm;
+        const size_t base = static_cast<size_t>(m_blk) * nv_blk;
+        const uint4* sp = reinterpret_cast<const uint4*>(cp.peer_buf[src]) + base;
+        uint4* dp = reinterpret_cast<uint4*>(cp.peer_buf[cp.rank]) + base;
+        size_t i = v_lo + threadIdx.x;
+        for (; i + 15 * NUM_THREADS < v_hi; i += 16 * NUM_THREADS) {
+          uint4 t[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t[j] = ld_stream_u4(sp + i + j * NUM_THREADS);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dp[i + j * NUM_THREADS] = t[j];
+        }
+        for (; i < v_hi; i += NUM_THREADS) dp[i] = ld_stream_u4(sp + i);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(cp.chunk_flags + m_blk) : "memory");
+      }
+    }
+  } else if (warp_idx == 0) {
     // ======================= TMA producer =======================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cta; tile < num_tiles; tile += cta_stride) {
         const int split = tile % p.k_splits;
         const int mn = tile / p.k_splits;
-        const int m_blk = mn / n_blocks, n_blk = mn % n_blocks;
+        const int m_blk = map_m(mn / n_blocks), n_blk = mn % n_blocks;
+        if (cp.mode == COMM_AG && m_blk / mbpr != cp.rank) {
+          // rows owned by a peer: wait until the copy CTAs have landed this row block locally
+          while (static_cast<int32_t>(ld_acquire_gpu_u32(cp.chunk_flags + m_blk) - cp.target) < 0) {
+          }
+          asm volatile("fence.proxy.async.global;\n" ::: "memory");
+        }
         const int kb0 = split * p.k_per_split;
         const int kb1 = min(kb0 + p.k_per_split, k_blocks_total);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -136,7 +232,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < num_tiles; tile += cta_stride) {
       const int split = tile % p.k_splits;
       const int kb0 = split * p.k_per_split;
       const int kb1 = min(kb0 + p.k_per_split, k_blocks_total);
@@ -179,9 +275,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int quad = warp_idx % 4;  // TMEM lanes [32*quad, 32*quad+32)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < num_tiles; tile += cta_stride) {
       const int mn = tile / p.k_splits;
-      const int m_blk = mn / n_blocks, n_blk = mn % n_blocks;
+      const int m_blk = map_m(mn / n_blocks), n_blk = mn % n_blocks;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const int row = m_blk * BLOCK_M + quad * 32 + lane;
@@ -199,7 +295,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           if constexpr (EPI == EPI_BF16) {
-            if (p.bias != nullptr) {
+            if (p.bias != nullptr && cp.mode != COMM_RS) {  // RS adds the bias once, in the reduce phase
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
                 if (col0 + i < p.N) {
@@ -210,6 +306,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               }
             }
             __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+            if (cp.mode == COMM_RS) {
+              // slot [src = rank] of the owner's staging buffer, row index local to the owner
+              const int owner = m_blk / mbpr;
+              const size_t lrow = static_cast<size_t>(cp.rank) * cp.rows_per_rank + (row - owner * cp.rows_per_rank);
+              orow = cp.peer_buf[owner] + cp.staging_parity_off + lrow * p.N + col0;
+            }
             if (p.pre_out != nullptr) {
               __nv_bfloat16* prow = p.pre_out + static_cast<size_t>(row) * p.ldo + col0;
 #pragma unroll
@@ -254,10 +356,67 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       tc_fence_before_sync();
       mbar_arrive(&tmem_empty[acc]);
+      if (cp.mode == COMM_RS) {
+        // all 128 epilogue threads have issued their P2P stores -> one release-increment on the owner's counter
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        if (threadIdx.x == 64) {
+          __threadfence_system();
+          const int owner = m_blk / mbpr;
+          // arrivals are counted in units of 64 columns so that the expected total (world * N / 64) does not
+          // depend on the tile width chosen by the heuristic
+          asm volatile("red.release.sys.global.add.u32 [%0], %1;\n" ::"l"(cp.peer_flags[owner] + (m_blk % mbpr)),
+                       "r"(static_cast<uint32_t>(BLOCK_N / 64))
+                       : "memory");
+        }
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
+    }
+  }
+
+  if (cp.mode == COMM_RS) {
+    // ---------------- reduce phase: out[r, :] = sum_src staging[src][r, :] (+ bias) (+ residual) ----------------
+    const int col_groups = (p.N + 255) / 256;
+    const int units = mbpr * col_groups;
+    const __nv_bfloat16* stag = cp.peer_buf[cp.rank] + cp.staging_parity_off;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int lm = u / col_groups, cg = u % col_groups;
+      if (threadIdx.x == 0) {
+        while (static_cast<int32_t>(ld_acquire_sys_u32(cp.peer_flags[cp.rank] + lm) - cp.target) < 0) {
+        }
+      }
+      __syncthreads();
+      const int c_lo = cg * 256;
+      const int c_n = min(256, p.N - c_lo) / 8;  // vectors of 8 per row in this column group
+      for (int v = threadIdx.x; v < BLOCK_M * c_n; v += NUM_THREADS) {
+        const int rr = lm * BLOCK_M + v / c_n;
+        const int cc = c_lo + (v % c_n) * 8;
+        float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int src = 0; src < cp.world; ++src) {
+          const uint4 q = *reinterpret_cast<const uint4*>(stag + (static_cast<size_t>(src) * cp.rows_per_rank + rr) * p.N + cc);
+          const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+          acc8[0] += a.x; acc8[1] += a.y; acc8[2] += b.x; acc8[3] += b.y;
+          acc8[4] += c.x; acc8[5] += c.y; acc8[6] += d.x; acc8[7] += d.y;
+        }
+        if (p.bias != nullptr) {
+          const uint4 q = *reinterpret_cast<const uint4*>(p.bias + cc);
+          const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+          acc8[0] += a.x; acc8[1] += a.y; acc8[2] += b.x; acc8[3] += b.y;
+          acc8[4] += c.x; acc8[5] += c.y; acc8[6] += d.x; acc8[7] += d.y;
+        }
+        if (cp.residual != nullptr) {
+          const uint4 q = *reinterpret_cast<const uint4*>(cp.residual + static_cast<size_t>(rr) * p.N + cc);
+          const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+          acc8[0] += a.x; acc8[1] += a.y; acc8[2] += b.x; acc8[3] += b.y;
+          acc8[4] += c.x; acc8[5] += c.y; acc8[6] += d.x; acc8[7] += d.y;
+        }
+        *reinterpret_cast<uint4*>(cp.rs_out + static_cast<size_t>(rr) * p.N + cc) =
+            make_uint4(pack_bf16(acc8[0], acc8[1]), pack_bf16(acc8[2], acc8[3]), pack_bf16(acc8[4], acc8[5]),
+                       pack_bf16(acc8[6], acc8[7]));
+      }
+      __syncthreads();
     }
   }
 
@@ -337,8 +496,8 @@ bool operand_tmap(CUtensorMap* m, const void* ptr, bool mn_major, int rows_or_co
 }
 
 template <int BN, bool AMN, bool BMN, int EPI>
-cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const lb::GemmParams& p, int grid,
-                       cudaStream_t stream) {
+cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const lb::GemmParams& p, const lb::CommParams& cp,
+                       int grid, cudaStream_t stream) {
   using Cfg = lb::StageCfg<BN>;
   auto kern = lb::gemm_kernel<BN, AMN, BMN, EPI>;
   static bool configured = false;
@@ -347,20 +506,20 @@ cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const lb::G
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, lb::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, lb::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p, cp);
   return cudaGetLastError();
 }
 
 template <bool AMN, bool BMN, int EPI>
-cudaError_t launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const lb::GemmParams& p, int grid,
-                      cudaStream_t s) {
+cudaError_t launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const lb::GemmParams& p,
+                      const lb::CommParams& cp, int grid, cudaStream_t s) {
   switch (bn) {
     case 256:
-      return launch_cfg<256, AMN, BMN, EPI>(ta, tb, p, grid, s);
+      return launch_cfg<256, AMN, BMN, EPI>(ta, tb, p, cp, grid, s);
     case 128:
-      return launch_cfg<128, AMN, BMN, EPI>(ta, tb, p, grid, s);
+      return launch_cfg<128, AMN, BMN, EPI>(ta, tb, p, cp, grid, s);
     default:
-      return launch_cfg<64, AMN, BMN, EPI>(ta, tb, p, grid, s);
+      return launch_cfg<64, AMN, BMN, EPI>(ta, tb, p, cp, grid, s);
   }
 }
 
@@ -369,9 +528,9 @@ cudaError_t launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, cons
 // layout: 0 = NT (A[M,K], B[N,K]); 1 = NN (A[M,K], B[K,N]); 2 = TN (A[K,M], B[K,N])
 // epi:    0 = bf16 store (+bias, act, optional pre-activation copy); 1 = fp32 store; 2 = fp32 atomic accumulate
 // Returns 0 on success, a negative code for unsupported arguments, or a cudaError_t (> 0).
-extern "C" int lb_gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo,
-                            int layout, int epi, const void* bias, int act, void* pre_out, int force_bn,
-                            int force_splits, cudaStream_t stream) {
+static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo, int layout,
+                     int epi, const void* bias, int act, void* pre_out, int force_bn, int force_splits,
+                     const lb::CommParams& cp, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (N % 8) || (ldo % 4)) return -1;
   const bool a_mn = (layout == 2);
@@ -380,6 +539,10 @@ extern "C" int lb_gemm_bf16(const void* a, const void* b, void* out, int M, int 
   const int m_blocks = (M + lb::BLOCK_M - 1) / lb::BLOCK_M;
   // ---- tile-N heuristic: fewest waves, ties -> wider tile (less smem traffic per flop)
   int bn = force_bn;
+  if (bn == 0 && epi == 2) {
+    // split-K fills the machine for the accumulate (wgrad) epilogue: always take the widest tile that fits N
+    bn = N >= 192 ? 256 : (N >= 96 ? 128 : 64);
+  }
   if (bn == 0) {
     double best = 1e30;
     const int cands[3] = {256, 128, 64};
@@ -388,7 +551,7 @@ extern "C" int lb_gemm_bf16(const void* a, const void* b, void* out, int M, int 
       const long tiles = (long)m_blocks * ((N + c - 1) / c);
       const long waves = (tiles + sms - 1) / sms;
       // cost ~ waves * per-tile time (proportional to c, with a small fixed overhead per tile)
-      const double cost = (double)waves * (c + 24.0);
+      const double cost = (double)waves * (c * (c == 256 ? 1.0 : (c == 128 ? 1.08 : 1.2)) + 24.0);
       if (cost < best - 1e-9) {
         best = cost;
         bn = c;
@@ -426,21 +589,66 @@ extern "C" int lb_gemm_bf16(const void* a, const void* b, void* out, int M, int 
   if (!operand_tmap(&ta, a, a_mn, M, K, lda, lb::BLOCK_M)) return -2;
   if (!operand_tmap(&tb, b, b_mn, N, K, ldb, bn)) return -2;
   const long num_tiles = (long)m_blocks * n_blocks * p.k_splits;
-  const int grid = (int)(num_tiles < sms ? num_tiles : sms);
+  int grid = (int)(num_tiles < sms ? num_tiles : sms);
+  if (cp.mode == lb::COMM_AG) {
+    const long g = num_tiles < (sms - cp.n_comm) ? num_tiles : (sms - cp.n_comm);
+    grid = (int)g + cp.n_comm;
+  }
 
   cudaError_t e;
   if (layout == 0) {
-    if (epi == 0) e = launch_bn<false, false, lb::EPI_BF16>(bn, ta, tb, p, grid, stream);
-    else if (epi == 1) e = launch_bn<false, false, lb::EPI_F32>(bn, ta, tb, p, grid, stream);
-    else e = launch_bn<false, false, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, grid, stream);
+    if (epi == 0) e = launch_bn<false, false, lb::EPI_BF16>(bn, ta, tb, p, cp, grid, stream);
+    else if (epi == 1) e = launch_bn<false, false, lb::EPI_F32>(bn, ta, tb, p, cp, grid, stream);
+    else e = launch_bn<false, false, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, cp, grid, stream);
   } else if (layout == 1) {
-    if (epi == 0) e = launch_bn<false, true, lb::EPI_BF16>(bn, ta, tb, p, grid, stream);
-    else if (epi == 1) e = launch_bn<false, true, lb::EPI_F32>(bn, ta, tb, p, grid, stream);
-    else e = launch_bn<false, true, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, grid, stream);
+    if (epi == 0) e = launch_bn<false, true, lb::EPI_BF16>(bn, ta, tb, p, cp, grid, stream);
+    else if (epi == 1) e = launch_bn<false, true, lb::EPI_F32>(bn, ta, tb, p, cp, grid, stream);
+    else e = launch_bn<false, true, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, cp, grid, stream);
   } else {
-    if (epi == 0) e = launch_bn<true, true, lb::EPI_BF16>(bn, ta, tb, p, grid, stream);
-    else if (epi == 1) e = launch_bn<true, true, lb::EPI_F32>(bn, ta, tb, p, grid, stream);
-    else e = launch_bn<true, true, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, grid, stream);
+    if (epi == 0) e = launch_bn<true, true, lb::EPI_BF16>(bn, ta, tb, p, cp, grid, stream);
+    else if (epi == 1) e = launch_bn<true, true, lb::EPI_F32>(bn, ta, tb, p, cp, grid, stream);
+    else e = launch_bn<true, true, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, cp, grid, stream);
   }
   return (int)e;
+}
+
+extern "C" int lb_gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo,
+                            int layout, int epi, const void* bias, int act, void* pre_out, int force_bn,
+                            int force_splits, cudaStream_t stream) {
+  lb::CommParams cp;
+  memset(&cp, 0, sizeof(cp));
+  return gemm_impl(a, b, out, M, N, K, lda, ldb, ldo, layout, epi, bias, act, pre_out, force_bn, force_splits, cp, stream);
+}
+
+// Tensor-parallel fused collective GEMMs (NT layout, bf16 output).
+//   mode 1 (AG->GEMM): a = local gathered buffer [M, K] (rows of peers are pulled inside the kernel), out [M, N]
+//   mode 2 (GEMM->RS): a = local [M, K_shard]; partial tiles go to the owners' staging buffers; rs_out [M/world, N]
+extern "C" int lb_gemm_bf16_comm(const void* a, const void* b, void* out, int M, int N, int K, int layout,
+                                 const void* bias, int act, void* pre_out, int mode, int world, int rank, unsigned epoch,
+                                 unsigned target, const long* peer_buf, const long* peer_flags, void* chunk_flags,
+                                 const void* residual, void* rs_out, long staging_parity_off, int n_comm,
+                                 cudaStream_t stream) {
+  if (world > 8 || M % (lb::BLOCK_M * world) != 0) return -4;
+  if (mode == 2 && (N % 256) != 0) return -5;
+  lb::CommParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.mode = mode;
+  cp.world = world;
+  cp.rank = rank;
+  cp.rows_per_rank = M / world;
+  cp.n_comm = n_comm;
+  cp.epoch = epoch;
+  cp.target = target;
+  for (int i = 0; i < world; ++i) {
+    cp.peer_buf[i] = reinterpret_cast<__nv_bfloat16*>(peer_buf[i]);
+    cp.peer_flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]);
+  }
+  cp.chunk_flags = reinterpret_cast<uint32_t*>(chunk_flags);
+  cp.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  cp.rs_out = reinterpret_cast<__nv_bfloat16*>(rs_out);
+  cp.staging_parity_off = staging_parity_off;
+  // the RS epilogue writes into the staging buffers; `out` is unused there (pass any valid pointer)
+  if (layout != 0 && layout != 1) return -6;
+  return gemm_impl(a, b, mode == 2 ? rs_out : out, M, N, K, K, layout == 0 ? K : N, N, layout, 0, bias, act, pre_out, 0, 1, cp,
+                   stream);
 }

@@ -153,13 +153,30 @@ norm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, const W* __re
   }
 }
 
-// out[c] = sum_r part[r, c]
-__global__ void colreduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nrows, int H) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= H) return;
+// out[c] = sum_r part[r, c]   (block = 32 columns x 8 row stripes, smem tree over the stripes)
+__global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                        int nrows, int H) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int c = blockIdx.x * 32 + tx;
   float acc = 0.f;
-  for (int r = 0; r < nrows; ++r) acc += part[static_cast<size_t>(r) * H + c];
-  out[c] = acc;
+  if (c < H) {
+    int r = ty;
+    for (; r + 24 < nrows; r += 32) {
+      const float a0 = part[static_cast<size_t>(r) * H + c], a1 = part[static_cast<size_t>(r + 8) * H + c];
+      const float a2 = part[static_cast<size_t>(r + 16) * H + c], a3 = part[static_cast<size_t>(r + 24) * H + c];
+      acc += (a0 + a1) + (a2 + a3);
+    }
+    for (; r < nrows; r += 8) acc += part[static_cast<size_t>(r) * H + c];
+  }
+  sm[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sm[j][tx];
+    out[c] = t;
+  }
 }
 
 // ---------------- generic (any H) fallbacks: one warp per row, strided scalar access ----------------
@@ -231,7 +248,7 @@ int norm_grid(int rows) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int need = (rows + lb::NORM_WARPS - 1) / lb::NORM_WARPS;
-  const int cap = sms * 4;
+  const int cap = sms * 2;
   return need < cap ? need : cap;
 }
 
@@ -321,8 +338,8 @@ extern "C" int lb_norm_bwd(const void* gy, const void* x, const void* gamma, con
                  : bwd_dispatch<T, W, false>(H / 256, (const T*)gy, (const T*)x, (const W*)gamma, mean, rstd,        \
                                              (T*)gx, pdg, pdb, rows, grid, s);                                       \
       if (done) {                                                                                                    \
-        lb::colreduce_kernel<<<(H + 255) / 256, 256, 0, s>>>(pdg, dgamma, grid, H);                                  \
-        if (dbeta != nullptr) lb::colreduce_kernel<<<(H + 255) / 256, 256, 0, s>>>(pdb, dbeta, grid, H);             \
+        lb::colreduce_kernel<<<(H + 31) / 32, 256, 0, s>>>(pdg, dgamma, grid, H);                                  \
+        if (dbeta != nullptr) lb::colreduce_kernel<<<(H + 31) / 32, 256, 0, s>>>(pdb, dbeta, grid, H);             \
       }                                                                                                              \
     }                                                                                                                \
     if (!done) {                                                                                                     \

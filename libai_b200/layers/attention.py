@@ -116,7 +116,21 @@ class MultiheadAttention(nn.Module):
             else:
                 raise ValueError("past_key_value and encoder_states cannot be None at the same time.")
         else:
-            qkv = self.query_key_value(hidden_states).view(bsz, -1, a, 3 * d).permute(0, 2, 1, 3)
+            qkv_packed = self.query_key_value(hidden_states).view(bsz, -1, a, 3 * d)
+            if (
+                past_key_value is None and not use_cache
+                and (attention_mask is None)
+                and OF.attention_qkvpacked_supported(qkv_packed, attention_mask, self.attention_dropout_prob, self.training)
+            ):
+                # fast path: flash attention directly on the packed projection
+                context = OF.attention_qkvpacked(
+                    qkv_packed, causal=self.attn_mask_type == AttnMaskType.causal, scale=self.softmax_scale
+                ).reshape(bsz, -1, a * d)
+                if sp and hidden_states.dim() == 2:
+                    context = context.reshape(-1, a * d)
+                output, bias = self.dense(context)
+                return OF.bias_dropout_add(output, bias, residual, self.output_dropout_prob, self.training)
+            qkv = qkv_packed.permute(0, 2, 1, 3)
             query, key, value = qkv[..., :d], qkv[..., d : 2 * d], qkv[..., 2 * d :]
             if past_key_value is not None:
                 past_key, past_value = past_key_value

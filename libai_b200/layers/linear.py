@@ -17,6 +17,7 @@ peer memory, ``libai_b200/ops/comm_gemm.py``) when ``train.dist.fused_tp_comm`` 
 """
 from __future__ import annotations
 
+import torch
 from torch import nn
 
 from libai_b200.ops import functional as OF
@@ -67,6 +68,10 @@ class Linear1D(nn.Module):
         topo = dutil.get_dist_util()
         sp = topo.sequence_parallel
         bias_now = None if self.skip_bias_add else self.bias
+        if topo.fused_tp_comm and self.parallel in ("col", "row") and x.is_cuda and x.dtype == self.weight.dtype:
+            y = self._forward_fused(x, bias_now, act, topo)
+            if y is not None:
+                return (y, self.bias) if self.skip_bias_add else y
         if self.parallel == "col":
             x = mappings.gather_from_sp(x) if sp else mappings.copy_to_tp(x)
             y = OF.linear(x, self.weight, bias_now, act)
@@ -82,6 +87,24 @@ class Linear1D(nn.Module):
         if self.skip_bias_add:
             return y, self.bias
         return y
+
+    def _forward_fused(self, x, bias_now, act, topo):
+        """AG->GEMM / GEMM->RS with the collective inside the tcgen05 kernel (None = shape unsupported)."""
+        from libai_b200.ops import comm_gemm, use_native
+
+        if not use_native(x) or x.dtype != torch.bfloat16:
+            return None
+        x2 = x.reshape(-1, x.shape[-1])
+        t = topo.tensor_parallel_size
+        if self.parallel == "col":
+            M, N, K = x2.shape[0] * t, self.weight.shape[0], x2.shape[1]
+            if not comm_gemm.fused_supported(M, N, K, t):
+                return None
+            return comm_gemm.column_parallel_linear(x2.contiguous(), self.weight, bias_now, act, topo.tp_group)
+        M, N, K = x2.shape[0], self.weight.shape[0], x2.shape[1]
+        if not comm_gemm.fused_supported(M, N, K, t) or act is not None:
+            return None
+        return comm_gemm.row_parallel_linear(x2.contiguous(), self.weight, bias_now, None, topo.tp_group)
 
     def extra_repr(self) -> str:
         return "in_features={}, out_features={}, bias={}, parallel={}".format(

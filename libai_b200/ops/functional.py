@@ -283,9 +283,54 @@ class _FlashAttnFn(torch.autograd.Function):
     def backward(ctx, go):
         ext = load_ext()
         q, k, v, o, lse = ctx.saved_tensors
-        dq, dk, dv = ext.attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale)
+        dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale)
         count_launch(3)
         return dq, dk, dv, None, None
+
+
+class _FlashAttnPackedFn(torch.autograd.Function):
+    """Self-attention straight from the packed QKV projection ``[b, s, a, 3d]`` (per-head ``[q|k|v]``):
+    the kernels read q/k/v through strided TMA maps and the backward writes one packed ``dqkv`` – no
+    slicing, no gradient accumulation kernels around the attention."""
+
+    @staticmethod
+    def forward(ctx, qkv, causal, scale):
+        ext = load_ext()
+        d = qkv.shape[-1] // 3
+        v4 = qkv.permute(0, 2, 1, 3)
+        q, k, v = v4[..., :d], v4[..., d : 2 * d], v4[..., 2 * d :]
+        o, lse = ext.attn_fwd(q, k, v, causal, scale)
+        count_launch()
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.causal, ctx.scale = causal, scale
+        return o.permute(0, 2, 1, 3)  # [b, s, a, d] contiguous
+
+    @staticmethod
+    def backward(ctx, go):
+        ext = load_ext()
+        qkv, o, lse = ctx.saved_tensors
+        d = qkv.shape[-1] // 3
+        v4 = qkv.permute(0, 2, 1, 3)
+        q, k, v = v4[..., :d], v4[..., d : 2 * d], v4[..., 2 * d :]
+        _, _, _, dqkv = ext.attn_bwd(go.permute(0, 2, 1, 3), q, k, v, o, lse, ctx.causal, ctx.scale)
+        count_launch(3)
+        return dqkv.view(qkv.shape), None, None
+
+
+def attention_qkvpacked_supported(qkv, mask, dropout_p, training) -> bool:
+    return (
+        use_native(qkv)
+        and qkv.dtype == torch.bfloat16
+        and mask is None
+        and (dropout_p == 0.0 or not training)
+        and qkv.shape[-1] // 3 in (64, 128)
+        and qkv.is_contiguous()
+    )
+
+
+def attention_qkvpacked(qkv, *, causal: bool, scale: float):
+    """qkv ``[b, s, a, 3d]`` → context ``[b, s, a, d]``."""
+    return _FlashAttnPackedFn.apply(qkv, causal, float(scale))
 
 
 def attention(q, k, v, *, causal: bool = False, scale: Optional[float] = None, mask=None, bias=None,

@@ -28,6 +28,7 @@ import torch
 import torch.distributed as dist
 
 from libai_b200.ops import count_launch, load_ext, use_native
+from libai_b200.ops import impl as ops_impl
 from libai_b200.parallel import state as pstate
 from libai_b200.utils import distributed as dutil
 
@@ -37,8 +38,10 @@ _ALIGN = 256  # elements; keeps every shard 1 KiB aligned for 128-bit vector acc
 class _Group:
     """Flat storage of one param group."""
 
-    def __init__(self, params: List[torch.nn.Parameter], dp_size: int, dp_rank: int, sharded: bool):
+    def __init__(self, params: List[torch.nn.Parameter], dp_size: int, dp_rank: int, sharded: bool,
+                 symm_ws=None, index: int = 0):
         self.params = params
+        self.symm = None
         self.dtype = params[0].dtype
         self.device = params[0].device
         assert all(p.dtype == self.dtype for p in params), "mixed dtypes inside one param group"
@@ -50,8 +53,17 @@ class _Group:
             n = (n + 7) // 8 * 8  # keep every parameter 16B/32B aligned inside the flat buffer
         chunk = _ALIGN * dp_size
         self.numel = (n + chunk - 1) // chunk * chunk
-        self.param_flat = torch.zeros(self.numel, dtype=self.dtype, device=self.device)
-        self.grad_flat = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        if symm_ws is not None:
+            # NVLink peer-mapped buffers: the fused ZeRO kernels read peers' gradients and write peers'
+            # parameters directly (K3/K4)
+            pbuf = symm_ws.buffer(("zero_param", index, self.numel), self.numel * params[0].element_size())
+            gbuf = symm_ws.buffer(("zero_grad", index, self.numel), self.numel * 4)
+            self.param_flat = pbuf.view(self.dtype, (self.numel,))
+            self.grad_flat = gbuf.view(torch.float32, (self.numel,))
+            self.symm = dict(ws=symm_ws, param=pbuf, grad=gbuf)
+        else:
+            self.param_flat = torch.zeros(self.numel, dtype=self.dtype, device=self.device)
+            self.grad_flat = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
         for p, off in zip(params, self.offsets):
             self.param_flat[off : off + p.numel()].copy_(p.data.reshape(-1))
             attrs = {k: getattr(p, k) for k in ("tp_dim", "tp_stride", "sequence_parallel", "init_index", "shared_from") if hasattr(p, k)}
@@ -93,6 +105,8 @@ class FlatOptimizer(torch.optim.Optimizer):
         self.skipped_steps = 0
         self.overlap_grad_sync = False
         self._synced = False
+        # ZeRO over NVLink peer memory: reduce-scatter / Adam / all-gather as fused kernels instead of NCCL
+        self.fused_zero_comm = True
 
     # ------------------------------------------------------------------ configuration
     def configure(self, *, zero_stage: int = 0, param_names: Optional[Dict[int, str]] = None,
@@ -112,12 +126,18 @@ class FlatOptimizer(torch.optim.Optimizer):
         topo = dutil.get_dist_util()
         sharded = self.zero_stage >= 1 and topo.data_parallel_size > 1
         self._groups = []
-        for g in self.param_groups:
+        for gi, g in enumerate(self.param_groups):
             params = [p for p in g["params"] if p.device.type != "meta" and p.requires_grad]
             if not params:
                 self._groups.append(None)
                 continue
-            fg = _Group(params, topo.data_parallel_size, topo.dp_rank, sharded)
+            ws = None
+            if (sharded and self.fused_zero_comm and params[0].is_cuda and params[0].dtype == torch.bfloat16
+                    and ops_impl() == "native" and topo.data_parallel_size <= 8):
+                from libai_b200.parallel.symm_mem import get_workspace
+
+                ws = get_workspace(topo.dp_group)
+            fg = _Group(params, topo.data_parallel_size, topo.dp_rank, sharded, symm_ws=ws, index=gi)
             for name in self.state_names:
                 fg.state[name] = torch.zeros(fg.hi - fg.lo, dtype=torch.float32, device=fg.device)
             self._groups.append(fg)
@@ -166,7 +186,17 @@ class FlatOptimizer(torch.optim.Optimizer):
                     if getattr(p, "shared_from", None) is not None or getattr(p, "is_tied_source", False):
                         dist.all_reduce(p.main_grad, group=topo.embedding_group)
             # (3) data parallel
-            if topo.dp_group is not None:
+            if topo.dp_group is not None and fg.symm is not None:
+                ext = load_ext()
+                ws = fg.symm["ws"]
+                scale = 1.0 / topo.data_parallel_size if self.dp_grad_reduce == "mean" else 1.0
+                if not hasattr(fg, "sq_partial"):
+                    fg.sq_partial = torch.zeros(1, dtype=torch.float32, device=fg.device)
+                fg.sq_partial.zero_()
+                ext.zero_reduce_scatter(fg.symm["grad"].peer_ptrs(0), ws.flags.peer_ptrs(0), fg.grad_shard(),
+                                        fg.sq_partial, fg.lo, fg.hi - fg.lo, scale, ws.world, ws.rank, ws.next_epoch())
+                count_launch()
+            elif topo.dp_group is not None:
                 if self.dp_grad_reduce == "mean":
                     fg.grad_flat.div_(topo.data_parallel_size)
                 if fg.sharded and fg.device.type == "cuda":
@@ -261,6 +291,9 @@ class FlatOptimizer(torch.optim.Optimizer):
             if fg is None:
                 continue
             scale = coef * self.grad_scale if coef is not None else None
+            if fg.symm is not None and hasattr(self, "_fused_zero_update"):
+                self._fused_zero_update(g, fg, self._step_count, scale)
+                continue
             self._update(g, fg, self._step_count, scale)
             if fg.sharded:
                 shard = fg.param_flat[fg.lo : fg.hi]
@@ -391,6 +424,22 @@ class AdamW(FlatOptimizer):
         master.add_(upd, alpha=-lr)
         if fg.master is not None:
             fg.param_flat[fg.lo : fg.hi].copy_(master)
+
+
+    def _fused_zero_update(self, group, fg, step, scale):
+        """AdamW on the owned slice + all-gather of the bf16 parameters by P2P stores, one kernel."""
+        ext = load_ext()
+        ws = fg.symm["ws"]
+        lr, (b1, b2), eps, wd = group["lr"], group["betas"], group["eps"], group["weight_decay"]
+        bc1, bc2 = (1.0 - b1 ** step, 1.0 - b2 ** step) if group.get("do_bias_correction", True) else (1.0, 1.0)
+        clip = scale if scale is not None else torch.ones((), dtype=torch.float32, device=fg.device)
+        ext.zero_adam_allgather(
+            fg.master, fg.grad_shard(), fg.state["exp_avg"], fg.state["exp_avg_sq"], fg.symm["param"].peer_ptrs(0),
+            ws.flags.peer_ptrs(0), ws.done_counter[0:1], clip.reshape(1).float(), fg.lo, fg.hi - fg.lo, float(lr),
+            float(b1), float(b2), float(eps), float(wd), float(bc1), float(bc2), bool(self.decoupled), ws.world, ws.rank,
+            ws.next_epoch(),
+        )
+        count_launch()
 
 
 class Adam(AdamW):

@@ -160,6 +160,8 @@ class DistributedTopology:
         # activations between TP blocks are sharded over tokens, col/row linears become
         # all-gather->GEMM / GEMM->reduce-scatter.
         self.sequence_parallel = bool(try_get_key(cfg, "sequence_parallel", default=False)) and tp > 1
+        # run the SP collectives inside the GEMM kernels (AG->GEMM / GEMM->RS over NVLink peer memory)
+        self.fused_tp_comm = bool(try_get_key(cfg, "fused_tp_comm", default=False)) and self.sequence_parallel
 
         # ---- layer → stage -------------------------------------------------------------
         self._layer_stage_ids = compute_layer_stage_ids(int(cfg.pipeline_num_layers), pp)

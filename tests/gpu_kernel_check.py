@@ -289,7 +289,7 @@ def main():
             e = [rel_err(o, ref)]
             go = torch.randn(B, S, A, D, device="cuda").bfloat16().permute(0, 2, 1, 3)
             ref.backward(go.float())
-            dq, dk, dv = ext.attn_bwd(go, q, k, v, o, lse, causal, scale)
+            dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, causal, scale)
             e += [rel_err(dq, qf.grad), rel_err(dk, kf.grad), rel_err(dv, vf.grad)]
             return {"ok": max(e) < 3e-2, "errs": e}
 
