@@ -15,6 +15,8 @@
 // the (MUFU-bound) softmax.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace lb {
 
 constexpr int ATT_BM = 128;   // queries per CTA
@@ -294,6 +296,258 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
 }  // namespace lb
 
+
+// =================================================================================================
+// Forward v2: P and O stay in tensor memory.
+//   * softmax threads write P (bf16) back into the S columns with tcgen05.st; the P·V MMA takes its A operand
+//     from TMEM (tcgen05.mma [d], [a_tmem], b_desc) – no shared-memory round trip, no proxy fence
+//   * O accumulates in TMEM across KV blocks; the running max is only advanced when it grows by more than 2^8
+//     ("lazy rescale"), in which case the softmax threads rescale O in place (tcgen05.ld → mul → tcgen05.st)
+//   * TMEM footprint 128 + D columns and 80 KB of shared memory at D = 64 → two CTAs per SM, whose
+//     softmax / MMA / TMA phases overlap each other
+// =================================================================================================
+namespace lb {
+
+template <int D>
+struct AttnCfg2 {
+  static constexpr int QK_CHUNKS = D / 64;
+  static constexpr int TILE_BYTES = ATT_BN * D * 2;
+  static constexpr int SMEM_BYTES = 5 * TILE_BYTES + 1024 + 256;   // Q + 2 x (K, V)
+  static constexpr uint32_t TMEM_COLS = 256;
+  static constexpr uint32_t S_COL = 0, O_COL = 128;                // P aliases S columns [0, 64)
+  static constexpr int MIN_CTAS = (D == 64) ? 2 : 1;
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, AttnCfg2<D>::MIN_CTAS)
+attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, AttnFwdParams p) {
+  using Cfg = AttnCfg2<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::TILE_BYTES;
+  uint8_t* sV = sK + 2 * Cfg::TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Cfg::TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;
+  uint64_t* p_full = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp_idx = threadIdx.x / 32, lane = threadIdx.x % 32;
+  // heavy (late) query blocks first: better tail behaviour under the causal mask
+  const int q_blk = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int q0 = q_blk * ATT_BM;
+  int nkv = (p.S + ATT_BN - 1) / ATT_BN;
+  if (p.causal) nkv = min(nkv, q_blk + 1);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp_idx == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, Cfg::TILE_BYTES);
+#pragma unroll
+      for (int c = 0; c < Cfg::QK_CHUNKS; ++c)
+        tma_load_4d(sQ + c * (ATT_BM * 128), &tmap_q, q_full, c * 64, q0, head, batch);
+      for (int j = 0; j < nkv; ++j) {
+        const int b = j & 1;
+        const uint32_t par = ((j >> 1) & 1) ^ 1;
+        mbar_wait(&k_empty[b], par);
+        mbar_arrive_expect_tx(&k_full[b], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < Cfg::QK_CHUNKS; ++c)
+          tma_load_4d(sK + b * Cfg::TILE_BYTES + c * (ATT_BN * 128), &tmap_k, &k_full[b], c * 64, j * ATT_BN, head, batch);
+        mbar_wait(&v_empty[b], par);
+        mbar_arrive_expect_tx(&v_full[b], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < Cfg::QK_CHUNKS; ++c)
+          tma_load_4d(sV + b * Cfg::TILE_BYTES + c * (ATT_BN * 128), &tmap_v, &v_full[b], c * 64, j * ATT_BN, head, batch);
+      }
+    }
+  } else if (warp_idx == 1) {
+    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BM, ATT_BN, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, D, false, true);
+    const uint32_t q_addr = smem_u32(sQ);
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < nkv; ++j) {
+      const int b = j & 1;
+      mbar_wait(&k_full[b], (j >> 1) & 1);
+      if (j > 0) mbar_wait(o_full, (j - 1) & 1);   // P·V of the previous block has retired: S/P columns are free
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t k_addr = smem_u32(sK + b * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk / 4) * (ATT_BM * 128) + (kk % 4) * 32;
+          umma_f16_ss(tmem_base + Cfg::S_COL, make_smem_desc_sw128(q_addr + off, 0, 1024),
+                      make_smem_desc_sw128(k_addr + off, 0, 1024), idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        umma_commit(&k_empty[b]);
+      }
+      __syncwarp();
+      mbar_wait(p_full, j & 1);
+      mbar_wait(&v_full[b], (j >> 1) & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t v_addr = smem_u32(sV + b * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+          // A = P from tensor memory: 16 bf16 per row = 8 columns per k-step
+          umma_f16_ts(tmem_base + Cfg::O_COL, tmem_base + Cfg::S_COL + kk * 8,
+                      make_smem_desc_sw128(v_addr + kk * (16 * 128), ATT_BN * 128, 1024), idesc_pv,
+                      (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&v_empty[b]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp_idx % 4;
+    const int r = quad * 32 + lane;
+    const int q_idx = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_off + Cfg::S_COL;
+    const uint32_t o_addr = tmem_base + lane_off + Cfg::O_COL;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after_sync();
+      const int k0 = j * ATT_BN;
+      const bool need_mask = (p.causal && j == q_blk) || (k0 + ATT_BN > p.S);
+      // ---- pass 1: row max (two 64-column halves, two loads in flight)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t t0[32], t1[32];
+        tmem_ld_32x32b_x32(s_addr + h * 64, t0);
+        tmem_ld_32x32b_x32(s_addr + h * 64 + 32, t1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x0 = __uint_as_float(t0[i]), x1 = __uint_as_float(t1[i]);
+          if (need_mask) {
+            const int k_a = k0 + h * 64 + i, k_b = k_a + 32;
+            if (k_a >= p.S || (p.causal && k_a > q_idx)) x0 = -INFINITY;
+            if (k_b >= p.S || (p.causal && k_b > q_idx)) x1 = -INFINITY;
+          }
+          mx = fmaxf(mx, fmaxf(x0, x1));
+        }
+      }
+      // ---- lazy rescale: only move the reference max when it grows by more than 2^8
+      const float m_cand = fmaxf(m_run, mx * p.scale_log2);
+      const bool bump = (m_cand - m_run > 8.0f) || (m_run == -INFINITY && m_cand != -INFINITY);
+      float alpha = 1.0f;
+      if (bump) {
+        alpha = exp2f(m_run - m_cand);   // 0 on the first block
+        m_run = m_cand;
+      }
+      const bool bump_any = __any_sync(0xffffffffu, bump && j > 0);
+      const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+      // ---- pass 2: P = exp2(s * scale - m) as bf16 back into the S columns
+      float rowsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < ATT_BN / 32; ++c) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(s_addr + c * 32, t);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float e0 = exp2f(__uint_as_float(t[i]) * p.scale_log2 - m_use);
+          float e1 = exp2f(__uint_as_float(t[i + 1]) * p.scale_log2 - m_use);
+          if (need_mask) {
+            const int kidx = k0 + c * 32 + i;
+            if (kidx >= p.S || (p.causal && kidx > q_idx)) e0 = 0.f;
+            if (kidx + 1 >= p.S || (p.causal && kidx + 1 > q_idx)) e1 = 0.f;
+          }
+          rowsum += e0 + e1;
+          packed[i / 2] = pack_bf16(e0, e1);
+        }
+        tmem_st_32x32b_x16(s_addr + c * 16, packed);
+      }
+      l_run = l_run * alpha + rowsum;
+      // ---- O *= alpha (rare): P·V of block j-1 has retired (the MMA warp waited for it before issuing S_j)
+      if (bump_any) {
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t t[32];
+          tmem_ld_32x32b_x32(o_addr + c * 32, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+          tmem_st_32x32b_x32(o_addr + c * 32, t);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l  →  [B, S, A, D]
+    mbar_wait(o_full, (nkv - 1) & 1);
+    tc_fence_after_sync();
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* orow = p.o + ((static_cast<size_t>(batch) * p.S + q_idx) * p.A + head) * D;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t t[32];
+      tmem_ld_32x32b_x32(o_addr + c * 32, t);
+      tmem_ld_wait();
+      if (q_idx < p.S) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          *reinterpret_cast<uint4*>(orow + c * 32 + i) = make_uint4(
+              pack_bf16(__uint_as_float(t[i]) * inv, __uint_as_float(t[i + 1]) * inv),
+              pack_bf16(__uint_as_float(t[i + 2]) * inv, __uint_as_float(t[i + 3]) * inv),
+              pack_bf16(__uint_as_float(t[i + 4]) * inv, __uint_as_float(t[i + 5]) * inv),
+              pack_bf16(__uint_as_float(t[i + 6]) * inv, __uint_as_float(t[i + 7]) * inv));
+        }
+      }
+    }
+    if (q_idx < p.S)
+      p.lse[(static_cast<size_t>(batch) * p.A + head) * p.S + q_idx] =
+          (m_run == -INFINITY) ? -INFINITY : (m_run + log2f(l_run)) * 0.6931471805599453f;
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace lb
+
 namespace {
 bool make_qkv_tmap(CUtensorMap* m, const void* ptr, int B, int A, int S, int D, const long* st) {
   // dims innermost first: {D, S, A, B}; st = {batch, head, seq} strides in elements
@@ -304,8 +558,34 @@ bool make_qkv_tmap(CUtensorMap* m, const void* ptr, int B, int A, int S, int D, 
 }
 
 template <int D>
+cudaError_t launch_fwd_v2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                          const lb::AttnFwdParams& p, cudaStream_t s) {
+  using Cfg = lb::AttnCfg2<D>;
+  auto kern = lb::attn_fwd_v2_kernel<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.S + lb::ATT_BM - 1) / lb::ATT_BM, p.A, p.B);
+  kern<<<grid, lb::ATT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, p);
+  return cudaGetLastError();
+}
+
+int attn_fwd_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LIBAI_B200_ATTN_FWD");
+    v = (e != nullptr && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
+template <int D>
 cudaError_t launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const lb::AttnFwdParams& p,
                        cudaStream_t s) {
+  if (attn_fwd_version() == 2) return launch_fwd_v2<D>(tq, tk, tv, p, s);
   using Cfg = lb::AttnCfg<D>;
   auto kern = lb::attn_fwd_kernel<D>;
   static bool configured = false;
@@ -360,7 +640,10 @@ struct AttnBwdCfg {
   static constexpr int TILE_BYTES = 128 * D * 2;
   static constexpr int PS_BYTES = 128 * 128 * 2;
   static constexpr int QST = (D == 64) ? 2 : 1;
-  static constexpr int SMEM_BYTES = 2 * TILE_BYTES /*K,V*/ + 2 * QST * TILE_BYTES /*Q,dO*/ + 2 * PS_BYTES + 1024 + 256;
+  static constexpr bool DQ_BULK = (D == 64);            // dQ via smem staging + TMA reduce-add (fp32)
+  static constexpr int DQ_ROW_FLOATS = D + 4;            // padded staging rows (conflict-free 16-byte stores)
+  static constexpr int DQ_STAGE_BYTES = DQ_BULK ? 128 * DQ_ROW_FLOATS * 4 : 0;
+  static constexpr int SMEM_BYTES = 2 * TILE_BYTES /*K,V*/ + 2 * QST * TILE_BYTES /*Q,dO*/ + 2 * PS_BYTES + DQ_STAGE_BYTES + 1024 + 256;
   static constexpr uint32_t S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + D;
   static constexpr uint32_t DQ_COL = (D == 64) ? 384 : 0;  // D = 128: dQ aliases the S columns
 };
@@ -392,7 +675,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sDO = sQ + QST * Cfg::TILE_BYTES;          // QST stages
   uint8_t* sP = sDO + QST * Cfg::TILE_BYTES;
   uint8_t* sDS = sP + Cfg::PS_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + Cfg::PS_BYTES);
+  float* sDQ = reinterpret_cast<float*>(sDS + Cfg::PS_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + Cfg::PS_BYTES + Cfg::DQ_STAGE_BYTES);
   uint64_t* kv_full = bars;          // 1
   uint64_t* qdo_full = bars + 1;     // 2
   uint64_t* qdo_empty = bars + 3;    // 2
@@ -570,6 +854,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // ---- dQ block: TMEM -> fp32 atomics
       mbar_wait(dq_full, it & 1);
       tc_fence_after_sync();
+      if constexpr (Cfg::DQ_BULK) {
+        // dQ row (D fp32) -> padded shared staging row -> one TMA reduce-add per thread into dq_accum
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous iteration's row consumed
+        float* srow = sDQ + r * Cfg::DQ_ROW_FLOATS;
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t t[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DQ_COL + c * 32, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(srow + c * 32 + k * 4) =
+                make_float4(__uint_as_float(t[k * 4]), __uint_as_float(t[k * 4 + 1]), __uint_as_float(t[k * 4 + 2]),
+                            __uint_as_float(t[k * 4 + 3]));
+        }
+        fence_proxy_async();
+        if (q_ok) {
+          float* dst = p.dq_accum + (bh * p.S + q_idx) * D;
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;\n" ::"l"(dst),
+                       "r"(smem_u32(srow)), "r"(D * 4)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+      } else {
       float* dq_row = p.dq_accum + (bh * p.S + q_idx) * D;
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
@@ -586,9 +894,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
       }
+      }
       tc_fence_before_sync();
       mbar_arrive(dq_empty);
     }
+    if (Cfg::DQ_BULK) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
     // ---- dV / dK accumulators: thread r <-> key row r
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();

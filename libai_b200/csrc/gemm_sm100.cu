@@ -15,6 +15,7 @@
 #include "common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -37,6 +38,8 @@ struct GemmParams {
   void* out;                  // bf16 or fp32 [M, ldo]
   __nv_bfloat16* pre_out;     // optional pre-activation copy (bf16)
   int ldo;                    // leading dimension of out (elements)
+  int rmw;                    // EPI_F32: out += acc (plain read-modify-write; a tile is owned by one CTA)
+  int bulk_reduce;            // EPI_ATOMIC_F32: cp.reduce.async.bulk (TMA reduce-add) instead of red.global
 };
 
 // Fused collective modes (tensor parallel): peer pointers refer to NVLink peer-mapped symmetric memory.
@@ -85,8 +88,10 @@ struct StageCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NUM_STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
-  static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int NUM_STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : (BLOCK_N == 128 ? 6 : 8));
+  static constexpr int EPI_ROW_FLOATS = 36;             // 32 payload + 4 pad: conflict-free 16-byte stores
+  static constexpr int EPI_STAGE_BYTES = 128 * EPI_ROW_FLOATS * 4;  // fp32 staging rows for the bulk-reduce epilogue
+  static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 };
 
@@ -98,7 +103,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr int NS = Cfg::NUM_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + NS * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES + Cfg::EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + NS;
   uint64_t* tmem_full = empty_bar + NS;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -339,16 +345,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              if (col0 + i < p.N) *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (col0 + i < p.N) {
+                float4 o4 = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (p.rmw) {
+                  const float4 old = *reinterpret_cast<const float4*>(orow + i);
+                  o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
+                }
+                *reinterpret_cast<float4*>(orow + i) = o4;
+              }
             }
           } else {
             float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+            if (p.bulk_reduce) {
+              // split-K partial sums: every thread stages its 32 fp32 values (128 B) in shared memory and hands
+              // them to the TMA unit as one reduce-add; L2 performs the accumulation per line instead of per float
+              float* srow = epi_stage + (quad * 32 + lane) * Cfg::EPI_ROW_FLOATS;  // padded rows: no bank conflicts
+              asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous chunk of this row consumed
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (col0 + i < p.N) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(orow + i), "f"(v[i]), "f"(v[i + 1]),
-                             "f"(v[i + 2]), "f"(v[i + 3])
-                             : "memory");
+              for (int k = 0; k < 8; ++k)
+                *reinterpret_cast<float4*>(srow + k * 4) = make_float4(v[k * 4], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
+              fence_proxy_async();
+              const int ncols = min(32, p.N - col0);
+              asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;\n" ::"l"(orow),
+                           "r"(smem_u32(srow)), "r"(ncols * 4)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                if (col0 + i < p.N) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(orow + i), "f"(v[i]), "f"(v[i + 1]),
+                               "f"(v[i + 2]), "f"(v[i + 3])
+                               : "memory");
+                }
               }
             }
           }
@@ -420,6 +449,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   }
 
+  if (EPI == EPI_ATOMIC_F32) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // reductions landed
   tc_fence_before_sync();
   __syncthreads();
   if (warp_idx == 1) {
@@ -516,6 +546,8 @@ cudaError_t launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, cons
   switch (bn) {
     case 256:
       return launch_cfg<256, AMN, BMN, EPI>(ta, tb, p, cp, grid, s);
+    case 192:
+      return launch_cfg<192, AMN, BMN, EPI>(ta, tb, p, cp, grid, s);
     case 128:
       return launch_cfg<128, AMN, BMN, EPI>(ta, tb, p, cp, grid, s);
     default:
@@ -545,13 +577,15 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   }
   if (bn == 0) {
     double best = 1e30;
-    const int cands[3] = {256, 128, 64};
+    const int cands[4] = {256, 192, 128, 64};
     for (int c : cands) {
       if (c > 64 && N <= c / 2) continue;
       const long tiles = (long)m_blocks * ((N + c - 1) / c);
       const long waves = (tiles + sms - 1) / sms;
-      // cost ~ waves * per-tile time (proportional to c, with a small fixed overhead per tile)
-      const double cost = (double)waves * (c * (c == 256 ? 1.0 : (c == 128 ? 1.08 : 1.2)) + 24.0);
+      // cost ~ waves * per-tile time (proportional to c, narrower tiles pay more shared-memory traffic per
+      // flop, plus a fixed prologue/epilogue overhead per tile)
+      const double eff = c == 256 ? 1.0 : (c == 192 ? 1.03 : (c == 128 ? 1.08 : 1.2));
+      const double cost = (double)waves * (c * eff + 24.0);
       if (cost < best - 1e-9) {
         best = cost;
         bn = c;
@@ -580,6 +614,21 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   p.k_per_split = (k_blocks + splits - 1) / splits;
   p.k_splits = (k_blocks + p.k_per_split - 1) / p.k_per_split;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.rmw = 0;
+  {
+    static int bulk = -1;
+    if (bulk < 0) {
+      const char* e = getenv("LIBAI_B200_WGRAD_BULK");
+      bulk = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    p.bulk_reduce = bulk;
+  }
+  if (epi == 2 && p.k_splits == 1) {
+    // a single K partition owns the whole tile: accumulate with a plain read-modify-write instead of
+    // L2 atomics (fp32 atomics are throughput-limited at the L2 slices)
+    epi = 1;
+    p.rmw = 1;
+  }
   p.act = act;
   p.out = out;
   p.pre_out = reinterpret_cast<__nv_bfloat16*>(pre_out);

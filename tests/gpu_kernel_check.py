@@ -113,7 +113,7 @@ def main():
 
     # ------------------------------------------------------------------ GEMM correctness
     for layout in (0, 1, 2):
-        for bn in (64, 128, 256):
+        for bn in (64, 128, 192, 256):
             check_gemm(ext, layout, 256, 512, 256, bn=bn)
     check_gemm(ext, 0, 1000, 1304, 1032)          # ragged M, N, K tails
     check_gemm(ext, 1, 1000, 1304, 1032)
