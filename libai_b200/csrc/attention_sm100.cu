@@ -42,6 +42,7 @@ struct AttnFwdParams {
   int causal;
   float scale_log2;   // scale * log2(e)
   float scale;
+  const int* kv_lens; // optional [B]: number of valid keys per sample (right-padded batches)
 };
 
 template <int D>
@@ -74,7 +75,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int q_blk = blockIdx.x;
   const int head = blockIdx.y, batch = blockIdx.z;
   const int q0 = q_blk * ATT_BM;
-  int nkv = (p.S + ATT_BN - 1) / ATT_BN;
+  const int kv_len = p.kv_lens != nullptr ? max(1, min(p.S, p.kv_lens[batch])) : p.S;
+  int nkv = (kv_len + ATT_BN - 1) / ATT_BN;
   if (p.causal) nkv = min(nkv, q_blk + 1);
 
   if (threadIdx.x == 0) {
@@ -204,7 +206,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_after_sync();
       const uint32_t s_addr = tmem_base + lane_off + b * ATT_BN;
       const int k0 = j * ATT_BN;
-      const bool need_mask = (p.causal && j == q_blk) || (k0 + ATT_BN > p.S);
+      const bool need_mask = (p.causal && j == q_blk) || (k0 + ATT_BN > kv_len);
       // ---- pass 1: row max
       float mx = -INFINITY;
 #pragma unroll
@@ -217,7 +219,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           float x = __uint_as_float(t[i]);
           if (need_mask) {
             const int kidx = k0 + c * 32 + i;
-            if (kidx >= p.S || (p.causal && kidx > q_idx)) x = -INFINITY;
+            if (kidx >= kv_len || (p.causal && kidx > q_idx)) x = -INFINITY;
           }
           mx = fmaxf(mx, x);
         }
@@ -241,8 +243,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           float e0 = exp2f(x0 * p.scale_log2 - m_use), e1 = exp2f(x1 * p.scale_log2 - m_use);
           if (need_mask) {
             const int kidx = k0 + c * 32 + i;
-            if (kidx >= p.S || (p.causal && kidx > q_idx)) e0 = 0.f;
-            if (kidx + 1 >= p.S || (p.causal && kidx + 1 > q_idx)) e1 = 0.f;
+            if (kidx >= kv_len || (p.causal && kidx > q_idx)) e0 = 0.f;
+            if (kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) e1 = 0.f;
           }
           rowsum += e0 + e1;
           packed[i / 2] = pack_bf16(e0, e1);
@@ -344,7 +346,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const int q_blk = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);
   const int head = blockIdx.y, batch = blockIdx.z;
   const int q0 = q_blk * ATT_BM;
-  int nkv = (p.S + ATT_BN - 1) / ATT_BN;
+  const int kv_len = p.kv_lens != nullptr ? max(1, min(p.S, p.kv_lens[batch])) : p.S;
+  int nkv = (kv_len + ATT_BN - 1) / ATT_BN;
   if (p.causal) nkv = min(nkv, q_blk + 1);
 
   if (threadIdx.x == 0) {
@@ -443,7 +446,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
       const int k0 = j * ATT_BN;
-      const bool need_mask = (p.causal && j == q_blk) || (k0 + ATT_BN > p.S);
+      const bool need_mask = (p.causal && j == q_blk) || (k0 + ATT_BN > kv_len);
       // ---- pass 1: row max (two 64-column halves, two loads in flight)
       float mx = -INFINITY;
 #pragma unroll
@@ -457,8 +460,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           float x0 = __uint_as_float(t0[i]), x1 = __uint_as_float(t1[i]);
           if (need_mask) {
             const int k_a = k0 + h * 64 + i, k_b = k_a + 32;
-            if (k_a >= p.S || (p.causal && k_a > q_idx)) x0 = -INFINITY;
-            if (k_b >= p.S || (p.causal && k_b > q_idx)) x1 = -INFINITY;
+            if (k_a >= kv_len || (p.causal && k_a > q_idx)) x0 = -INFINITY;
+            if (k_b >= kv_len || (p.causal && k_b > q_idx)) x1 = -INFINITY;
           }
           mx = fmaxf(mx, fmaxf(x0, x1));
         }
@@ -487,8 +490,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           float e1 = exp2f(__uint_as_float(t[i + 1]) * p.scale_log2 - m_use);
           if (need_mask) {
             const int kidx = k0 + c * 32 + i;
-            if (kidx >= p.S || (p.causal && kidx > q_idx)) e0 = 0.f;
-            if (kidx + 1 >= p.S || (p.causal && kidx + 1 > q_idx)) e1 = 0.f;
+            if (kidx >= kv_len || (p.causal && kidx > q_idx)) e0 = 0.f;
+            if (kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) e1 = 0.f;
           }
           rowsum += e0 + e1;
           packed[i / 2] = pack_bf16(e0, e1);
@@ -602,7 +605,7 @@ cudaError_t launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 
 extern "C" int lb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int A, int S, int D,
                            const long* q_strides, const long* k_strides, const long* v_strides, int causal, float scale,
-                           cudaStream_t s) {
+                           const int* kv_lens, cudaStream_t s) {
   if (D != 64 && D != 128) return -1;
   for (int i = 0; i < 3; ++i)
     if ((q_strides[i] % 8) || (k_strides[i] % 8) || (v_strides[i] % 8)) return -3;
@@ -619,6 +622,7 @@ extern "C" int lb_attn_fwd(const void* q, const void* k, const void* v, void* o,
   p.causal = causal;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.kv_lens = kv_lens;
   cudaError_t e = (D == 64) ? launch_fwd<64>(tq, tk, tv, p, s) : launch_fwd<128>(tq, tk, tv, p, s);
   return (int)e;
 }
@@ -658,6 +662,7 @@ struct AttnBwdParams {
   int B, A, S;
   int causal;
   float scale, scale_log2;
+  const int* kv_lens;   // optional [B]
 };
 
 template <int D>
@@ -691,6 +696,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int warp_idx = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int kv_blk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
   const int k0 = kv_blk * 128;
+  const int kv_len = p.kv_lens != nullptr ? max(1, min(p.S, p.kv_lens[batch])) : p.S;
   const int nq = (p.S + 127) / 128;
   const int i_begin = p.causal ? kv_blk : 0;
   const int iters = nq - i_begin;
@@ -811,7 +817,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const bool q_ok = q_idx < p.S;
       const float lse2 = q_ok ? p.lse[bh * p.S + q_idx] * 1.4426950408889634f : 0.f;
       const float delta = q_ok ? p.delta[bh * p.S + q_idx] : 0.f;
-      const bool need_mask = (p.causal && q_blk == kv_blk) || (k0 + 128 > p.S) || (q_blk * 128 + 128 > p.S);
+      const bool need_mask = (p.causal && q_blk == kv_blk) || (k0 + 128 > kv_len) || (q_blk * 128 + 128 > p.S);
       mbar_wait(sdp_full, it & 1);
       tc_fence_after_sync();
       mbar_wait(pds_empty, (it & 1) ^ 1);
@@ -830,8 +836,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           float p1 = exp2f(__uint_as_float(ts[i + 1]) * p.scale_log2 - lse2);
           if (need_mask) {
             const int kidx = k0 + c * 32 + i;
-            if (!q_ok || kidx >= p.S || (p.causal && kidx > q_idx)) p0 = 0.f;
-            if (!q_ok || kidx + 1 >= p.S || (p.causal && kidx + 1 > q_idx)) p1 = 0.f;
+            if (!q_ok || kidx >= kv_len || (p.causal && kidx > q_idx)) p0 = 0.f;
+            if (!q_ok || kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) p1 = 0.f;
           }
           const float d0 = p0 * (__uint_as_float(td[i]) - delta) * p.scale;
           const float d1 = p1 * (__uint_as_float(td[i + 1]) - delta) * p.scale;
@@ -991,7 +997,7 @@ cudaError_t launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o,
                            const float* lse, void* dq, void* dk, void* dv, float* delta, float* dq_accum, int B, int A,
                            int S, int D, const long* q_strides, const long* k_strides, const long* v_strides,
-                           const long* do_strides, int causal, float scale, cudaStream_t s) {
+                           const long* do_strides, int causal, float scale, const int* kv_lens, cudaStream_t s) {
   if (D != 64 && D != 128) return -1;
   for (int i = 0; i < 3; ++i)
     if ((q_strides[i] % 8) || (k_strides[i] % 8) || (v_strides[i] % 8) || (do_strides[i] % 8)) return -3;
@@ -1019,6 +1025,7 @@ extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const
   p.causal = causal;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.kv_lens = kv_lens;
   cudaError_t e = (D == 64) ? launch_bwd<64>(tq, tk, tv, tdo, p, s) : launch_bwd<128>(tq, tk, tv, tdo, p, s);
   if (e != cudaSuccess) return (int)e;
   const long nvec = rows * D / 4;

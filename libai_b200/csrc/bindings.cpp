@@ -48,11 +48,11 @@ int lb_p2p_allgather(const void* shard, const long* out_ptrs, const long* flag_p
                      long nbytes, int world, int rank, unsigned epoch, cudaStream_t s);
 int lb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int A, int S, int D,
                 const long* q_strides, const long* k_strides, const long* v_strides, int causal, float scale,
-                cudaStream_t s);
+                const int* kv_lens, cudaStream_t s);
 int lb_attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o, const float* lse,
                 void* dq, void* dk, void* dv, float* delta, float* dq_accum, int B, int A, int S, int D,
                 const long* q_strides, const long* k_strides, const long* v_strides, const long* do_strides, int causal,
-                float scale, cudaStream_t s);
+                float scale, const int* kv_lens, cudaStream_t s);
 }
 
 namespace {
@@ -299,7 +299,8 @@ Tensor sqnorm(const Tensor& x) {
 // ---- attention ----------------------------------------------------------------------------------------------
 // q, k, v: [B, A, S, D] views with arbitrary batch/head/seq strides (D contiguous). Output o is allocated as
 // [B, S, A, D] and returned as the [B, A, S, D] view, lse fp32 [B, A, S].
-std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, bool causal, double scale) {
+std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, bool causal, double scale,
+                                    const c10::optional<Tensor>& kv_lens) {
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(q.dim() == 4 && q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1, "attn_fwd: [B,A,S,D], D contiguous");
   const int B = (int)q.size(0), A = (int)q.size(1), S = (int)q.size(2), D = (int)q.size(3);
@@ -308,14 +309,20 @@ std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tens
   long qs[3] = {q.stride(0), q.stride(1), q.stride(2)};
   long ks[3] = {k.stride(0), k.stride(1), k.stride(2)};
   long vs[3] = {v.stride(0), v.stride(1), v.stride(2)};
+  const int* kvl = nullptr;
+  if (kv_lens.has_value() && kv_lens->defined()) {
+    TORCH_CHECK(kv_lens->scalar_type() == at::kInt && kv_lens->numel() == B && kv_lens->is_cuda(), "kv_lens: int32 cuda [B]");
+    kvl = kv_lens->data_ptr<int>();
+  }
   check(lb_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), B, A, S, D, qs, ks,
-                    vs, causal ? 1 : 0, (float)scale, cur_stream()),
+                    vs, causal ? 1 : 0, (float)scale, kvl, cur_stream()),
         "attn_fwd");
   return std::make_tuple(o.permute({0, 2, 1, 3}), lse);
 }
 
 std::tuple<Tensor, Tensor, Tensor, Tensor> attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor& v,
-                                            const Tensor& o, const Tensor& lse, bool causal, double scale) {
+                                            const Tensor& o, const Tensor& lse, bool causal, double scale,
+                                            const c10::optional<Tensor>& kv_lens) {
   c10::cuda::CUDAGuard guard(q.device());
   const int B = (int)q.size(0), A = (int)q.size(1), S = (int)q.size(2), D = (int)q.size(3);
   // gradients are produced in the packed [B, S, A, 3, D] layout so that the QKV dgrad/wgrad GEMMs read them directly
@@ -337,7 +344,8 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> attn_bwd(const Tensor& dout, const Te
   long ds[3] = {dout_c.stride(0), dout_c.stride(1), dout_c.stride(2)};
   check(lb_attn_bwd(dout_c.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(),
                     dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr<float>(), dq_acc.data_ptr<float>(), B, A,
-                    S, D, qs, ks, vs, ds, causal ? 1 : 0, (float)scale, cur_stream()),
+                    S, D, qs, ks, vs, ds, causal ? 1 : 0, (float)scale,
+                    (kv_lens.has_value() && kv_lens->defined()) ? kv_lens->data_ptr<int>() : nullptr, cur_stream()),
         "attn_bwd");
   return std::make_tuple(dq, dk, dv, dqkv);
 }
@@ -429,6 +437,6 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("ce_bwd(Tensor(a!) logits, Tensor labels, Tensor lse, Tensor gloss, int vocab_start) -> Tensor(a!)", &ce_bwd);
   m.def("fused_adamw(Tensor(a!) master, Tensor grad, Tensor(b!) m, Tensor(c!) v, Tensor? lp_out, Tensor scale, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, bool decoupled) -> ()", &fused_adamw);
   m.def("sqnorm(Tensor x) -> Tensor", &sqnorm);
-  m.def("attn_fwd(Tensor q, Tensor k, Tensor v, bool causal, float scale) -> (Tensor, Tensor)", &attn_fwd);
-  m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor o, Tensor lse, bool causal, float scale) -> (Tensor, Tensor, Tensor, Tensor)", &attn_bwd);
+  m.def("attn_fwd(Tensor q, Tensor k, Tensor v, bool causal, float scale, Tensor? kv_lens) -> (Tensor, Tensor)", &attn_fwd);
+  m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor o, Tensor lse, bool causal, float scale, Tensor? kv_lens) -> (Tensor, Tensor, Tensor, Tensor)", &attn_bwd);
 }

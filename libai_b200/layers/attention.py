@@ -34,6 +34,25 @@ class AttnMaskType(enum.Enum):
     causal = 2
 
 
+class KeyPaddingMask:
+    """Padding mask of a right-padded batch.
+
+    Carries the per-sample number of valid keys (``lengths``, int32 ``[b]``) for the flash-attention
+    kernel and builds the reference's dense ``[b, 1, s, s]`` mask (``m_i * m_j``, reference
+    libai/models/bert_model.py:36-48) on demand for the reference math."""
+
+    def __init__(self, mask_2d: torch.Tensor):
+        self.mask_2d = mask_2d
+        self.lengths = mask_2d.to(torch.int32).sum(dim=-1).to(torch.int32).contiguous()
+        self._dense = None
+
+    def dense(self) -> torch.Tensor:
+        if self._dense is None:
+            m = self.mask_2d.to(torch.int8)
+            self._dense = (m.unsqueeze(1) * m.unsqueeze(2)).unsqueeze(1)
+        return self._dense
+
+
 class MultiheadAttention(nn.Module):
     def __init__(
         self,
@@ -117,14 +136,16 @@ class MultiheadAttention(nn.Module):
                 raise ValueError("past_key_value and encoder_states cannot be None at the same time.")
         else:
             qkv_packed = self.query_key_value(hidden_states).view(bsz, -1, a, 3 * d)
+            kv_lens = attention_mask.lengths if isinstance(attention_mask, KeyPaddingMask) else None
             if (
                 past_key_value is None and not use_cache
-                and (attention_mask is None)
-                and OF.attention_qkvpacked_supported(qkv_packed, attention_mask, self.attention_dropout_prob, self.training)
+                and (attention_mask is None or kv_lens is not None)
+                and OF.attention_qkvpacked_supported(qkv_packed, None, self.attention_dropout_prob, self.training)
             ):
                 # fast path: flash attention directly on the packed projection
                 context = OF.attention_qkvpacked(
-                    qkv_packed, causal=self.attn_mask_type == AttnMaskType.causal, scale=self.softmax_scale
+                    qkv_packed, causal=self.attn_mask_type == AttnMaskType.causal, scale=self.softmax_scale,
+                    kv_lens=kv_lens,
                 ).reshape(bsz, -1, a * d)
                 if sp and hidden_states.dim() == 2:
                     context = context.reshape(-1, a * d)
@@ -139,6 +160,8 @@ class MultiheadAttention(nn.Module):
         if use_cache:
             past_key_value = (key, value)
 
+        if isinstance(attention_mask, KeyPaddingMask):
+            attention_mask = attention_mask.dense()
         causal = (
             self.attn_mask_type == AttnMaskType.causal
             and attention_mask is None

@@ -273,7 +273,7 @@ class _FlashAttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, causal, scale):
         ext = load_ext()
-        o, lse = ext.attn_fwd(q, k, v, causal, scale)
+        o, lse = ext.attn_fwd(q, k, v, causal, scale, None)
         count_launch()
         ctx.save_for_backward(q, k, v, o, lse)
         ctx.causal, ctx.scale = causal, scale
@@ -283,7 +283,7 @@ class _FlashAttnFn(torch.autograd.Function):
     def backward(ctx, go):
         ext = load_ext()
         q, k, v, o, lse = ctx.saved_tensors
-        dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale)
+        dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale, None)
         count_launch(3)
         return dq, dk, dv, None, None
 
@@ -294,27 +294,27 @@ class _FlashAttnPackedFn(torch.autograd.Function):
     slicing, no gradient accumulation kernels around the attention."""
 
     @staticmethod
-    def forward(ctx, qkv, causal, scale):
+    def forward(ctx, qkv, causal, scale, kv_lens):
         ext = load_ext()
         d = qkv.shape[-1] // 3
         v4 = qkv.permute(0, 2, 1, 3)
         q, k, v = v4[..., :d], v4[..., d : 2 * d], v4[..., 2 * d :]
-        o, lse = ext.attn_fwd(q, k, v, causal, scale)
+        o, lse = ext.attn_fwd(q, k, v, causal, scale, kv_lens)
         count_launch()
-        ctx.save_for_backward(qkv, o, lse)
+        ctx.save_for_backward(qkv, o, lse, kv_lens)
         ctx.causal, ctx.scale = causal, scale
         return o.permute(0, 2, 1, 3)  # [b, s, a, d] contiguous
 
     @staticmethod
     def backward(ctx, go):
         ext = load_ext()
-        qkv, o, lse = ctx.saved_tensors
+        qkv, o, lse, kv_lens = ctx.saved_tensors
         d = qkv.shape[-1] // 3
         v4 = qkv.permute(0, 2, 1, 3)
         q, k, v = v4[..., :d], v4[..., d : 2 * d], v4[..., 2 * d :]
-        _, _, _, dqkv = ext.attn_bwd(go.permute(0, 2, 1, 3), q, k, v, o, lse, ctx.causal, ctx.scale)
+        _, _, _, dqkv = ext.attn_bwd(go.permute(0, 2, 1, 3), q, k, v, o, lse, ctx.causal, ctx.scale, kv_lens)
         count_launch(3)
-        return dqkv.view(qkv.shape), None, None
+        return dqkv.view(qkv.shape), None, None, None
 
 
 def attention_qkvpacked_supported(qkv, mask, dropout_p, training) -> bool:
@@ -328,9 +328,10 @@ def attention_qkvpacked_supported(qkv, mask, dropout_p, training) -> bool:
     )
 
 
-def attention_qkvpacked(qkv, *, causal: bool, scale: float):
-    """qkv ``[b, s, a, 3d]`` → context ``[b, s, a, d]``."""
-    return _FlashAttnPackedFn.apply(qkv, causal, float(scale))
+def attention_qkvpacked(qkv, *, causal: bool, scale: float, kv_lens=None):
+    """qkv ``[b, s, a, 3d]`` → context ``[b, s, a, d]``; ``kv_lens`` (int32 ``[b]``): valid keys per sample
+    of a right-padded batch (keys beyond it are masked inside the kernel)."""
+    return _FlashAttnPackedFn.apply(qkv, causal, float(scale), kv_lens)
 
 
 def attention(q, k, v, *, causal: bool = False, scale: Optional[float] = None, mask=None, bias=None,

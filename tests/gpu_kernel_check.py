@@ -283,13 +283,13 @@ def main():
             v4 = qkv.view(B, S, A, 3 * D).permute(0, 2, 1, 3)
             q, k, v = v4[..., :D], v4[..., D:2 * D], v4[..., 2 * D:]
             scale = 1.0 / math.sqrt(D)
-            o, lse = ext.attn_fwd(q, k, v, causal, scale)
+            o, lse = ext.attn_fwd(q, k, v, causal, scale, None)
             qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
             ref = attention_ref(qf, kf, vf, causal=causal, scale=scale, fill=-1e30)
             e = [rel_err(o, ref)]
             go = torch.randn(B, S, A, D, device="cuda").bfloat16().permute(0, 2, 1, 3)
             ref.backward(go.float())
-            dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, causal, scale)
+            dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, causal, scale, None)
             e += [rel_err(dq, qf.grad), rel_err(dk, kf.grad), rel_err(dv, vf.grad)]
             return {"ok": max(e) < 3e-2, "errs": e}
 
@@ -302,10 +302,10 @@ def main():
             v4 = qkv.permute(0, 2, 1, 3)
             q, k, v = v4[..., :D], v4[..., D:2 * D], v4[..., 2 * D:]
             scale = 0.125
-            ms = timeit(lambda: ext.attn_fwd(q, k, v, True, scale))
-            o, lse = ext.attn_fwd(q, k, v, True, scale)
+            ms = timeit(lambda: ext.attn_fwd(q, k, v, True, scale, None))
+            o, lse = ext.attn_fwd(q, k, v, True, scale, None)
             go = torch.randn(B, S, A, D, device="cuda").bfloat16().permute(0, 2, 1, 3)
-            msb = timeit(lambda: ext.attn_bwd(go, q, k, v, o, lse, True, scale))
+            msb = timeit(lambda: ext.attn_bwd(go, q, k, v, o, lse, True, scale, None))
             flops = 4.0 * B * A * S * S * D / 2
             qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
             sd = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qc, kc, vc, is_causal=True))
