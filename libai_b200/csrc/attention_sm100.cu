@@ -15,6 +15,8 @@
 // the (MUFU-bound) softmax.
 #include "common.cuh"
 
+#include <type_traits>
+
 #include <cstdlib>
 
 namespace lb {
@@ -226,7 +228,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m_run - m_use);   // m_run = -inf -> 0
+      const float alpha = fast_exp2(m_run - m_use);   // m_run = -inf -> 0
       // ---- wait for the P buffer to be free, then pass 2: p = exp2(s*scale - m), write bf16 to swizzled smem
       mbar_wait(&p_empty[pb], ((j / PST) & 1) ^ 1);
       uint8_t* prow = sP + pb * Cfg::P_BYTES + r * 128;
@@ -240,7 +242,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float x0 = __uint_as_float(t[i]), x1 = __uint_as_float(t[i + 1]);
-          float e0 = exp2f(x0 * p.scale_log2 - m_use), e1 = exp2f(x1 * p.scale_log2 - m_use);
+          float e0 = fast_exp2(x0 * p.scale_log2 - m_use), e1 = fast_exp2(x1 * p.scale_log2 - m_use);
           if (need_mask) {
             const int kidx = k0 + c * 32 + i;
             if (kidx >= kv_len || (p.causal && kidx > q_idx)) e0 = 0.f;
@@ -448,56 +450,69 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const int k0 = j * ATT_BN;
       const bool need_mask = (p.causal && j == q_blk) || (k0 + ATT_BN > kv_len);
       // ---- pass 1: row max (two 64-column halves, two loads in flight)
+      // (the masked / unmasked variants are separate code copies: a per-element `if (need_mask)` costs a
+      //  BSSY/BRA/BSYNC triple per element pair - 40% of the instructions of this loop in the first profile)
       float mx = -INFINITY;
+      auto pass1 = [&](auto mask_tag) {
+        constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t t0[32], t1[32];
-        tmem_ld_32x32b_x32(s_addr + h * 64, t0);
-        tmem_ld_32x32b_x32(s_addr + h * 64 + 32, t1);
-        tmem_ld_wait();
+        for (int h = 0; h < 2; ++h) {
+          uint32_t t0[32], t1[32];
+          tmem_ld_32x32b_x32(s_addr + h * 64, t0);
+          tmem_ld_32x32b_x32(s_addr + h * 64 + 32, t1);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x0 = __uint_as_float(t0[i]), x1 = __uint_as_float(t1[i]);
-          if (need_mask) {
-            const int k_a = k0 + h * 64 + i, k_b = k_a + 32;
-            if (k_a >= kv_len || (p.causal && k_a > q_idx)) x0 = -INFINITY;
-            if (k_b >= kv_len || (p.causal && k_b > q_idx)) x1 = -INFINITY;
+          for (int i = 0; i < 32; ++i) {
+            float x0 = __uint_as_float(t0[i]), x1 = __uint_as_float(t1[i]);
+            if constexpr (MASK) {
+              const int k_a = k0 + h * 64 + i, k_b = k_a + 32;
+              if (k_a >= kv_len || (p.causal && k_a > q_idx)) x0 = -INFINITY;
+              if (k_b >= kv_len || (p.causal && k_b > q_idx)) x1 = -INFINITY;
+            }
+            mx = fmaxf(mx, fmaxf(x0, x1));
           }
-          mx = fmaxf(mx, fmaxf(x0, x1));
         }
-      }
+      };
+      if (need_mask) pass1(std::true_type{}); else pass1(std::false_type{});
       // ---- lazy rescale: only move the reference max when it grows by more than 2^8
       const float m_cand = fmaxf(m_run, mx * p.scale_log2);
       const bool bump = (m_cand - m_run > 8.0f) || (m_run == -INFINITY && m_cand != -INFINITY);
       float alpha = 1.0f;
       if (bump) {
-        alpha = exp2f(m_run - m_cand);   // 0 on the first block
+        alpha = fast_exp2(m_run - m_cand);   // 0 on the first block
         m_run = m_cand;
       }
       const bool bump_any = __any_sync(0xffffffffu, bump && j > 0);
       const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
       // ---- pass 2: P = exp2(s * scale - m) as bf16 back into the S columns
       float rowsum = 0.f;
+      auto pass2 = [&](auto mask_tag) {
+        constexpr bool MASK = decltype(mask_tag)::value;
+        float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < ATT_BN / 32; ++c) {
-        uint32_t t[32];
-        tmem_ld_32x32b_x32(s_addr + c * 32, t);
-        tmem_ld_wait();
-        uint32_t packed[16];
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+          uint32_t t[32];
+          tmem_ld_32x32b_x32(s_addr + c * 32, t);
+          tmem_ld_wait();
+          uint32_t packed[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float e0 = exp2f(__uint_as_float(t[i]) * p.scale_log2 - m_use);
-          float e1 = exp2f(__uint_as_float(t[i + 1]) * p.scale_log2 - m_use);
-          if (need_mask) {
-            const int kidx = k0 + c * 32 + i;
-            if (kidx >= kv_len || (p.causal && kidx > q_idx)) e0 = 0.f;
-            if (kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) e1 = 0.f;
+          for (int i = 0; i < 32; i += 2) {
+            float e0 = fast_exp2(__uint_as_float(t[i]) * p.scale_log2 - m_use);
+            float e1 = fast_exp2(__uint_as_float(t[i + 1]) * p.scale_log2 - m_use);
+            if constexpr (MASK) {
+              const int kidx = k0 + c * 32 + i;
+              if (kidx >= kv_len || (p.causal && kidx > q_idx)) e0 = 0.f;
+              if (kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) e1 = 0.f;
+            }
+            rs0 += e0;   // two independent accumulation chains
+            rs1 += e1;
+            packed[i / 2] = pack_bf16(e0, e1);
           }
-          rowsum += e0 + e1;
-          packed[i / 2] = pack_bf16(e0, e1);
+          tmem_st_32x32b_x16(s_addr + c * 16, packed);
         }
-        tmem_st_32x32b_x16(s_addr + c * 16, packed);
-      }
+        rowsum = rs0 + rs1;
+      };
+      if (need_mask) pass2(std::true_type{}); else pass2(std::false_type{});
       l_run = l_run * alpha + rowsum;
       // ---- O *= alpha (rare): P·V of block j-1 has retired (the MMA warp waited for it before issuing S_j)
       if (bump_any) {
@@ -823,37 +838,42 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(pds_empty, (it & 1) ^ 1);
       uint8_t* prow = sP + r * 128;
       uint8_t* dsrow = sDS + r * 128;
+      const float delta_s = delta * p.scale;
+      auto pds = [&](auto mask_tag) {
+        constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t ts[32], td[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::S_COL + c * 32, ts);
-        tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DP_COL + c * 32, td);
-        tmem_ld_wait();
-        uint32_t pp[16], dd[16];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t ts[32], td[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::S_COL + c * 32, ts);
+          tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DP_COL + c * 32, td);
+          tmem_ld_wait();
+          uint32_t pp[16], dd[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(__uint_as_float(ts[i]) * p.scale_log2 - lse2);
-          float p1 = exp2f(__uint_as_float(ts[i + 1]) * p.scale_log2 - lse2);
-          if (need_mask) {
-            const int kidx = k0 + c * 32 + i;
-            if (!q_ok || kidx >= kv_len || (p.causal && kidx > q_idx)) p0 = 0.f;
-            if (!q_ok || kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) p1 = 0.f;
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = fast_exp2(__uint_as_float(ts[i]) * p.scale_log2 - lse2);
+            float p1 = fast_exp2(__uint_as_float(ts[i + 1]) * p.scale_log2 - lse2);
+            if constexpr (MASK) {
+              const int kidx = k0 + c * 32 + i;
+              if (!q_ok || kidx >= kv_len || (p.causal && kidx > q_idx)) p0 = 0.f;
+              if (!q_ok || kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) p1 = 0.f;
+            }
+            const float d0 = p0 * fmaf(__uint_as_float(td[i]), p.scale, -delta_s);
+            const float d1 = p1 * fmaf(__uint_as_float(td[i + 1]), p.scale, -delta_s);
+            pp[i / 2] = pack_bf16(p0, p1);
+            dd[i / 2] = pack_bf16(d0, d1);
           }
-          const float d0 = p0 * (__uint_as_float(td[i]) - delta) * p.scale;
-          const float d1 = p1 * (__uint_as_float(td[i + 1]) - delta) * p.scale;
-          pp[i / 2] = pack_bf16(p0, p1);
-          dd[i / 2] = pack_bf16(d0, d1);
-        }
-        const int half_off = (c / 2) * (128 * 128);
+          const int half_off = (c / 2) * (128 * 128);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int phys = ((c % 2) * 4 + q4) ^ (r & 7);
-          *reinterpret_cast<uint4*>(prow + half_off + phys * 16) =
-              make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
-          *reinterpret_cast<uint4*>(dsrow + half_off + phys * 16) =
-              make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int phys = ((c % 2) * 4 + q4) ^ (r & 7);
+            *reinterpret_cast<uint4*>(prow + half_off + phys * 16) =
+                make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
+            *reinterpret_cast<uint4*>(dsrow + half_off + phys * 16) =
+                make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
+          }
         }
-      }
+      };
+      if (need_mask) pds(std::true_type{}); else pds(std::false_type{});
       tc_fence_before_sync();
       fence_proxy_async();
       mbar_arrive(pds_full);

@@ -18,11 +18,15 @@ int lb_norm_bwd(const void* gy, const void* x, const void* gamma, const float* m
                 float* dgamma, float* dbeta, float* workspace, int rows, int H, int rms, int dtype, int wdtype,
                 cudaStream_t s);
 int lb_bias_act_fwd(const void* x, const void* bias, void* y, long rows, int N, int act, cudaStream_t s);
+int lb_gemm_bf16_actgrad(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo,
+                         int layout, int act, const void* pre_in, cudaStream_t stream);
 int lb_bias_act_bwd(const void* gy, const void* x, const void* bias, void* gx, long rows, int N, int act,
                     cudaStream_t s);
 int lb_bias_residual(const void* x, const void* bias, const void* res, void* y, long rows, int N, cudaStream_t s);
 int lb_swiglu_fwd(const void* gate, const void* up, void* y, long n, cudaStream_t s);
 int lb_swiglu_bwd(const void* gy, const void* gate, const void* up, void* dgate, void* dup, long n, cudaStream_t s);
+int lb_rope_qkv(const void* x, const float* cosv, const float* sinv, void* y, long heads, int S, int A, int D,
+                int pos_offset, int backward, cudaStream_t s);
 int lb_rope(const void* x, const float* cosv, const float* sinv, void* y, long rows, int S, int D, int backward,
             cudaStream_t s);
 int lb_colsum(const void* x, float* out, int M, int N, cudaStream_t s);
@@ -108,6 +112,23 @@ Tensor gemm(const Tensor& a, const Tensor& b, int64_t layout, const c10::optiona
   check(lb_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, (int)a.stride(0),
                      (int)b.stride(0), (int)out.stride(0), (int)layout, epi, bias_ptr, 0, nullptr, 0, 0, cur_stream()),
         "gemm");
+  return out;
+}
+
+// dpre = (gy @ w) * act'(pre): the dgrad GEMM of the layer that consumed act(pre), with the activation backward
+// applied in its epilogue (gy [M,N], w [N,K] row-major, pre [M,K]).
+Tensor dgrad_actgrad(const Tensor& gy, const Tensor& w, const Tensor& pre, int64_t act) {
+  TORCH_CHECK(gy.is_cuda() && gy.dim() == 2 && w.dim() == 2 && pre.dim() == 2, "dgrad_actgrad: 2-D CUDA tensors");
+  TORCH_CHECK(gy.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && pre.scalar_type() == at::kBFloat16,
+              "dgrad_actgrad: bf16 expected");
+  TORCH_CHECK(gy.stride(1) == 1 && w.stride(1) == 1 && pre.is_contiguous(), "dgrad_actgrad: row-major operands");
+  const int64_t M = gy.size(0), K = gy.size(1), N = w.size(1);
+  TORCH_CHECK(w.size(0) == K && pre.size(0) == M && pre.size(1) == N, "dgrad_actgrad: shape mismatch");
+  c10::cuda::CUDAGuard guard(gy.device());
+  Tensor out = at::empty({M, N}, gy.options());
+  check(lb_gemm_bf16_actgrad(gy.data_ptr(), w.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, (int)gy.stride(0),
+                             (int)w.stride(0), (int)N, 1, (int)act, pre.data_ptr(), cur_stream()),
+        "dgrad_actgrad");
   return out;
 }
 
@@ -243,6 +264,25 @@ std::tuple<Tensor, Tensor> swiglu_bwd(const Tensor& gy, const Tensor& gate, cons
         "swiglu_bwd");
   return std::make_tuple(dg, du);
 }
+// qkv [b, s, a, 3d] packed projection; rotates q and k (v copied).  inplace=true rewrites qkv itself.
+Tensor rope_qkv(const Tensor& qkv, const Tensor& cosv, const Tensor& sinv, int64_t pos_offset, bool backward,
+                bool inplace) {
+  c10::cuda::CUDAGuard guard(qkv.device());
+  TORCH_CHECK(qkv.dim() == 4 && qkv.is_contiguous() && qkv.scalar_type() == at::kBFloat16,
+              "rope_qkv: contiguous bf16 [b,s,a,3d]");
+  const int S = qkv.size(1), A = qkv.size(2), D = qkv.size(3) / 3;
+  TORCH_CHECK(qkv.size(3) == 3 * D && D % 2 == 0, "rope_qkv: last dim must be 3*d");
+  TORCH_CHECK(cosv.scalar_type() == at::kFloat && sinv.scalar_type() == at::kFloat && cosv.is_contiguous() &&
+                  sinv.is_contiguous() && cosv.size(0) >= S + pos_offset && cosv.size(1) == D &&
+                  sinv.sizes() == cosv.sizes(),
+              "rope_qkv: cos/sin fp32 [>=S+offset, D]");
+  Tensor y = inplace ? qkv : at::empty_like(qkv);
+  check(lb_rope_qkv(qkv.data_ptr(), cosv.data_ptr<float>(), sinv.data_ptr<float>(), y.data_ptr(),
+                    qkv.numel() / (3 * D), S, A, D, (int)pos_offset, backward ? 1 : 0, cur_stream()),
+        "rope_qkv");
+  return y;
+}
+
 Tensor rope(const Tensor& x, const Tensor& cosv, const Tensor& sinv, bool backward) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.dim() == 4 && x.is_contiguous() && x.scalar_type() == at::kBFloat16, "rope: contiguous bf16 [b,a,s,d]");
@@ -432,7 +472,9 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("bias_residual_fwd(Tensor x, Tensor? bias, Tensor? res) -> Tensor", &bias_residual_fwd);
   m.def("swiglu_fwd(Tensor gate, Tensor up) -> Tensor", &swiglu_fwd);
   m.def("swiglu_bwd(Tensor gy, Tensor gate, Tensor up) -> (Tensor, Tensor)", &swiglu_bwd);
+  m.def("dgrad_actgrad(Tensor gy, Tensor w, Tensor pre, int act) -> Tensor", &dgrad_actgrad);
   m.def("rope(Tensor x, Tensor cos, Tensor sin, bool backward) -> Tensor", &rope);
+  m.def("rope_qkv(Tensor(a!) qkv, Tensor cos, Tensor sin, int pos_offset, bool backward, bool inplace) -> Tensor(a!)", &rope_qkv);
   m.def("ce_stats(Tensor logits, Tensor labels, int vocab_start) -> (Tensor, Tensor, Tensor)", &ce_stats);
   m.def("ce_bwd(Tensor(a!) logits, Tensor labels, Tensor lse, Tensor gloss, int vocab_start) -> Tensor(a!)", &ce_bwd);
   m.def("fused_adamw(Tensor(a!) master, Tensor grad, Tensor(b!) m, Tensor(c!) v, Tensor? lp_out, Tensor scale, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, bool decoupled) -> ()", &fused_adamw);

@@ -231,13 +231,55 @@ LB_DEVICE float2 unpack_bf16(uint32_t u) {
 
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_GELU_TANH = 2, ACT_RELU = 3, ACT_SILU = 4, ACT_QUICK_GELU = 5 };
 
+// erfc(|x|/sqrt2) and exp(-x^2/2) from one MUFU.EX2 + one MUFU.RCP (Abramowitz-Stegun 7.1.26, |err(erf)| < 1.5e-7 -
+// three orders of magnitude below bf16 resolution).  The libm erff costs ~60 instructions with a divergent branch,
+// which made the 4-warp GEMM epilogue (one thread per accumulator row) the bottleneck of the h->4h projection.
+LB_DEVICE void gelu_terms(float x, float& erfc_abs, float& gauss) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));  // exp(-x^2/2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  erfc_abs = poly * t * e;
+  gauss = e;
+}
+LB_DEVICE float gelu_fast(float x) {
+  float q, e;
+  gelu_terms(x, q, e);
+  const float h = 0.5f * q;                 // 0.5 * erfc(|x|/sqrt2)
+  return x * (x >= 0.f ? 1.0f - h : h);     // no cancellation on the negative side
+}
+LB_DEVICE float gelu_grad_fast(float x) {
+  float q, e;
+  gelu_terms(x, q, e);
+  const float h = 0.5f * q;
+  const float cdf = x >= 0.f ? 1.0f - h : h;
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+// 2^x on the SFU without the denormal-range fix-up branch that exp2f() compiles to (one BSSY/BRA/BSYNC triple per
+// element in the softmax loops); ex2.approx(-inf) = +0.
+LB_DEVICE float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+LB_DEVICE float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 LB_DEVICE float act_fwd(float x, int act) {
   switch (act) {
     case ACT_GELU:
-      return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+      return gelu_fast(x);
     case ACT_GELU_TANH: {
       float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-      return 0.5f * x * (1.0f + tanhf(u));
+      return 0.5f * x * (1.0f + tanh_fast(u));
     }
     case ACT_RELU:
       return x > 0.f ? x : 0.f;
@@ -252,15 +294,12 @@ LB_DEVICE float act_fwd(float x, int act) {
 // d act(x) / dx
 LB_DEVICE float act_grad(float x, int act) {
   switch (act) {
-    case ACT_GELU: {
-      float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-      float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-      return cdf + x * pdf;
-    }
+    case ACT_GELU:
+      return gelu_grad_fast(x);
     case ACT_GELU_TANH: {
       float x2 = x * x;
       float u = 0.7978845608028654f * (x + 0.044715f * x * x2);
-      float t = tanhf(u);
+      float t = tanh_fast(u);
       float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x2);
       return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
     }

@@ -140,6 +140,41 @@ __global__ void rope_kernel(const __nv_bfloat16* __restrict__ x, const float* __
   }
 }
 
+// Rotary embedding on the packed QKV projection [tokens(b*s), A, 3*D] (per-head [q|k|v]): q and k are rotated
+// with the position (s + pos_offset), v is copied.  `y` may alias `x` (in-place, used by the backward).
+__global__ void rope_qkv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ cosv,
+                                const float* __restrict__ sinv, __nv_bfloat16* __restrict__ y, size_t heads, int S,
+                                int A, int D, int pos_offset, int backward, int copy_v) {
+  const int half = D / 2;
+  const int parts = copy_v ? 3 : 2;
+  const size_t total = heads * parts * half;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(i % half);
+    const int part = static_cast<int>((i / half) % parts);
+    const size_t head = i / (static_cast<size_t>(half) * parts);
+    const size_t base = head * 3 * D + static_cast<size_t>(part) * D;
+    const float x1 = __bfloat162float(x[base + c]), x2 = __bfloat162float(x[base + c + half]);
+    if (part == 2) {
+      y[base + c] = x[base + c];
+      y[base + c + half] = x[base + c + half];
+      continue;
+    }
+    const int s = static_cast<int>((head / A) % S) + pos_offset;
+    const float c1 = cosv[s * D + c], c2 = cosv[s * D + c + half];
+    const float s1 = sinv[s * D + c], s2 = sinv[s * D + c + half];
+    float y1, y2;
+    if (!backward) {
+      y1 = x1 * c1 - x2 * s1;
+      y2 = x2 * c2 + x1 * s2;
+    } else {
+      y1 = x1 * c1 + x2 * s2;
+      y2 = x2 * c2 - x1 * s1;
+    }
+    y[base + c] = __float2bfloat16(y1);
+    y[base + c + half] = __float2bfloat16(y2);
+  }
+}
+
 // out[c] += sum_r x[r, c]   (out fp32, zero-initialised by the caller)
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int M, int N,
                               int rows_per_block) {
@@ -389,6 +424,14 @@ extern "C" int lb_rope(const void* x, const float* cosv, const float* sinv, void
   if (rows == 0) return 0;
   lb::rope_kernel<<<ew_grid((size_t)rows * D / 2, 256), 256, 0, s>>>((const bf16*)x, cosv, sinv, (bf16*)y,
                                                                      (size_t)rows, S, D, backward);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_rope_qkv(const void* x, const float* cosv, const float* sinv, void* y, long heads, int S, int A, int D,
+                           int pos_offset, int backward, cudaStream_t s) {
+  if (heads == 0) return 0;
+  const int copy_v = (x != y);
+  lb::rope_qkv_kernel<<<ew_grid((size_t)heads * (copy_v ? 3 : 2) * D / 2, 256), 256, 0, s>>>(
+      (const bf16*)x, cosv, sinv, (bf16*)y, (size_t)heads, S, A, D, pos_offset, backward, copy_v);
   return (int)cudaGetLastError();
 }
 extern "C" int lb_colsum(const void* x, float* out, int M, int N, cudaStream_t s) {

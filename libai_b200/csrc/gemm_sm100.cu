@@ -9,9 +9,10 @@
 // Replaces the cuBLAS matmuls behind libai/layers/linear.py:123-157 and the separate
 // fused_bias_add_gelu kernel (libai/layers/mlp.py:95) of the reference.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
-// warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).  One CTA per SM, static
-// round-robin tile scheduler over (m_blk, n_blk, k_split).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+// warps 2..9 = epilogue (TMEM lane quadrant = warp_idx % 4, column half = (warp_idx - 2) / 4: two warps per
+// scheduler keep the elementwise epilogue math (bias, GELU, GELU') off the critical path).  One CTA per SM,
+// static round-robin tile scheduler over (m_blk, n_blk, k_split).
 #include "common.cuh"
 
 #include <cstdio>
@@ -24,8 +25,8 @@ namespace lb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
-constexpr int NUM_EPI_THREADS = 128;
+constexpr int NUM_THREADS = 320;
+constexpr int NUM_EPI_THREADS = 256;
 
 enum Epi : int { EPI_BF16 = 0, EPI_F32 = 1, EPI_ATOMIC_F32 = 2 };
 
@@ -37,9 +38,9 @@ struct GemmParams {
   int act;                    // Act enum
   void* out;                  // bf16 or fp32 [M, ldo]
   __nv_bfloat16* pre_out;     // optional pre-activation copy (bf16)
+  const __nv_bfloat16* pre_in;  // optional [M, ldo]: out = acc * act'(pre_in)  (dgrad fused with the activation backward)
   int ldo;                    // leading dimension of out (elements)
   int rmw;                    // EPI_F32: out += acc (plain read-modify-write; a tile is owned by one CTA)
-  int bulk_reduce;            // EPI_ATOMIC_F32: cp.reduce.async.bulk (TMA reduce-add) instead of red.global
 };
 
 // Fused collective modes (tensor parallel): peer pointers refer to NVLink peer-mapped symmetric memory.
@@ -89,9 +90,7 @@ struct StageCfg {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NUM_STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : (BLOCK_N == 128 ? 6 : 8));
-  static constexpr int EPI_ROW_FLOATS = 36;             // 32 payload + 4 pad: conflict-free 16-byte stores
-  static constexpr int EPI_STAGE_BYTES = 128 * EPI_ROW_FLOATS * 4;  // fp32 staging rows for the bulk-reduce epilogue
-  static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 };
 
@@ -103,8 +102,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr int NS = Cfg::NUM_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* epi_stage = reinterpret_cast<float*>(smem + NS * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES + Cfg::EPI_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + NS;
   uint64_t* tmem_full = empty_bar + NS;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -277,8 +275,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     }
   } else {
-    // ======================= epilogue (4 warps) =======================
-    const int quad = warp_idx % 4;  // TMEM lanes [32*quad, 32*quad+32)
+    // ======================= epilogue (8 warps) =======================
+    const int quad = warp_idx % 4;          // TMEM lanes [32*quad, 32*quad+32)
+    const int half = (warp_idx - 2) / 4;    // column half of the tile
+    constexpr int CHUNKS_PER_HALF = BLOCK_N / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cta; tile < num_tiles; tile += cta_stride) {
@@ -290,7 +290,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = half * CHUNKS_PER_HALF; c < (half + 1) * CHUNKS_PER_HALF; ++c) {
         const int col0 = n_blk * BLOCK_N + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
@@ -329,7 +329,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 }
               }
             }
-            if (p.act != ACT_NONE) {
+            if (p.pre_in != nullptr) {
+              const __nv_bfloat16* prow = p.pre_in + static_cast<size_t>(row) * p.ldo + col0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (col0 + i < p.N) {
+                  const uint4 q = *reinterpret_cast<const uint4*>(prow + i);
+                  const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c2 = unpack_bf16(q.z), d = unpack_bf16(q.w);
+                  if (p.act == ACT_GELU) {  // hot case without the per-element switch
+                    v[i] *= gelu_grad_fast(a.x); v[i + 1] *= gelu_grad_fast(a.y);
+                    v[i + 2] *= gelu_grad_fast(b.x); v[i + 3] *= gelu_grad_fast(b.y);
+                    v[i + 4] *= gelu_grad_fast(c2.x); v[i + 5] *= gelu_grad_fast(c2.y);
+                    v[i + 6] *= gelu_grad_fast(d.x); v[i + 7] *= gelu_grad_fast(d.y);
+                  } else {
+                    v[i] *= act_grad(a.x, p.act); v[i + 1] *= act_grad(a.y, p.act);
+                    v[i + 2] *= act_grad(b.x, p.act); v[i + 3] *= act_grad(b.y, p.act);
+                    v[i + 4] *= act_grad(c2.x, p.act); v[i + 5] *= act_grad(c2.y, p.act);
+                    v[i + 6] *= act_grad(d.x, p.act); v[i + 7] *= act_grad(d.y, p.act);
+                  }
+                }
+              }
+            } else if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+            } else if (p.act != ACT_NONE) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = act_fwd(v[i], p.act);
             }
@@ -356,21 +379,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
           } else {
             float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-            if (p.bulk_reduce) {
-              // split-K partial sums: every thread stages its 32 fp32 values (128 B) in shared memory and hands
-              // them to the TMA unit as one reduce-add; L2 performs the accumulation per line instead of per float
-              float* srow = epi_stage + (quad * 32 + lane) * Cfg::EPI_ROW_FLOATS;  // padded rows: no bank conflicts
-              asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous chunk of this row consumed
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                *reinterpret_cast<float4*>(srow + k * 4) = make_float4(v[k * 4], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
-              fence_proxy_async();
-              const int ncols = min(32, p.N - col0);
-              asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;\n" ::"l"(orow),
-                           "r"(smem_u32(srow)), "r"(ncols * 4)
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-            } else {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 if (col0 + i < p.N) {
@@ -379,15 +387,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                : "memory");
                 }
               }
-            }
           }
         }
       }
       tc_fence_before_sync();
       mbar_arrive(&tmem_empty[acc]);
       if (cp.mode == COMM_RS) {
-        // all 128 epilogue threads have issued their P2P stores -> one release-increment on the owner's counter
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        // all 256 epilogue threads have issued their P2P stores -> one release-increment on the owner's counter
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
         if (threadIdx.x == 64) {
           __threadfence_system();
           const int owner = m_blk / mbpr;
@@ -449,7 +456,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   }
 
-  if (EPI == EPI_ATOMIC_F32) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // reductions landed
   tc_fence_before_sync();
   __syncthreads();
   if (warp_idx == 1) {
@@ -561,8 +567,8 @@ cudaError_t launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, cons
 // epi:    0 = bf16 store (+bias, act, optional pre-activation copy); 1 = fp32 store; 2 = fp32 atomic accumulate
 // Returns 0 on success, a negative code for unsupported arguments, or a cudaError_t (> 0).
 static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo, int layout,
-                     int epi, const void* bias, int act, void* pre_out, int force_bn, int force_splits,
-                     const lb::CommParams& cp, cudaStream_t stream) {
+                     int epi, const void* bias, int act, void* pre_out, const void* pre_in, int force_bn,
+                     int force_splits, const lb::CommParams& cp, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (N % 8) || (ldo % 4)) return -1;
   const bool a_mn = (layout == 2);
@@ -615,14 +621,6 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   p.k_splits = (k_blocks + p.k_per_split - 1) / p.k_per_split;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.rmw = 0;
-  {
-    static int bulk = -1;
-    if (bulk < 0) {
-      const char* e = getenv("LIBAI_B200_WGRAD_BULK");
-      bulk = (e == nullptr || e[0] != '0') ? 1 : 0;
-    }
-    p.bulk_reduce = bulk;
-  }
   if (epi == 2 && p.k_splits == 1) {
     // a single K partition owns the whole tile: accumulate with a plain read-modify-write instead of
     // L2 atomics (fp32 atomics are throughput-limited at the L2 slices)
@@ -632,6 +630,7 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   p.act = act;
   p.out = out;
   p.pre_out = reinterpret_cast<__nv_bfloat16*>(pre_out);
+  p.pre_in = reinterpret_cast<const __nv_bfloat16*>(pre_in);
   p.ldo = ldo;
 
   CUtensorMap ta, tb;
@@ -666,7 +665,17 @@ extern "C" int lb_gemm_bf16(const void* a, const void* b, void* out, int M, int 
                             int force_splits, cudaStream_t stream) {
   lb::CommParams cp;
   memset(&cp, 0, sizeof(cp));
-  return gemm_impl(a, b, out, M, N, K, lda, ldb, ldo, layout, epi, bias, act, pre_out, force_bn, force_splits, cp, stream);
+  return gemm_impl(a, b, out, M, N, K, lda, ldb, ldo, layout, epi, bias, act, pre_out, nullptr, force_bn, force_splits, cp,
+                   stream);
+}
+
+// dgrad fused with the activation backward: out[M,N] = (A·B) * act'(pre_in[M,N])   (bf16 output, ldo = row stride
+// of both `out` and `pre_in`)
+extern "C" int lb_gemm_bf16_actgrad(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb,
+                                    int ldo, int layout, int act, const void* pre_in, cudaStream_t stream) {
+  lb::CommParams cp;
+  memset(&cp, 0, sizeof(cp));
+  return gemm_impl(a, b, out, M, N, K, lda, ldb, ldo, layout, 0, nullptr, act, nullptr, pre_in, 0, 0, cp, stream);
 }
 
 // Tensor-parallel fused collective GEMMs (NT layout, bf16 output).
@@ -698,6 +707,6 @@ extern "C" int lb_gemm_bf16_comm(const void* a, const void* b, void* out, int M,
   cp.staging_parity_off = staging_parity_off;
   // the RS epilogue writes into the staging buffers; `out` is unused there (pass any valid pointer)
   if (layout != 0 && layout != 1) return -6;
-  return gemm_impl(a, b, mode == 2 ? rs_out : out, M, N, K, K, layout == 0 ? K : N, N, layout, 0, bias, act, pre_out, 0, 1, cp,
-                   stream);
+  return gemm_impl(a, b, mode == 2 ? rs_out : out, M, N, K, K, layout == 0 ? K : N, N, layout, 0, bias, act, pre_out, nullptr, 0, 1,
+                   cp, stream);
 }

@@ -9,6 +9,8 @@ function).
 from torch import nn
 
 from libai_b200.ops import functional as OF
+from libai_b200.parallel import mappings
+from libai_b200.utils import distributed as dutil
 
 from ._param import xavier_normal_
 from .linear import Linear
@@ -44,8 +46,15 @@ class MLP(nn.Module):
 
     def forward(self, hidden_states, residual=None):
         """Returns ``residual + dropout(mlp(x))`` when ``residual`` is given (fused epilogue)."""
-        inter = self.dense_h_to_4h(hidden_states, act="gelu")
-        out, bias = self.dense_4h_to_h(inter)
+        topo = dutil.get_dist_util()
+        if not topo.sequence_parallel and not topo.fused_tp_comm:
+            # both GEMMs in one autograd node: GELU' runs in the epilogue of the second layer's dgrad
+            x = mappings.copy_to_tp(hidden_states)
+            out = OF.mlp(x, self.dense_h_to_4h.weight, self.dense_h_to_4h.bias, self.dense_4h_to_h.weight, "gelu")
+            out, bias = mappings.reduce_from_tp(out), self.dense_4h_to_h.bias
+        else:
+            inter = self.dense_h_to_4h(hidden_states, act="gelu")
+            out, bias = self.dense_4h_to_h(inter)
         return OF.bias_dropout_add(out, bias, residual, self.output_dropout_prob, self.training)
 
     def extra_repr(self) -> str:

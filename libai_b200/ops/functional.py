@@ -130,6 +130,66 @@ def linear(x, w, bias=None, act: Optional[str] = None):
     return _act_ref(y, act)
 
 
+
+class _MLPFn(torch.autograd.Function):
+    """``act(x @ w1ᵀ + b1) @ w2ᵀ`` as one autograd node so the backward can fuse across the two GEMMs:
+    ``dpre = (dy @ w2) ⊙ act'(pre)`` is a single kernel (activation backward in the dgrad epilogue) – the
+    separate bias+activation backward pass over the ``[tokens, ffn]`` tensor disappears."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, act):
+        ext = load_ext()
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        h, pre = ext.linear_fwd(x2, w1, b1, _ACT_IDS[act], True)
+        y, _ = ext.linear_fwd(h, w2, None, 0, False)
+        count_launch(2)
+        ctx.act = act
+        ctx.save_for_backward(x2, w1, w2, pre, h)
+        ctx.x_shape = x.shape
+        ctx.has_bias = b1 is not None
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        ext = load_ext()
+        x2, w1, w2, pre, h = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        dpre = ext.dgrad_actgrad(g2, w2, pre, _ACT_IDS[ctx.act])
+        count_launch()
+
+        def wgrad(g, inp, w):
+            main_grad = getattr(w, "main_grad", None)
+            count_launch()
+            if main_grad is not None:
+                ext.gemm(g, inp, 2, None, main_grad, True, torch.float32)
+                w.grad_added_to_main_grad = True
+                return None
+            return ext.gemm(g, inp, 2, None, None, False, torch.float32).to(w.dtype)
+
+        gw2 = wgrad(g2, h, w2) if ctx.needs_input_grad[3] else None
+        gw1 = wgrad(dpre, x2, w1) if ctx.needs_input_grad[1] else None
+        gb1 = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb1 = ext.colsum(dpre)
+            count_launch()
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = ext.gemm(dpre, w1, 1, None, None, False, torch.bfloat16).view(ctx.x_shape)
+            count_launch()
+        return gx, gw1, gb1, gw2, None
+
+
+def mlp(x, w1, b1, w2, act: str = "gelu"):
+    """``act(x @ w1ᵀ + b1) @ w2ᵀ`` (the second bias is left to the fused bias+dropout+residual op)."""
+    if use_native(x, w1) and _gemm_ok(x, w1) and _gemm_ok(x.new_empty(1, w1.shape[0]), w2):
+        return _MLPFn.apply(x, w1, b1, w2, act)
+    return linear(linear(x, w1, b1, act), w2)
+
+
 def matmul_nt(a, b):
     """``a @ b.T`` without autograd bookkeeping beyond PyTorch's (used by LM head on ref path)."""
     return linear(a, b)
@@ -465,6 +525,41 @@ def apply_rotary(x, cos, sin):
     c = cos[None, None].to(x.dtype)
     s = sin[None, None].to(x.dtype)
     return x * c + rotate_half(x) * s
+
+
+
+class _RopeQKVFn(torch.autograd.Function):
+    """Rotary embedding on q and k of the packed projection ``[b, s, a, 3d]`` in one pass (v copied);
+    the backward rotates the packed ``dqkv`` of the attention kernel in place with the inverse rotation."""
+
+    @staticmethod
+    def forward(ctx, qkv, cos, sin, pos_offset):
+        ext = load_ext()
+        ctx.save_for_backward(cos, sin)
+        ctx.pos_offset = pos_offset
+        count_launch()
+        return ext.rope_qkv(qkv, cos, sin, pos_offset, False, False)
+
+    @staticmethod
+    def backward(ctx, g):
+        ext = load_ext()
+        cos, sin = ctx.saved_tensors
+        count_launch()
+        g = g if g.is_contiguous() else g.contiguous()
+        return ext.rope_qkv(g, cos, sin, ctx.pos_offset, True, True), None, None, None
+
+
+def apply_rotary_qkv(qkv, cos, sin, pos_offset: int = 0):
+    """qkv ``[b, s, a, 3d]`` (per-head ``[q|k|v]``); cos/sin fp32 ``[max_pos, d]``; token ``i`` of the
+    sequence uses position ``i + pos_offset``."""
+    if use_native(qkv) and qkv.dtype == torch.bfloat16 and cos.dtype == torch.float32 and qkv.is_contiguous():
+        return _RopeQKVFn.apply(qkv, cos, sin, int(pos_offset))
+    d = qkv.shape[-1] // 3
+    s_len = qkv.shape[1]
+    c = cos[pos_offset : pos_offset + s_len, None, :].to(qkv.dtype)
+    sn = sin[pos_offset : pos_offset + s_len, None, :].to(qkv.dtype)
+    q, k, v = qkv[..., :d], qkv[..., d : 2 * d], qkv[..., 2 * d :]
+    return torch.cat([q * c + rotate_half(q) * sn, k * c + rotate_half(k) * sn, v], dim=-1)
 
 
 # --------------------------------------------------------------------------------------

@@ -143,6 +143,41 @@ def main():
 
     record("linear_fwd bias+gelu", lin)
 
+    def lin_speed():
+        # the h->4h projection of the benchmark model: bias + GELU + pre-activation copy in the GEMM epilogue
+        x = torch.randn(8192, 1024, device="cuda").bfloat16()
+        w = (torch.randn(4096, 1024, device="cuda") * 0.02).bfloat16()
+        b = torch.randn(4096, device="cuda").bfloat16()
+        ms = timeit(lambda: ext.linear_fwd(x, w, b, 1, True))
+        ms_plain = timeit(lambda: ext.linear_fwd(x, w, None, 0, False))
+        return {"ok": True, "ms_bias_gelu_pre": ms, "ms_plain": ms_plain,
+                "tflops": 2 * 8192 * 4096 * 1024 / ms / 1e9}
+
+    record("linear_fwd speed", lin_speed)
+
+    def mlp_fn():
+        from libai_b200.ops import functional as OF
+        x = (torch.randn(1024, 512, device="cuda")).bfloat16().requires_grad_(True)
+        w1 = (torch.randn(2048, 512, device="cuda") * 0.05).bfloat16().requires_grad_(True)
+        b1 = (torch.randn(2048, device="cuda") * 0.1).bfloat16().requires_grad_(True)
+        w2 = (torch.randn(512, 2048, device="cuda") * 0.05).bfloat16().requires_grad_(True)
+        y = OF.mlp(x, w1, b1, w2, "gelu")
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        xf, w1f, b1f, w2f = [t.detach().float().requires_grad_(True) for t in (x, w1, b1, w2)]
+        ref = torch.nn.functional.gelu(xf @ w1f.t() + b1f) @ w2f.t()
+        ref.backward(gy.float())
+        e = [rel_err(y, ref), rel_err(x.grad, xf.grad), rel_err(w1.grad, w1f.grad), rel_err(b1.grad, b1f.grad),
+             rel_err(w2.grad, w2f.grad)]
+        pre = (torch.randn(8192, 4096, device="cuda")).bfloat16()
+        g = torch.randn(8192, 1024, device="cuda").bfloat16()
+        w = (torch.randn(1024, 4096, device="cuda") * 0.02).bfloat16()
+        ms = timeit(lambda: ext.dgrad_actgrad(g, w, pre, 1))
+        ms_sep = timeit(lambda: ext.act_bwd(ext.gemm(g, w, 1, None, None, False, torch.bfloat16), pre, 1))
+        return {"ok": max(e) < 3e-2, "errs": e, "dgrad_actgrad_ms": ms, "dgrad_then_actbwd_ms": ms_sep}
+
+    record("mlp fused fwd/bwd", mlp_fn)
+
     # ------------------------------------------------------------------ norms
     for rms in (False, True):
         for H in (1024, 768, 4096, 200):
@@ -232,6 +267,27 @@ def main():
 
     record("rope", rope)
 
+    def rope_qkv():
+        from libai_b200.ops.functional import rotate_half
+
+        b, sq, a, d, off = 2, 96, 4, 64, 5
+        qkv = torch.randn(b, sq, a, 3 * d, device="cuda").bfloat16()
+        pos = torch.arange(sq + off, device="cuda").float()
+        inv = 1.0 / (10000 ** (torch.arange(0, d, 2, device="cuda").float() / d))
+        fr = torch.outer(pos, inv)
+        emb = torch.cat([fr, fr], -1)
+        cos, sin = emb.cos().contiguous(), emb.sin().contiguous()
+        y = ext.rope_qkv(qkv, cos, sin, off, False, False)
+        c, s_ = cos[off:off + sq, None, :], sin[off:off + sq, None, :]
+        qf = qkv.float()
+        q, k, v = qf[..., :d], qf[..., d:2 * d], qf[..., 2 * d:]
+        ref = torch.cat([q * c + rotate_half(q) * s_, k * c + rotate_half(k) * s_, v], -1)
+        back = ext.rope_qkv(y.clone(), cos, sin, off, True, True)  # inverse rotation in place
+        e = [rel_err(y, ref), rel_err(back, qf)]
+        return {"ok": max(e) < 2e-2, "errs": e}
+
+    record("rope_qkv packed", rope_qkv)
+
     # ------------------------------------------------------------------ cross entropy
     def ce():
         T, V = 513, 50304
@@ -295,6 +351,25 @@ def main():
 
         record(f"attention B{B} A{A} S{S} D{D} causal={causal}", att)
 
+    def att_kvlens():
+        B, A, S, D = 3, 2, 320, 64
+        qkv = torch.randn(B, S, A, 3 * D, device="cuda").bfloat16()
+        v4 = qkv.permute(0, 2, 1, 3)
+        q, k, v = v4[..., :D], v4[..., D:2 * D], v4[..., 2 * D:]
+        lens = torch.tensor([320, 200, 77], device="cuda", dtype=torch.int32)
+        scale = 0.125
+        o, lse = ext.attn_fwd(q, k, v, False, scale, lens)
+        qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+        mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None])[:, None, None, :]
+        ref = attention_ref(qf, kf, vf, causal=False, scale=scale, mask=mask, fill=-1e30)
+        go = torch.randn(B, S, A, D, device="cuda").bfloat16().permute(0, 2, 1, 3)
+        ref.backward(go.float())
+        dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, False, scale, lens)
+        e = [rel_err(o, ref), rel_err(dq, qf.grad), rel_err(dk, kf.grad), rel_err(dv, vf.grad)]
+        return {"ok": max(e) < 3e-2, "errs": e}
+
+    record("attention kv_lens (key padding)", att_kvlens)
+
     if not args.quick:
         def att_speed():
             B, A, S, D = 8, 16, 1024, 64
@@ -309,8 +384,12 @@ def main():
             flops = 4.0 * B * A * S * S * D / 2
             qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
             sd = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qc, kc, vc, is_causal=True))
+            qg, kg, vg = (t.detach().clone().requires_grad_(True) for t in (qc, kc, vc))
+            og = torch.nn.functional.scaled_dot_product_attention(qg, kg, vg, is_causal=True)
+            gog = torch.randn_like(og)
+            sdb = timeit(lambda: torch.autograd.grad(og, (qg, kg, vg), gog, retain_graph=True))
             return {"fwd_ms": ms, "fwd_tflops": flops / ms / 1e9, "bwd_ms": msb, "bwd_tflops": 2.5 * flops / msb / 1e9,
-                    "sdpa_fwd_ms": sd}
+                    "sdpa_fwd_ms": sd, "sdpa_bwd_ms": sdb}
 
         record("attention speed B8 A16 S1024 D64 causal", att_speed)
 
