@@ -16,7 +16,7 @@ int lb_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, flo
 int lb_norm_bwd_workspace_rows(int rows);
 int lb_norm_bwd(const void* gy, const void* x, const void* gamma, const float* mean, const float* rstd, void* gx,
                 float* dgamma, float* dbeta, float* workspace, int rows, int H, int rms, int dtype, int wdtype,
-                cudaStream_t s);
+                int accumulate, cudaStream_t s);
 int lb_bias_act_fwd(const void* x, const void* bias, void* y, long rows, int N, int act, cudaStream_t s);
 int lb_gemm_bf16_actgrad(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo,
                          int layout, int act, const void* pre_in, cudaStream_t stream);
@@ -29,7 +29,7 @@ int lb_rope_qkv(const void* x, const float* cosv, const float* sinv, void* y, lo
                 int pos_offset, int backward, cudaStream_t s);
 int lb_rope(const void* x, const float* cosv, const float* sinv, void* y, long rows, int S, int D, int backward,
             cudaStream_t s);
-int lb_colsum(const void* x, float* out, int M, int N, cudaStream_t s);
+int lb_colsum(const void* x, float* out, int M, int N, int accumulate, cudaStream_t s);
 int lb_ce_stats(const void* logits, const int64_t* labels, float* mx, float* se, float* tgt, int T, int V,
                 long vocab_start, int dtype, cudaStream_t s);
 int lb_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* gloss, void* dlogits, int T,
@@ -183,11 +183,19 @@ Tensor act_bwd(const Tensor& gy, const Tensor& pre, int64_t act) {
   return gx;
 }
 
-Tensor colsum(const Tensor& x) {
+// column sums of a bf16 [M, N] tensor.  With `accum` (fp32 [N], e.g. a bias' slice of the flat main-grad buffer) the
+// sums are added into it and an empty tensor is returned; otherwise a fresh bf16 [N] tensor.
+Tensor colsum(const Tensor& x, const c10::optional<Tensor>& accum) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && x.scalar_type() == at::kBFloat16, "colsum: contiguous bf16 [M,N]");
+  if (accum.has_value() && accum->defined()) {
+    TORCH_CHECK(accum->scalar_type() == at::kFloat && accum->numel() == x.size(1) && accum->is_contiguous(),
+                "colsum: accum must be contiguous fp32 [N]");
+    check(lb_colsum(x.data_ptr(), accum->data_ptr<float>(), (int)x.size(0), (int)x.size(1), 1, cur_stream()), "colsum");
+    return at::empty({0}, x.options());
+  }
   Tensor out = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
-  check(lb_colsum(x.data_ptr(), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1), cur_stream()), "colsum");
+  check(lb_colsum(x.data_ptr(), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1), 0, cur_stream()), "colsum");
   return out.to(at::kBFloat16);
 }
 
@@ -209,20 +217,33 @@ std::tuple<Tensor, Tensor, Tensor> norm_fwd(const Tensor& x, const Tensor& gamma
 }
 
 std::tuple<Tensor, Tensor, Tensor> norm_bwd(const Tensor& gy, const Tensor& x, const Tensor& gamma, const Tensor& mean,
-                                            const Tensor& rstd, bool rms, bool has_bias) {
+                                            const Tensor& rstd, bool rms, bool has_bias,
+                                            const c10::optional<Tensor>& dgamma_accum,
+                                            const c10::optional<Tensor>& dbeta_accum) {
   c10::cuda::CUDAGuard guard(x.device());
   const int rows = (int)x.size(0), H = (int)x.size(1);
   Tensor gx = at::empty_like(x);
   auto fopt = x.options().dtype(at::kFloat);
-  Tensor dgamma = at::empty({H}, fopt);
-  Tensor dbeta = has_bias ? at::empty({H}, fopt) : at::empty({0}, fopt);
+  // accumulate mode: dgamma / dbeta are added straight into the fp32 main-grad slices of the parameters
+  const bool acc = dgamma_accum.has_value() && dgamma_accum->defined();
+  if (acc) {
+    TORCH_CHECK(dgamma_accum->scalar_type() == at::kFloat && dgamma_accum->numel() == H && dgamma_accum->is_contiguous(),
+                "norm_bwd: dgamma_accum must be contiguous fp32 [H]");
+    TORCH_CHECK(!has_bias || (dbeta_accum.has_value() && dbeta_accum->defined() &&
+                              dbeta_accum->scalar_type() == at::kFloat && dbeta_accum->numel() == H &&
+                              dbeta_accum->is_contiguous()),
+                "norm_bwd: dbeta_accum must be contiguous fp32 [H]");
+  }
+  Tensor dgamma = acc ? dgamma_accum.value() : at::empty({H}, fopt);
+  Tensor dbeta = !has_bias ? at::empty({0}, fopt) : (acc ? dbeta_accum.value() : at::empty({H}, fopt));
   const int wrows = lb_norm_bwd_workspace_rows(rows);
   Tensor ws = at::empty({2 * (int64_t)wrows * H}, fopt);
   check(lb_norm_bwd(gy.data_ptr(), x.data_ptr(), gamma.data_ptr(), rms ? nullptr : mean.data_ptr<float>(),
                     rstd.data_ptr<float>(), gx.data_ptr(), dgamma.data_ptr<float>(),
                     has_bias ? dbeta.data_ptr<float>() : nullptr, ws.data_ptr<float>(), rows, H, rms ? 1 : 0,
-                    dtype_code(x), dtype_code(gamma), cur_stream()),
+                    dtype_code(x), dtype_code(gamma), acc ? 1 : 0, cur_stream()),
         "norm_bwd");
+  if (acc) return std::make_tuple(gx, at::empty({0}, fopt), at::empty({0}, fopt));
   return std::make_tuple(gx, dgamma, dbeta);
 }
 
@@ -464,9 +485,9 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("gemm_tuned(Tensor a, Tensor b, int layout, int bn, int splits, bool fp32_out) -> Tensor", &gemm_tuned);
   m.def("linear_fwd(Tensor x, Tensor w, Tensor? bias, int act, bool need_pre) -> (Tensor, Tensor)", &linear_fwd);
   m.def("act_bwd(Tensor gy, Tensor pre, int act) -> Tensor", &act_bwd);
-  m.def("colsum(Tensor x) -> Tensor", &colsum);
+  m.def("colsum(Tensor x, Tensor(a!)? accum=None) -> Tensor", &colsum);
   m.def("norm_fwd(Tensor x, Tensor gamma, Tensor? beta, float eps, bool rms) -> (Tensor, Tensor, Tensor)", &norm_fwd);
-  m.def("norm_bwd(Tensor gy, Tensor x, Tensor gamma, Tensor mean, Tensor rstd, bool rms, bool has_bias) -> (Tensor, Tensor, Tensor)", &norm_bwd);
+  m.def("norm_bwd(Tensor gy, Tensor x, Tensor gamma, Tensor mean, Tensor rstd, bool rms, bool has_bias, Tensor(a!)? dgamma_accum=None, Tensor(b!)? dbeta_accum=None) -> (Tensor, Tensor, Tensor)", &norm_bwd);
   m.def("bias_act_fwd(Tensor x, Tensor? bias, int act) -> Tensor", &bias_act_fwd);
   m.def("bias_act_bwd(Tensor gy, Tensor x, Tensor? bias, int act) -> Tensor", &bias_act_bwd);
   m.def("bias_residual_fwd(Tensor x, Tensor? bias, Tensor? res) -> Tensor", &bias_residual_fwd);

@@ -295,20 +295,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
+        // global operands of this chunk (bias slice: same address for the whole warp = broadcast; pre-activation
+        // row segment for the fused activation backward) are fetched while the TMEM load is in flight
+        uint4 bq[4], pq[4];
+        const bool use_bias = (EPI == EPI_BF16) && p.bias != nullptr && cp.mode != COMM_RS;  // RS: bias added once, in the reduce phase
+        const bool use_pre = (EPI == EPI_BF16) && p.pre_in != nullptr && row_ok;
+        if constexpr (EPI == EPI_BF16) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool in = col0 + i * 8 < p.N;  // N % 8 == 0
+            bq[i] = (use_bias && in) ? *reinterpret_cast<const uint4*>(p.bias + col0 + i * 8) : make_uint4(0, 0, 0, 0);
+            pq[i] = (use_pre && in)
+                        ? *reinterpret_cast<const uint4*>(p.pre_in + static_cast<size_t>(row) * p.ldo + col0 + i * 8)
+                        : make_uint4(0, 0, 0, 0);
+          }
+        }
         tmem_ld_wait();
         if (row_ok) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           if constexpr (EPI == EPI_BF16) {
-            if (p.bias != nullptr && cp.mode != COMM_RS) {  // RS adds the bias once, in the reduce phase
+            if (use_bias) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                if (col0 + i < p.N) {
-                  const float2 b = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.bias + col0 + i));
-                  v[i] += b.x;
-                  v[i + 1] += b.y;
-                }
+              for (int i = 0; i < 4; ++i) {
+                const float2 a = unpack_bf16(bq[i].x), b = unpack_bf16(bq[i].y), c2 = unpack_bf16(bq[i].z), d = unpack_bf16(bq[i].w);
+                v[i * 8] += a.x; v[i * 8 + 1] += a.y; v[i * 8 + 2] += b.x; v[i * 8 + 3] += b.y;
+                v[i * 8 + 4] += c2.x; v[i * 8 + 5] += c2.y; v[i * 8 + 6] += d.x; v[i * 8 + 7] += d.y;
               }
             }
             __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
@@ -330,11 +343,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               }
             }
             if (p.pre_in != nullptr) {
-              const __nv_bfloat16* prow = p.pre_in + static_cast<size_t>(row) * p.ldo + col0;
 #pragma unroll
               for (int i = 0; i < 32; i += 8) {
                 if (col0 + i < p.N) {
-                  const uint4 q = *reinterpret_cast<const uint4*>(prow + i);
+                  const uint4 q = pq[i / 8];
                   const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c2 = unpack_bf16(q.z), d = unpack_bf16(q.w);
                   if (p.act == ACT_GELU) {  // hot case without the per-element switch
                     v[i] *= gelu_grad_fast(a.x); v[i + 1] *= gelu_grad_fast(a.y);

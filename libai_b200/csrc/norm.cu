@@ -154,8 +154,13 @@ norm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, const W* __re
 }
 
 // out[c] = sum_r part[r, c]   (block = 32 columns x 8 row stripes, smem tree over the stripes)
-__global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                                        int nrows, int H) {
+// blockIdx.y selects (part0 -> out0) / (part1 -> out1): dgamma and dbeta in one launch; `accumulate` adds into `out`
+// (each column is owned by exactly one thread, so the fp32 main-grad buffer is updated with a plain read-modify-write)
+__global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict__ part0, float* __restrict__ out0,
+                                                        const float* __restrict__ part1, float* __restrict__ out1,
+                                                        int nrows, int H, int accumulate) {
+  const float* __restrict__ part = blockIdx.y == 0 ? part0 : part1;
+  float* __restrict__ out = blockIdx.y == 0 ? out0 : out1;
   __shared__ float sm[8][33];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int c = blockIdx.x * 32 + tx;
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict_
     float t = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += sm[j][tx];
-    out[c] = t;
+    out[c] = accumulate ? out[c] + t : t;
   }
 }
 
@@ -323,7 +328,7 @@ extern "C" int lb_norm_bwd_workspace_rows(int rows) { return norm_grid(rows); }
 
 extern "C" int lb_norm_bwd(const void* gy, const void* x, const void* gamma, const float* mean, const float* rstd,
                            void* gx, float* dgamma, float* dbeta, float* workspace, int rows, int H, int rms, int dtype,
-                           int wdtype, cudaStream_t s) {
+                           int wdtype, int accumulate, cudaStream_t s) {
   if (rows == 0) return 0;
   const bool fast = (H % 256 == 0) && (H / 256 <= 16);
   const int grid = norm_grid(rows);
@@ -338,13 +343,15 @@ extern "C" int lb_norm_bwd(const void* gy, const void* x, const void* gamma, con
                  : bwd_dispatch<T, W, false>(H / 256, (const T*)gy, (const T*)x, (const W*)gamma, mean, rstd,        \
                                              (T*)gx, pdg, pdb, rows, grid, s);                                       \
       if (done) {                                                                                                    \
-        lb::colreduce_kernel<<<(H + 31) / 32, 256, 0, s>>>(pdg, dgamma, grid, H);                                  \
-        if (dbeta != nullptr) lb::colreduce_kernel<<<(H + 31) / 32, 256, 0, s>>>(pdb, dbeta, grid, H);             \
+        lb::colreduce_kernel<<<dim3((H + 31) / 32, dbeta != nullptr ? 2 : 1), 256, 0, s>>>(pdg, dgamma, pdb, dbeta, grid, \
+                                                                                           H, accumulate);           \
       }                                                                                                              \
     }                                                                                                                \
     if (!done) {                                                                                                     \
-      cudaMemsetAsync(dgamma, 0, sizeof(float) * H, s);                                                              \
-      if (dbeta != nullptr) cudaMemsetAsync(dbeta, 0, sizeof(float) * H, s);                                         \
+      if (!accumulate) {                                                                                             \
+        cudaMemsetAsync(dgamma, 0, sizeof(float) * H, s);                                                            \
+        if (dbeta != nullptr) cudaMemsetAsync(dbeta, 0, sizeof(float) * H, s);                                       \
+      }                                                                                                              \
       const int wpb = 8;                                                                                             \
       const int g2 = (rows + wpb - 1) / wpb;                                                                         \
       if (rms)                                                                                                       \

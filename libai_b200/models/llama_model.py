@@ -28,6 +28,8 @@ from libai_b200.ops import functional as OF
 from libai_b200.parallel import mappings
 from libai_b200.utils import distributed as dutil
 
+from libai_b200.inference.generator.generation_utils import Generator
+
 from .utils.pipeline_model import PipelineStageMixin
 from .utils.weight_init import init_method_normal, scaled_init_method_normal
 
@@ -234,7 +236,7 @@ class SFTLoss(nn.Module):
         return {"lm_loss": (loss * keep).sum() / keep.sum().clamp(min=1.0)}
 
 
-class LlamaForCausalLM(nn.Module, PipelineStageMixin):
+class LlamaForCausalLM(nn.Module, PipelineStageMixin, Generator):
     @configurable
     def __init__(self, hidden_layers, vocab_size, hidden_size, intermediate_size, num_attention_heads,
                  max_position_embeddings=1024, rms_norm_eps=1e-5, initializer_range=0.02,
@@ -320,10 +322,13 @@ class LlamaForCausalLM(nn.Module, PipelineStageMixin):
         )
         self.past_key_values = list(past_key_values)
 
-    def prepare_inputs_for_generation(self, input_ids, **kwargs):
-        out = {"input_ids": input_ids}
-        if kwargs.get("attention_mask") is not None:
-            out["attention_mask"] = kwargs["attention_mask"]
+    def prepare_inputs_for_generation(self, input_ids, past=None, attention_mask=None, use_cache=None, **kwargs):
+        """With a warm cache only the newest token is fed; the padding mask always covers cache + new tokens."""
+        if past is not None and use_cache:
+            input_ids = input_ids[:, -1:]
+        out = {"input_ids": input_ids, "use_cache": bool(use_cache)}
+        if attention_mask is not None and not bool(attention_mask.all()):
+            out["attention_mask"] = attention_mask
         return out
 
     @staticmethod

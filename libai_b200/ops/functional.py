@@ -72,6 +72,20 @@ def _gemm_ok(x: torch.Tensor, w: torch.Tensor) -> bool:
     )
 
 
+
+def _bias_grad(ext, g2, bias):
+    """Column sums of ``g2`` as the gradient of ``bias``: accumulated straight into ``bias.main_grad`` (fp32 slice of
+    the optimizer's flat gradient buffer) when the parameter owns one – no temporary, no bf16 round trip, no
+    per-parameter add kernel later – otherwise returned as a tensor for autograd."""
+    count_launch()
+    main_grad = getattr(bias, "main_grad", None)
+    if main_grad is not None and main_grad.dtype == torch.float32:
+        ext.colsum(g2, main_grad)
+        bias.grad_added_to_main_grad = True
+        return None
+    return ext.colsum(g2).to(bias.dtype)
+
+
 class _LinearFn(torch.autograd.Function):
     """Native linear: fwd ``NT`` GEMM with fused bias/activation epilogue, dgrad ``NN`` GEMM,
     wgrad ``TN`` split-K GEMM accumulating in fp32 straight into ``weight.main_grad`` when the
@@ -88,6 +102,7 @@ class _LinearFn(torch.autograd.Function):
         count_launch()
         ctx.act = act
         ctx.has_bias = bias is not None
+        ctx.bias_param = bias
         ctx.save_for_backward(x2, w, pre if need_pre else None)
         ctx.x_shape = x.shape
         return y.view(*x.shape[:-1], w.shape[0])
@@ -117,8 +132,7 @@ class _LinearFn(torch.autograd.Function):
                 gw = ext.gemm(g2, x2, 2, None, None, False, torch.float32).to(w.dtype)
             count_launch()
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = ext.colsum(g2)
-            count_launch()
+            gb = _bias_grad(ext, g2, ctx.bias_param)
         return gx, gw, gb, None
 
 
@@ -149,6 +163,7 @@ class _MLPFn(torch.autograd.Function):
         ctx.save_for_backward(x2, w1, w2, pre, h)
         ctx.x_shape = x.shape
         ctx.has_bias = b1 is not None
+        ctx.bias_param = b1
         return y.view(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
@@ -174,8 +189,7 @@ class _MLPFn(torch.autograd.Function):
         gw1 = wgrad(dpre, x2, w1) if ctx.needs_input_grad[1] else None
         gb1 = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb1 = ext.colsum(dpre)
-            count_launch()
+            gb1 = _bias_grad(ext, dpre, ctx.bias_param)
         gx = None
         if ctx.needs_input_grad[0]:
             gx = ext.gemm(dpre, w1, 1, None, None, False, torch.bfloat16).view(ctx.x_shape)
@@ -208,6 +222,7 @@ class _LayerNormFn(torch.autograd.Function):
         ctx.save_for_backward(x2, weight, mean, rstd)
         ctx.rms = rms
         ctx.has_bias = bias is not None
+        ctx.bias_param = bias
         return y.view(x.shape)
 
     @staticmethod
@@ -215,8 +230,17 @@ class _LayerNormFn(torch.autograd.Function):
         ext = load_ext()
         x2, weight, mean, rstd = ctx.saved_tensors
         g2 = gy.reshape(-1, gy.shape[-1]).contiguous()
-        gx, gw, gb = ext.norm_bwd(g2, x2, weight, mean, rstd, ctx.rms, ctx.has_bias)
         count_launch(2)
+        wg = getattr(weight, "main_grad", None)
+        bg = getattr(ctx.bias_param, "main_grad", None) if ctx.has_bias else None
+        if wg is not None and wg.dtype == torch.float32 and (not ctx.has_bias or bg is not None):
+            # dγ / dβ are reduced straight into the fp32 main-grad slices (one kernel for both)
+            gx, _, _ = ext.norm_bwd(g2, x2, weight, mean, rstd, ctx.rms, ctx.has_bias, wg, bg)
+            weight.grad_added_to_main_grad = True
+            if ctx.has_bias:
+                ctx.bias_param.grad_added_to_main_grad = True
+            return gx.view(gy.shape), None, None, None, None
+        gx, gw, gb = ext.norm_bwd(g2, x2, weight, mean, rstd, ctx.rms, ctx.has_bias, None, None)
         return gx.view(gy.shape), gw.to(weight.dtype), (gb.to(weight.dtype) if ctx.has_bias else None), None, None
 
 
@@ -248,6 +272,7 @@ class _BiasActFn(torch.autograd.Function):
         count_launch()
         ctx.save_for_backward(x2, bias)
         ctx.act = act
+        ctx.bias_param = bias
         return y.view(x.shape)
 
     @staticmethod
@@ -259,8 +284,7 @@ class _BiasActFn(torch.autograd.Function):
         count_launch()
         gb = None
         if bias is not None and ctx.needs_input_grad[1]:
-            gb = ext.colsum(gx).to(bias.dtype)
-            count_launch()
+            gb = _bias_grad(ext, gx, ctx.bias_param)
         return gx.view(gy.shape), gb, None
 
 
@@ -295,6 +319,7 @@ class _BiasAddFn(torch.autograd.Function):
         y = ext.bias_residual_fwd(x2, bias, r2)
         count_launch()
         ctx.has_bias = bias is not None
+        ctx.bias_param = bias
         ctx.has_res = residual is not None
         return y.view(x.shape)
 
@@ -302,9 +327,7 @@ class _BiasAddFn(torch.autograd.Function):
     def backward(ctx, gy):
         gb = None
         if ctx.has_bias and ctx.needs_input_grad[1]:
-            ext = load_ext()
-            gb = ext.colsum(gy.reshape(-1, gy.shape[-1]).contiguous())
-            count_launch()
+            gb = _bias_grad(load_ext(), gy.reshape(-1, gy.shape[-1]).contiguous(), ctx.bias_param)
         return gy, gb, (gy if ctx.has_res else None)
 
 

@@ -247,6 +247,30 @@ def main():
 
     record("elementwise", ew)
 
+    def accum_grads():
+        # bias / LayerNorm gradients accumulated straight into fp32 main-grad slices
+        x = torch.randn(4096, 1024, device="cuda").bfloat16()
+        acc = torch.full((1024,), 0.5, device="cuda")
+        ext.colsum(x, acc)
+        e = [rel_err(acc, x.float().sum(0) + 0.5)]
+        g = (1 + 0.1 * torch.randn(1024, device="cuda")).bfloat16()
+        b = (0.1 * torch.randn(1024, device="cuda")).bfloat16()
+        y, mean, rstd = ext.norm_fwd(x, g, b, 1e-5, False)
+        gy = torch.randn_like(x)
+        gx0, dg0, db0 = ext.norm_bwd(gy, x, g, mean, rstd, False, True, None, None)
+        dga = torch.full((1024,), 1.0, device="cuda")
+        dba = torch.full((1024,), -2.0, device="cuda")
+        gx1, _, _ = ext.norm_bwd(gy, x, g, mean, rstd, False, True, dga, dba)
+        e += [rel_err(dga, dg0 + 1.0), rel_err(dba, db0 - 2.0), rel_err(gx1, gx0)]
+        ms = timeit(lambda: ext.colsum(x, acc))
+        x2 = torch.randn(8192, 4096, device="cuda").bfloat16()
+        acc2 = torch.zeros(4096, device="cuda")
+        ms2 = timeit(lambda: ext.colsum(x2, acc2))
+        return {"ok": max(e) < 1e-2, "errs": e, "colsum_4096x1024_ms": ms, "colsum_8192x4096_ms": ms2,
+                "colsum_8192x4096_GBs": x2.numel() * 2 / ms2 / 1e6}
+
+    record("accumulating colsum / norm_bwd", accum_grads)
+
     def rope():
         from libai_b200.ops.functional import rotate_half
 
