@@ -659,9 +659,11 @@ struct AttnBwdCfg {
   static constexpr int TILE_BYTES = 128 * D * 2;
   static constexpr int PS_BYTES = 128 * 128 * 2;
   static constexpr int QST = (D == 64) ? 2 : 1;
-  static constexpr bool DQ_BULK = (D == 64);            // dQ via smem staging + TMA reduce-add (fp32)
-  static constexpr int DQ_ROW_FLOATS = D + 4;            // padded staging rows (conflict-free 16-byte stores)
-  static constexpr int DQ_STAGE_BYTES = DQ_BULK ? 128 * DQ_ROW_FLOATS * 4 : 0;
+  static constexpr bool DQ_BULK = (D == 64);            // dQ via swizzled smem staging + TMA tensor reduce-add (fp32)
+  // staging: per warp D/32 boxes of [32 rows x 32 floats] (128-byte rows, 128B swizzle = the layout of the fp32
+  // dq_accum tensor map) -> one cp.reduce.async.bulk.tensor per box instead of one bulk reduce per thread
+  static constexpr int DQ_BOX_BYTES = 32 * 128;
+  static constexpr int DQ_STAGE_BYTES = DQ_BULK ? 4 * (D / 32) * DQ_BOX_BYTES : 0;
   static constexpr int SMEM_BYTES = 2 * TILE_BYTES /*K,V*/ + 2 * QST * TILE_BYTES /*Q,dO*/ + 2 * PS_BYTES + DQ_STAGE_BYTES + 1024 + 256;
   static constexpr uint32_t S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + D;
   static constexpr uint32_t DQ_COL = (D == 64) ? 384 : 0;  // D = 128: dQ aliases the S columns
@@ -684,7 +686,7 @@ template <int D>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmap_dq, AttnBwdParams p) {
   using Cfg = AttnBwdCfg<D>;
   constexpr int QST = Cfg::QST;
   extern __shared__ uint8_t smem_raw[];
@@ -695,7 +697,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sDO = sQ + QST * Cfg::TILE_BYTES;          // QST stages
   uint8_t* sP = sDO + QST * Cfg::TILE_BYTES;
   uint8_t* sDS = sP + Cfg::PS_BYTES;
-  float* sDQ = reinterpret_cast<float*>(sDS + Cfg::PS_BYTES);
+  uint8_t* sDQ = sDS + Cfg::PS_BYTES;  // 1024-byte aligned (all tiles before it are multiples of 1 KB)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + Cfg::PS_BYTES + Cfg::DQ_STAGE_BYTES);
   uint64_t* kv_full = bars;          // 1
   uint64_t* qdo_full = bars + 1;     // 2
@@ -768,7 +770,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
     const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
     mbar_wait(kv_full, 0);
-    for (int it = 0; it < iters; ++it) {
+    // S / dP of query block `it`; issued one iteration ahead (right behind the dV/dK/dQ MMAs of block it-1) so the
+    // tensor core computes them while the softmax warps are still draining dQ of the previous block
+    auto issue_s_dp = [&](int it) {
       const int st = it % QST;
       mbar_wait(&qdo_full[st], (it / QST) & 1);
       if (D == 128) mbar_wait(dq_empty, (it & 1) ^ 1);   // dQ aliases S
@@ -791,7 +795,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         umma_commit(sdp_full);
       }
       __syncwarp();
-      mbar_wait(pds_full, it & 1);
+    };
+    issue_s_dp(0);
+    for (int it = 0; it < iters; ++it) {
+      const int st = it % QST;
+      const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
+      const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
+      mbar_wait(pds_full, it & 1);   // P / dS tiles written; the softmax warps are done reading S / dP
       if (D == 64) mbar_wait(dq_empty, (it & 1) ^ 1);
       tc_fence_after_sync();
       if (elect_one()) {
@@ -820,6 +830,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (it == iters - 1) umma_commit(acc_full);
       }
       __syncwarp();
+      if (it + 1 < iters) issue_s_dp(it + 1);
     }
   } else {
     const int quad = warp_idx % 4;
@@ -881,26 +892,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(dq_full, it & 1);
       tc_fence_after_sync();
       if constexpr (Cfg::DQ_BULK) {
-        // dQ row (D fp32) -> padded shared staging row -> one TMA reduce-add per thread into dq_accum
-        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous iteration's row consumed
-        float* srow = sDQ + r * Cfg::DQ_ROW_FLOATS;
+        // dQ rows of this warp -> swizzled [32 x 128 B] boxes in shared memory -> one TMA tensor reduce-add per box
+        // into the fp32 dq_accum (rows beyond S are clipped by the tensor map; they hold zeros anyway)
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous boxes consumed
+        __syncwarp();
+        uint8_t* wbox = sDQ + quad * (D / 32) * Cfg::DQ_BOX_BYTES;
 #pragma unroll
         for (int c = 0; c < D / 32; ++c) {
           uint32_t t[32];
           tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DQ_COL + c * 32, t);
           tmem_ld_wait();
+          uint8_t* brow = wbox + c * Cfg::DQ_BOX_BYTES + lane * 128;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<float4*>(srow + c * 32 + k * 4) =
+            *reinterpret_cast<float4*>(brow + ((k ^ (lane & 7)) * 16)) =
                 make_float4(__uint_as_float(t[k * 4]), __uint_as_float(t[k * 4 + 1]), __uint_as_float(t[k * 4 + 2]),
                             __uint_as_float(t[k * 4 + 3]));
         }
         fence_proxy_async();
-        if (q_ok) {
-          float* dst = p.dq_accum + (bh * p.S + q_idx) * D;
-          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;\n" ::"l"(dst),
-                       "r"(smem_u32(srow)), "r"(D * 4)
-                       : "memory");
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) {
+            asm volatile(
+                "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];\n" ::"l"(
+                    reinterpret_cast<uint64_t>(&tmap_dq)),
+                "r"(c * 32), "r"(q_blk * 128 + quad * 32), "r"(static_cast<int>(bh)),
+                "r"(smem_u32(wbox + c * Cfg::DQ_BOX_BYTES))
+                : "memory");
+          }
           asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
       } else {
@@ -924,7 +944,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_before_sync();
       mbar_arrive(dq_empty);
     }
-    if (Cfg::DQ_BULK) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    if (Cfg::DQ_BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
     // ---- dV / dK accumulators: thread r <-> key row r
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
@@ -999,7 +1019,7 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloa
 namespace {
 template <int D>
 cudaError_t launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-                       const lb::AttnBwdParams& p, cudaStream_t s) {
+                       const CUtensorMap& tdq, const lb::AttnBwdParams& p, cudaStream_t s) {
   using Cfg = lb::AttnBwdCfg<D>;
   auto kern = lb::attn_bwd_kernel<D>;
   static bool configured = false;
@@ -1009,7 +1029,7 @@ cudaError_t launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
     configured = true;
   }
   dim3 grid((p.S + 127) / 128, p.A, p.B);
-  kern<<<grid, lb::ATT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+  kern<<<grid, lb::ATT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, tdo, tdq, p);
   return cudaGetLastError();
 }
 }  // namespace
@@ -1026,6 +1046,16 @@ extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const
   if (!make_qkv_tmap(&tk, k, B, A, S, D, k_strides)) return -2;
   if (!make_qkv_tmap(&tv, v, B, A, S, D, v_strides)) return -2;
   if (!make_qkv_tmap(&tdo, dout, B, A, S, D, do_strides)) return -2;
+  CUtensorMap tdq;
+  {
+    // fp32 dq_accum [B*A, S, D]: 32x32-float boxes (128-byte rows, 128B swizzle) for the TMA reduce-add
+    uint64_t dims[3] = {(uint64_t)D, (uint64_t)S, (uint64_t)B * A};
+    uint64_t strides[3] = {4, (uint64_t)D * 4, (uint64_t)S * D * 4};
+    uint32_t box[3] = {32, 32, 1};
+    if (!lb_host::make_tmap_typed(&tdq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dq_accum, 3, dims, strides, box,
+                                  CU_TENSOR_MAP_SWIZZLE_128B))
+      return -2;
+  }
   const long rows = (long)B * A * S;
   lb::attn_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta, B, A, S, D, do_strides[0], do_strides[1], do_strides[2]);
@@ -1046,7 +1076,7 @@ extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.kv_lens = kv_lens;
-  cudaError_t e = (D == 64) ? launch_bwd<64>(tq, tk, tv, tdo, p, s) : launch_bwd<128>(tq, tk, tv, tdo, p, s);
+  cudaError_t e = (D == 64) ? launch_bwd<64>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd<128>(tq, tk, tv, tdo, tdq, p, s);
   if (e != cudaSuccess) return (int)e;
   const long nvec = rows * D / 4;
   int blocks = (int)((nvec + 255) / 256);

@@ -175,34 +175,49 @@ __global__ void rope_qkv_kernel(const __nv_bfloat16* __restrict__ x, const float
   }
 }
 
-// out[c] += sum_r x[r, c]: 16-byte loads (8 columns per thread), a block covers 1024 columns x rows_per_block rows
-__global__ void __launch_bounds__(128) colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
+// out[c] += sum_r x[r, c]: block = 32 column lanes (8 columns each, 16-byte loads) x 8 row stripes; the stripes are
+// combined in shared memory so that a block issues one atomic per column (the first version issued one per thread
+// and serialised on 256-way contended addresses).
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
                                                          int M, int N, int rows_per_block) {
-  const int c8 = (blockIdx.x * 128 + threadIdx.x) * 8;
-  if (c8 >= N) return;
+  __shared__ float sm[8][32][9];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int c8 = (blockIdx.x * 32 + tx) * 8;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int r = r0;
-  for (; r + 3 < r1; r += 4) {  // four independent loads in flight
-    uint4 q[4];
+  if (c8 < N) {
+    int r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {  // four independent 16-byte loads in flight
+      uint4 q[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) q[j] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r + j) * N + c8);
+      for (int j = 0; j < 4; ++j) q[j] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r + j * 8) * N + c8);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 a = unpack_bf16(q[j].x), b = unpack_bf16(q[j].y), c = unpack_bf16(q[j].z), d = unpack_bf16(q[j].w);
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16(q[j].x), b = unpack_bf16(q[j].y), c = unpack_bf16(q[j].z), d = unpack_bf16(q[j].w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+        acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 q = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * N + c8);
+      const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
       acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
       acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
     }
   }
-  for (; r < r1; ++r) {
-    const uint4 q = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * N + c8);
-    const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
-    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-    acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
-  }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(out + c8 + j, acc[j]);
+  for (int j = 0; j < 8; ++j) sm[ty][tx][j] = acc[j];
+  __syncthreads();
+  // 256 threads <-> 256 columns of the block
+  const int col = threadIdx.x;
+  const int gcol = blockIdx.x * 256 + col;
+  if (gcol < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sm[j][col / 8][col % 8];
+    atomicAdd(out + gcol, t);
+  }
 }
 
 // out[c] += sum_r x[r, c]   (out fp32, zero-initialised by the caller)
@@ -469,13 +484,13 @@ extern "C" int lb_colsum(const void* x, float* out, int M, int N, int accumulate
   if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, s);
   if (M == 0) return 0;
   if (N % 8 == 0) {
-    const int col_blocks = (N + 1023) / 1024;
-    int row_blocks = 592 / col_blocks;
+    const int col_blocks = (N + 255) / 256;
+    int row_blocks = (2 * 148 + col_blocks - 1) / col_blocks;  // ~2 blocks per SM
+    if (row_blocks > (M + 63) / 64) row_blocks = (M + 63) / 64;
     if (row_blocks < 1) row_blocks = 1;
-    if (row_blocks > (M + 15) / 16) row_blocks = (M + 15) / 16;
     const int rpb = (M + row_blocks - 1) / row_blocks;
     dim3 grid(col_blocks, (M + rpb - 1) / rpb);
-    lb::colsum_vec_kernel<<<grid, 128, 0, s>>>((const bf16*)x, out, M, N, rpb);
+    lb::colsum_vec_kernel<<<grid, 256, 0, s>>>((const bf16*)x, out, M, N, rpb);
     return (int)cudaGetLastError();
   }
   const int rpb = 128;

@@ -495,8 +495,8 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, CUtensorMapSwizzle swizzle) {
+bool make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_tiled();
   if (fn == nullptr) return false;
   cuuint64_t gdim[5];
@@ -509,10 +509,31 @@ bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t
     estr[i] = 1;
     if (i > 0) gstride[i - 1] = strides_bytes[i];
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstride, gbox, estr,
+  CUresult r = fn(out, dtype, rank, const_cast<void*>(base), gdim, gstride, gbox, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT) {
+    // driver entry point called on a thread (e.g. the autograd engine's) that has not touched the runtime yet:
+    // bind the primary context to this thread and retry
+    cudaFree(nullptr);
+    r = fn(out, dtype, rank, const_cast<void*>(base), gdim, gstride, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[libai_b200] cuTensorMapEncodeTiled failed (%d): base=%p rank=%d dims=", (int)r, base, rank);
+    for (int i = 0; i < rank; ++i) fprintf(stderr, "%llu ", (unsigned long long)gdim[i]);
+    fprintf(stderr, "strides(B)=");
+    for (int i = 0; i + 1 < rank; ++i) fprintf(stderr, "%llu ", (unsigned long long)gstride[i]);
+    fprintf(stderr, "box=");
+    for (int i = 0; i < rank; ++i) fprintf(stderr, "%u ", gbox[i]);
+    fprintf(stderr, "\n");
+  }
   return r == CUDA_SUCCESS;
+}
+
+bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle);
 }
 
 }  // namespace lb_host
