@@ -1,0 +1,11 @@
+from libai_b200.config import LazyCall
+from libai_b200.models import ResMLP
+
+from .resmlp_12 import cfg
+
+cfg.patch_size = 8
+cfg.embed_dim = 768
+cfg.depth = 24
+cfg.init_scale = 1e-06
+
+model = LazyCall(ResMLP)(cfg=cfg)

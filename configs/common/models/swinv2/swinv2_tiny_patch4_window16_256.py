@@ -1,0 +1,8 @@
+from libai_b200.config import LazyCall
+from libai_b200.models import SwinTransformerV2
+
+from .swinv2_tiny_patch4_window8_256 import cfg
+
+cfg.window_size = 16
+
+model = LazyCall(SwinTransformerV2)(cfg=cfg)

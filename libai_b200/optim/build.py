@@ -105,3 +105,20 @@ def reduce_param_groups(params: List[Dict[str, Any]]) -> List[Dict[str, Any]]:
         g["params"] = plist
         out.append(g)
     return out
+
+
+def set_weight_decay(model, skip_list=(), skip_keywords=()):
+    """Two param groups – decayed / not decayed (1-D tensors, biases, names in ``skip_list`` or containing one of
+    ``skip_keywords``) – as used by the SwinV2 recipes (reference configs/swinv2_imagenet.py:74-101 defines the
+    same helper inline)."""
+    if isinstance(skip_list, str):
+        skip_list = (skip_list,)
+    has_decay, no_decay = [], []
+    for name, param in model.named_parameters():
+        if not param.requires_grad or param.device.type == "meta":
+            continue
+        if param.dim() == 1 or name.endswith(".bias") or name in skip_list or any(k in name for k in skip_keywords):
+            no_decay.append(param)
+        else:
+            has_decay.append(param)
+    return [{"params": has_decay}, {"params": no_decay, "weight_decay": 0.0}]

@@ -473,3 +473,55 @@ class SGD(FlatOptimizer):
         master.add_(g, alpha=-lr)
         if fg.master is not None:
             fg.param_flat[fg.lo : fg.hi].copy_(master)
+
+
+class LAMB(FlatOptimizer):
+    """Layer-wise adaptive moments (You et al. 2019) on the flat buffers: Adam direction per element, then one trust
+    ratio ``‖w‖ / ‖update‖`` per *parameter tensor*.  Used by the ResMLP recipe (reference configs/resmlp_imagenet.py:52
+    selects ``flow.optim.LAMB``).  Under ZeRO the per-tensor norms are completed with one all-reduce over the
+    data-parallel group (a shard may cut through a tensor)."""
+
+    state_names = ("exp_avg", "exp_avg_sq")
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, adam_w_mode=True,
+                 do_bias_correction=True, **unused):
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, adam_w_mode=adam_w_mode,
+                        do_bias_correction=do_bias_correction)
+        super().__init__(params, defaults)
+
+    def _update(self, group, fg, step, scale):
+        lr, (b1, b2), eps, wd = group["lr"], group["betas"], group["eps"], group["weight_decay"]
+        bc1, bc2 = (1.0 - b1 ** step, 1.0 - b2 ** step) if group.get("do_bias_correction", True) else (1.0, 1.0)
+        g = fg.grad_shard()
+        if scale is not None:
+            g = g * scale
+        master = fg.master_view()
+        m, v = fg.state["exp_avg"], fg.state["exp_avg_sq"]
+        if not group.get("adam_w_mode", True) and wd != 0.0:
+            g = g + wd * master
+        m.mul_(b1).add_(g, alpha=1.0 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1.0 - b2)
+        upd = (m / bc1) / ((v / bc2).sqrt_().add_(eps))
+        if group.get("adam_w_mode", True) and wd != 0.0:
+            upd.add_(master, alpha=wd)
+        # per-tensor squared norms over the part of each tensor that lives in [lo, hi)
+        n = len(fg.params)
+        sq = torch.zeros(2, n, dtype=torch.float32, device=master.device)
+        spans = []
+        for i, (p, off) in enumerate(zip(fg.params, fg.offsets)):
+            a, b = max(off, fg.lo) - fg.lo, min(off + p.numel(), fg.hi) - fg.lo
+            spans.append((a, b))
+            if b > a:
+                sq[0, i] = master[a:b].pow(2).sum()
+                sq[1, i] = upd[a:b].pow(2).sum()
+        if fg.sharded:
+            topo = dutil.get_dist_util()
+            if topo.data_parallel_size > 1:
+                dist.all_reduce(sq, group=topo.dp_group)
+        w_norm, u_norm = sq[0].sqrt(), sq[1].sqrt()
+        trust = torch.where((w_norm > 0) & (u_norm > 0), w_norm / u_norm, torch.ones_like(w_norm))
+        for i, (a, b) in enumerate(spans):
+            if b > a:
+                master[a:b].add_(upd[a:b] * trust[i], alpha=-lr)
+        if fg.master is not None:
+            fg.param_flat[fg.lo : fg.hi].copy_(master)
