@@ -310,7 +310,15 @@ class FlatOptimizer(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ (de)serialisation
     def _names(self, fg: _Group) -> List[str]:
-        return [self._param_names.get(id(p), f"param_{id(p)}") for p in fg.params]
+        if not hasattr(self, "_positional_names"):
+            # fallback when no names were configured: position in the optimizer's param groups (stable across runs)
+            self._positional_names = {}
+            k = 0
+            for g in self.param_groups:
+                for p in g["params"]:
+                    self._positional_names[id(p)] = f"param_{k}"
+                    k += 1
+        return [self._param_names.get(id(p), self._positional_names.get(id(p), f"param_{id(p)}")) for p in fg.params]
 
     def _gather_shard(self, fg: _Group, shard: torch.Tensor) -> torch.Tensor:
         topo = dutil.get_dist_util()

@@ -266,6 +266,9 @@ class PreTrainedTokenizer:
                     nxt.append(piece)
                     continue
                 parts = piece.split(tok)
+                if len(parts) == 1:  # token absent: keep the text untouched (leading spaces matter for byte-BPE)
+                    nxt.append(piece)
+                    continue
                 for i, part in enumerate(parts):
                     part = part.strip()  # the white space around a no-split token belongs to it
                     if part:

@@ -211,8 +211,11 @@ def main():
     record("ZeRO fused RS+Adam+AG vs NCCL", zero)
 
     if rank == 0:
-        os.makedirs("gpurun_out", exist_ok=True)
-        with open("gpurun_out/comm_check.json", "w") as f:
+        out = "gpurun_out/comm_check.json"
+        if "--out" in sys.argv:
+            out = sys.argv[sys.argv.index("--out") + 1]
+        os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
+        with open(out, "w") as f:
             json.dump(RESULTS, f, indent=1)
         bad = [r["name"] for r in RESULTS if not r["ok"]]
         print(f"SUMMARY: {len(RESULTS) - len(bad)}/{len(RESULTS)} ok; failed: {bad}")
