@@ -1,0 +1,6 @@
+"""``BaichuanDataset`` (reference projects/Baichuan/baichuan_dataset.py): pre-tokenised SFT samples."""
+from projects.common.sft import SFTDataset
+
+
+class BaichuanDataset(SFTDataset):
+    pass

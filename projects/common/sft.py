@@ -143,3 +143,100 @@ class SentencePieceTokenizer:
 
     def convert_id_to_token(self, index):
         return self.sp_model.IdToPiece(index)
+
+
+class ByteBPEChatTokenizer:
+    """Byte-level BPE (``vocab.json`` + ``merges.txt``) behind the same small API as ``SentencePieceTokenizer``
+    (Aquila: reference projects/Aquila/tokenizer.py; Qwen2: reference projects/Qwen/tokenizer.py).  ``special_tokens``
+    are matched verbatim before BPE; ``pattern`` overrides the GPT-2 pre-tokenisation regex."""
+
+    def __init__(self, vocab_file, merges_file, bos_token=None, eos_token="<|endoftext|>", pad_token="<|endoftext|>",
+                 unk_token="<|endoftext|>", special_tokens=(), pattern=None, errors="replace"):
+        import regex as re
+
+        from libai_b200.tokenizer.tokenization_gpt2 import ByteLevelBPE
+
+        self._bpe = ByteLevelBPE(vocab_file, merges_file, errors)
+        if pattern is not None:
+            self._bpe.pat = re.compile(pattern)
+        self.encoder, self.decoder = self._bpe.encoder, self._bpe.decoder
+        self.special = {}
+        for tok in list(special_tokens) + [t for t in (bos_token, eos_token, pad_token, unk_token) if t]:
+            if tok not in self.special:
+                if tok not in self.encoder:
+                    self.encoder[tok] = len(self.encoder)
+                    self.decoder[self.encoder[tok]] = tok
+                self.special[tok] = self.encoder[tok]
+        self._special_re = re.compile("(" + "|".join(re.escape(t) for t in sorted(self.special, key=len, reverse=True)) + ")") \
+            if self.special else None
+        self.bos_token, self.eos_token, self.pad_token, self.unk_token = bos_token, eos_token, pad_token, unk_token
+        self.bos_token_id = self.encoder.get(bos_token) if bos_token else None
+        self.eos_token_id = self.encoder.get(eos_token) if eos_token else None
+        self.pad_token_id = self.encoder.get(pad_token, 0) if pad_token else 0
+        self.eod_token = None
+
+    @property
+    def vocab_size(self):
+        return len(self.encoder)
+
+    def __len__(self):
+        return self.vocab_size
+
+    def padded_vocab_size(self, multiple=1):
+        return (self.vocab_size + multiple - 1) // multiple * multiple
+
+    def get_vocab(self):
+        return dict(self.encoder)
+
+    def encode(self, text, return_tensors=None, **kwargs):
+        ids = []
+        chunks = self._special_re.split(text) if self._special_re is not None else [text]
+        for chunk in chunks:
+            if not chunk:
+                continue
+            if chunk in self.special:
+                ids.append(self.special[chunk])
+            else:
+                ids.extend(self.encoder.get(t, self.encoder.get(self.unk_token, 0)) for t in self._bpe.tokenize(chunk))
+        if return_tensors in ("pt", "of"):
+            return torch.tensor([ids], dtype=torch.long)
+        return ids
+
+    def tokenize(self, text, add_bos=False, add_eos=False, padding=False, device=None, max_length=4096, **kwargs):
+        texts = [text] if isinstance(text, str) else list(text)
+        tokens = [self.encode(s)[:max_length] for s in texts]
+        if add_bos and self.bos_token_id is not None:
+            tokens = [[self.bos_token_id] + t for t in tokens]
+        if add_eos and self.eos_token_id is not None:
+            tokens = [t + [self.eos_token_id] for t in tokens]
+        if padding or len({len(t) for t in tokens}) > 1:
+            width = max(len(t) for t in tokens)
+            tokens = [t + (width - len(t)) * [self.pad_token_id] for t in tokens]
+        out = torch.tensor(tokens, dtype=torch.long)
+        if device and (device != "cuda" or torch.cuda.is_available()):
+            out = out.to(device)
+        return out
+
+    def decode(self, tokens, skip_special_tokens=True, **kwargs):
+        if torch.is_tensor(tokens):
+            tokens = tokens.tolist()
+        pieces, run = [], []
+        special_ids = set(self.special.values())
+        for t in tokens:
+            if t in special_ids:
+                if run:
+                    pieces.append(self._bpe.detokenize(run))
+                    run = []
+                if not skip_special_tokens:
+                    pieces.append(self.decoder[t])
+            else:
+                run.append(self.decoder.get(t, ""))
+        if run:
+            pieces.append(self._bpe.detokenize(run))
+        return "".join(pieces)
+
+    def convert_token_to_id(self, token):
+        return self.encoder.get(token)
+
+    def convert_id_to_token(self, index):
+        return self.decoder.get(index)
