@@ -1,0 +1,13 @@
+"""Mask helpers (reference projects/T5/utils/mask.py)."""
+import torch
+
+
+def extended_mask(mask, is_decoder=False):
+    """``[b, s]`` / ``[b, q, k]`` → boolean ``[b, 1, q, k]`` (lower-triangular when ``is_decoder``)."""
+    m = mask.bool()
+    if m.dim() == 2:
+        m = m[:, None, :] & m[:, :, None]
+    m = m[:, None]
+    if is_decoder:
+        m = m & torch.ones(m.shape[-2:], dtype=torch.bool, device=m.device).tril()
+    return m
