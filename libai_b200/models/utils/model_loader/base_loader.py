@@ -87,22 +87,25 @@ class LoadPretrainedBase:
         return model
 
     def _align_prefix(self, model, state_dict):
-        """Add / strip the task-model prefix so a backbone checkpoint fits a task model and vice versa."""
-        p2 = self.base_model_prefix_2
-        if not p2:
-            return state_dict
+        """Backbone checkpoint ↔ task model (or the reverse): pick, among {as is, first segment stripped, task prefix
+        added}, the key mapping that matches most of the model's own keys."""
         own = set(model.state_dict().keys())
-        has_prefix_module = any(k.startswith(p2 + ".") for k in own)
-        ckpt_has_prefix = any(k.startswith(p2 + ".") for k in state_dict)
-        if has_prefix_module and not ckpt_has_prefix:
-            return collections.OrderedDict(
-                ((p2 + "." + k) if (p2 + "." + k) in own else k, v) for k, v in state_dict.items()
-            )
-        if not has_prefix_module and ckpt_has_prefix:
-            return collections.OrderedDict(
-                (k[len(p2) + 1 :] if k.startswith(p2 + ".") else k, v) for k, v in state_dict.items()
-            )
-        return state_dict
+
+        def score(mapping):
+            return sum(1 for k in mapping if k in own)
+
+        candidates = [collections.OrderedDict(state_dict)]
+        firsts = {k.split(".", 1)[0] for k in state_dict if "." in k}
+        for first in firsts:
+            candidates.append(collections.OrderedDict(
+                (k[len(first) + 1 :] if k.startswith(first + ".") else k, v) for k, v in state_dict.items()))
+        prefixes = {k.split(".", 1)[0] for k in own if "." in k}
+        if self.base_model_prefix_2:
+            prefixes.add(self.base_model_prefix_2)
+        for p2 in prefixes:
+            candidates.append(collections.OrderedDict(
+                ((p2 + "." + k) if (p2 + "." + k) in own else k, v) for k, v in state_dict.items()))
+        return max(candidates, key=score)
 
 
 class ModelLoaderLiBai(LoadPretrainedBase):
