@@ -61,9 +61,9 @@ def _tiny_gpt(impl):
     opt = AdamW([{"params": list(model.parameters())}], lr=1e-3)
     opt.setup()
     g = torch.Generator(device="cuda").manual_seed(1)
+    ids = torch.randint(0, 512, (4, 256), device="cuda", generator=g)  # one fixed batch: the loss must go down
     losses = []
-    for _ in range(4):
-        ids = torch.randint(0, 512, (4, 256), device="cuda", generator=g)
+    for _ in range(6):
         opt.zero_grad()
         loss = model(ids, ids)["lm_loss"]
         loss.backward()
@@ -81,7 +81,7 @@ def test_native_training_step_matches_reference_path():
     ref = _tiny_gpt("ref")
     os.environ["LIBAI_B200_IMPL"] = "native"
     assert all(abs(a - b) < 5e-2 for a, b in zip(native, ref)), (native, ref)
-    assert native[-1] < native[0]
+    assert native[-1] < native[0] - 0.05, native
 
 
 def test_smoke_entry_point():
