@@ -24,6 +24,8 @@ namespace lb {
 constexpr int ATT_BM = 128;   // queries per CTA
 constexpr int ATT_BN = 128;   // keys per tile
 constexpr int ATT_THREADS = 192;
+constexpr int ATT_BWD_THREADS = 320;
+constexpr int ATT_FWD2_THREADS = 320; // forward v2: 8 softmax warps (row pairs exchange their block max through smem)  // TMA + MMA + 8 compute warps (two per TMEM lane quadrant: each takes half of the columns)
 
 template <int D>
 struct AttnCfg {
@@ -316,14 +318,17 @@ template <int D>
 struct AttnCfg2 {
   static constexpr int QK_CHUNKS = D / 64;
   static constexpr int TILE_BYTES = ATT_BN * D * 2;
-  static constexpr int SMEM_BYTES = 5 * TILE_BYTES + 1024 + 256;   // Q + 2 x (K, V)
-  static constexpr uint32_t TMEM_COLS = 256;
-  static constexpr uint32_t S_COL = 0, O_COL = 128;                // P aliases S columns [0, 64)
+  static constexpr int XCHG_BYTES = 2 * 2 * 128 * 4;               // block-max exchange: [parity][half][row]
+  static constexpr int SMEM_BYTES = 5 * TILE_BYTES + XCHG_BYTES + 1024 + 256;   // Q + 2 x (K, V)
+  static constexpr uint32_t TMEM_COLS = (D == 64) ? 256 : 512;
+  // S fp32 [0,128) | O fp32 [128,128+D) | P bf16 (64 columns) behind O: P no longer aliases S, so the two softmax
+  // halves never race on it and Q·Kᵀ of the next block may be issued right behind P·V of the current one
+  static constexpr uint32_t S_COL = 0, O_COL = 128, P_COL = 128 + D;
   static constexpr int MIN_CTAS = (D == 64) ? 2 : 1;
 };
 
 template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, AttnCfg2<D>::MIN_CTAS)
+__global__ void __launch_bounds__(ATT_FWD2_THREADS, AttnCfg2<D>::MIN_CTAS)
 attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, AttnFwdParams p) {
   using Cfg = AttnCfg2<D>;
@@ -332,7 +337,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::TILE_BYTES;
   uint8_t* sV = sK + 2 * Cfg::TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Cfg::TILE_BYTES);
+  float* sXchg = reinterpret_cast<float*>(sV + 2 * Cfg::TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Cfg::TILE_BYTES + Cfg::XCHG_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* k_empty = bars + 3;
@@ -364,7 +370,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(o_full, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -404,7 +410,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     for (int j = 0; j < nkv; ++j) {
       const int b = j & 1;
       mbar_wait(&k_full[b], (j >> 1) & 1);
-      if (j > 0) mbar_wait(o_full, (j - 1) & 1);   // P·V of the previous block has retired: S/P columns are free
+      // (S is free: P·V(j-1) was only issued after the softmax warps finished reading S(j-1))
       tc_fence_after_sync();
       if (elect_one()) {
         const uint32_t k_addr = smem_u32(sK + b * Cfg::TILE_BYTES);
@@ -426,7 +432,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
         for (int kk = 0; kk < ATT_BN / 16; ++kk) {
           // A = P from tensor memory: 16 bf16 per row = 8 columns per k-step
-          umma_f16_ts(tmem_base + Cfg::O_COL, tmem_base + Cfg::S_COL + kk * 8,
+          umma_f16_ts(tmem_base + Cfg::O_COL, tmem_base + Cfg::P_COL + kk * 8,
                       make_smem_desc_sw128(v_addr + kk * (16 * 128), ATT_BN * 128, 1024), idesc_pv,
                       (j > 0 || kk > 0) ? 1u : 0u);
         }
@@ -437,43 +443,46 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
   } else {
     const int quad = warp_idx % 4;
+    const int half = (warp_idx - 2) / 4;        // this warp's 64 of the 128 key columns
     const int r = quad * 32 + lane;
     const int q_idx = q0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_off + Cfg::S_COL;
-    const uint32_t o_addr = tmem_base + lane_off + Cfg::O_COL;
-    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t s_addr = tmem_base + lane_off + Cfg::S_COL + half * 64;
+    const uint32_t p_addr = tmem_base + lane_off + Cfg::P_COL + half * 32;
+    const uint32_t o_addr = tmem_base + lane_off + Cfg::O_COL + half * (D / 2);
+    float m_run = -INFINITY, l_run = 0.f;       // l_run: partial row sum over this half's columns
 
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
-      const int k0 = j * ATT_BN;
-      const bool need_mask = (p.causal && j == q_blk) || (k0 + ATT_BN > kv_len);
-      // ---- pass 1: row max (two 64-column halves, two loads in flight)
-      // (the masked / unmasked variants are separate code copies: a per-element `if (need_mask)` costs a
-      //  BSSY/BRA/BSYNC triple per element pair - 40% of the instructions of this loop in the first profile)
+      const int k0 = j * ATT_BN + half * 64;
+      const bool need_mask = (p.causal && j == q_blk) || (j * ATT_BN + ATT_BN > kv_len);
+      // ---- pass 1: max over this half's columns, then exchange with the partner thread of the same row
       float mx = -INFINITY;
       auto pass1 = [&](auto mask_tag) {
         constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t t0[32], t1[32];
-          tmem_ld_32x32b_x32(s_addr + h * 64, t0);
-          tmem_ld_32x32b_x32(s_addr + h * 64 + 32, t1);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t t[32];
+          tmem_ld_32x32b_x32(s_addr + c * 32, t);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x0 = __uint_as_float(t0[i]), x1 = __uint_as_float(t1[i]);
+          for (int i = 0; i < 32; i += 2) {
+            float x0 = __uint_as_float(t[i]), x1 = __uint_as_float(t[i + 1]);
             if constexpr (MASK) {
-              const int k_a = k0 + h * 64 + i, k_b = k_a + 32;
-              if (k_a >= kv_len || (p.causal && k_a > q_idx)) x0 = -INFINITY;
-              if (k_b >= kv_len || (p.causal && k_b > q_idx)) x1 = -INFINITY;
+              const int kidx = k0 + c * 32 + i;
+              if (kidx >= kv_len || (p.causal && kidx > q_idx)) x0 = -INFINITY;
+              if (kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) x1 = -INFINITY;
             }
             mx = fmaxf(mx, fmaxf(x0, x1));
           }
         }
       };
       if (need_mask) pass1(std::true_type{}); else pass1(std::false_type{});
+      float* xch = sXchg + (j & 1) * 256;
+      xch[half * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);
       // ---- lazy rescale: only move the reference max when it grows by more than 2^8
       const float m_cand = fmaxf(m_run, mx * p.scale_log2);
       const bool bump = (m_cand - m_run > 8.0f) || (m_run == -INFINITY && m_cand != -INFINITY);
@@ -484,13 +493,13 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       }
       const bool bump_any = __any_sync(0xffffffffu, bump && j > 0);
       const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-      // ---- pass 2: P = exp2(s * scale - m) as bf16 back into the S columns
+      // ---- pass 2: P = exp2(s * scale - m) as bf16 into the P columns
       float rowsum = 0.f;
       auto pass2 = [&](auto mask_tag) {
         constexpr bool MASK = decltype(mask_tag)::value;
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < ATT_BN / 32; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t t[32];
           tmem_ld_32x32b_x32(s_addr + c * 32, t);
           tmem_ld_wait();
@@ -504,20 +513,22 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               if (kidx >= kv_len || (p.causal && kidx > q_idx)) e0 = 0.f;
               if (kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) e1 = 0.f;
             }
-            rs0 += e0;   // two independent accumulation chains
+            rs0 += e0;
             rs1 += e1;
             packed[i / 2] = pack_bf16(e0, e1);
           }
-          tmem_st_32x32b_x16(s_addr + c * 16, packed);
+          tmem_st_32x32b_x16(p_addr + c * 16, packed);
         }
         rowsum = rs0 + rs1;
       };
       if (need_mask) pass2(std::true_type{}); else pass2(std::false_type{});
       l_run = l_run * alpha + rowsum;
-      // ---- O *= alpha (rare): P·V of block j-1 has retired (the MMA warp waited for it before issuing S_j)
+      // ---- O *= alpha (rare): wait until P·V of block j-1 has retired, then rescale this half's O columns
       if (bump_any) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after_sync();
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
+        for (int c = 0; c < D / 64; ++c) {
           uint32_t t[32];
           tmem_ld_32x32b_x32(o_addr + c * 32, t);
           tmem_ld_wait();
@@ -530,13 +541,17 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tc_fence_before_sync();
       mbar_arrive(p_full);
     }
-    // ---- epilogue: O / l  →  [B, S, A, D]
+    // ---- epilogue: combine the two partial row sums, O / l  →  [B, S, A, D]
+    float* xch = sXchg + (nkv & 1) * 256;
+    xch[half * 128 + r] = l_run;
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    l_run += xch[(half ^ 1) * 128 + r];
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after_sync();
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-    __nv_bfloat16* orow = p.o + ((static_cast<size_t>(batch) * p.S + q_idx) * p.A + head) * D;
+    __nv_bfloat16* orow = p.o + ((static_cast<size_t>(batch) * p.S + q_idx) * p.A + head) * D + half * (D / 2);
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < D / 64; ++c) {
       uint32_t t[32];
       tmem_ld_32x32b_x32(o_addr + c * 32, t);
       tmem_ld_wait();
@@ -551,7 +566,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
       }
     }
-    if (q_idx < p.S)
+    if (half == 0 && q_idx < p.S)
       p.lse[(static_cast<size_t>(batch) * p.A + head) * p.S + q_idx] =
           (m_run == -INFINITY) ? -INFINITY : (m_run + log2f(l_run)) * 0.6931471805599453f;
   }
@@ -587,7 +602,7 @@ cudaError_t launch_fwd_v2(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     configured = true;
   }
   dim3 grid((p.S + lb::ATT_BM - 1) / lb::ATT_BM, p.A, p.B);
-  kern<<<grid, lb::ATT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, p);
+  kern<<<grid, lb::ATT_FWD2_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, p);
   return cudaGetLastError();
 }
 
@@ -683,7 +698,7 @@ struct AttnBwdParams {
 };
 
 template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_dq, AttnBwdParams p) {
@@ -729,10 +744,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&qdo_empty[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, 256);
     mbar_init(pds_empty, 1);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 128);
+    mbar_init(dq_empty, 256);
     mbar_init(acc_full, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -834,6 +849,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else {
     const int quad = warp_idx % 4;
+    const int half = (warp_idx - 2) / 4;   // column half of S / dP (and of dQ, dK, dV) handled by this warp
     const int r = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const size_t bh = static_cast<size_t>(batch) * p.A + head;
@@ -853,7 +869,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       auto pds = [&](auto mask_tag) {
         constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = half * 2; c < half * 2 + 2; ++c) {
           uint32_t ts[32], td[32];
           tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::S_COL + c * 32, ts);
           tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DP_COL + c * 32, td);
@@ -897,8 +913,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous boxes consumed
         __syncwarp();
         uint8_t* wbox = sDQ + quad * (D / 32) * Cfg::DQ_BOX_BYTES;
+        constexpr int DQ_PER_HALF = D / 64;  // 32-column chunks per warp
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
+        for (int c = half * DQ_PER_HALF; c < (half + 1) * DQ_PER_HALF; ++c) {
           uint32_t t[32];
           tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DQ_COL + c * 32, t);
           tmem_ld_wait();
@@ -913,7 +930,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
-          for (int c = 0; c < D / 32; ++c) {
+          for (int c = half * DQ_PER_HALF; c < (half + 1) * DQ_PER_HALF; ++c) {
             asm volatile(
                 "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];\n" ::"l"(
                     reinterpret_cast<uint64_t>(&tmap_dq)),
@@ -926,7 +943,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       } else {
       float* dq_row = p.dq_accum + (bh * p.S + q_idx) * D;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = half * (D / 64); c < (half + 1) * (D / 64); ++c) {
         uint32_t t[32];
         tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DQ_COL + c * 32, t);
         tmem_ld_wait();
@@ -955,7 +972,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __nv_bfloat16* row = base + batch * p.g_strides[0] + head * p.g_strides[1] + static_cast<long>(k_idx) * p.g_strides[2];
       const uint32_t col = which == 0 ? Cfg::DV_COL : Cfg::DK_COL;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = half * (D / 64); c < (half + 1) * (D / 64); ++c) {
         uint32_t t[32];
         tmem_ld_32x32b_x32(tmem_base + lane_off + col + c * 32, t);
         tmem_ld_wait();
@@ -1029,7 +1046,7 @@ cudaError_t launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
     configured = true;
   }
   dim3 grid((p.S + 127) / 128, p.A, p.B);
-  kern<<<grid, lb::ATT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, tdo, tdq, p);
+  kern<<<grid, lb::ATT_BWD_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, tdo, tdq, p);
   return cudaGetLastError();
 }
 }  // namespace
