@@ -45,8 +45,9 @@ struct GemmParams {
 
 // Fused collective modes (tensor parallel): peer pointers refer to NVLink peer-mapped symmetric memory.
 //   COMM_AG : all-gather -> GEMM.  A = [M, K] "gathered" buffer; rank r produced rows [r*rpr, (r+1)*rpr) of its own
-//             buffer, the other rows are pulled from the owners by `n_comm` dedicated CTAs while the GEMM CTAs
-//             already work on the local rows; per-row-block arrival counters gate the TMA loads.
+//             buffer and `n_comm` dedicated CTAs push them into every peer's buffer (P2P stores) while the GEMM CTAs
+//             already work on the local rows; per-row-block arrival counters (bumped by the pushing peer) gate the
+//             TMA loads of the remote rows.
 //   COMM_RS : GEMM -> reduce-scatter.  Each rank computes the full [M, N] partial product; the epilogue stores
 //             row block tiles straight into the owner's staging slot (P2P stores) and bumps the owner's arrival
 //             counter; after its tiles every CTA helps reducing the local rows (sum over sources + bias + residual).
@@ -58,8 +59,8 @@ struct CommParams {
   uint32_t epoch;               // call counter (>= 1) for the "shard ready" handshake
   uint32_t target;              // cumulative arrival count expected by this call (per row block)
   __nv_bfloat16* peer_buf[8];   // AG: gathered buffers of all ranks; RS: staging buffers of all ranks
-  uint32_t* peer_flags[8];      // AG: handshake flag rows of all ranks; RS: arrival counters of all ranks
-  uint32_t* chunk_flags;        // AG: local per-row-block arrival counters
+  uint32_t* peer_flags[8];      // per-row-block arrival counters of all ranks (AG: M/128 entries; RS: rows_per_rank/128)
+  uint32_t* chunk_flags;        // unused (kept for ABI stability)
   const __nv_bfloat16* residual;  // RS: optional [rows_per_rank, N]
   __nv_bfloat16* rs_out;        // RS: [rows_per_rank, N]
   long staging_parity_off;      // RS: element offset of the staging half used by this call
@@ -152,38 +153,88 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (n_comm > 0 && static_cast<int>(blockIdx.x) < n_comm) {
-    // ======================= COMM_AG copy CTA: pull the peers' row blocks over NVLink =======================
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      __threadfence_system();
-      for (int q = 0; q < cp.world; ++q)
-        asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(cp.peer_flags[q] + cp.rank), "r"(cp.epoch) : "memory");
-    }
-    const size_t nv_blk = static_cast<size_t>(BLOCK_M) * p.K / 8;  // uint4 vectors per row block
-    const size_t v_lo = nv_blk * blockIdx.x / n_comm, v_hi = nv_blk * (blockIdx.x + 1) / n_comm;
-    for (int s = 1; s < cp.world; ++s) {
-      const int src = (cp.rank + s) % cp.world;
-      if (threadIdx.x == 0) {
-        while (static_cast<int32_t>(ld_acquire_sys_u32(cp.peer_flags[cp.rank] + src) - cp.epoch) < 0) {
+    // ======================= COMM_AG copy CTA: push the local row blocks to the peers over NVLink ==============
+    // Push, not pull: P2P stores are posted (no NVLink round trip per request) and the data is ready by stream
+    // order, so no "shard ready" handshake is needed.  The copy itself is done by the TMA engine: one thread streams
+    // 32 KB chunks  local global -> smem ring (cp.async.bulk + mbarrier)  ->  peer global (cp.async.bulk store),
+    // keeping the whole ring (6 x 32 KB = the GEMM pipeline's smem, idle in this CTA) in flight, instead of
+    // 16-byte register round trips.  Row blocks (128 rows x K, contiguous in both buffers) are taken round-robin,
+    // destination by destination in the order the peers consume them (the peer right "below" needs our rows
+    // first); after a row block has fully landed the peer's arrival counter is bumped with a system-scope release.
+    // WAR safety: the gathered buffers are double-buffered by call parity; a peer only finishes call n-1 after our
+    // pushes of call n-1, which we issue after our call n-2 kernel ended, so nobody still reads parity (n-2).
+    if (threadIdx.x == 0) {
+      constexpr uint32_t CHUNK = 32768;
+      constexpr int NSLOT = (NS * Cfg::STAGE_BYTES) / CHUNK < 2 * NS ? (NS * Cfg::STAGE_BYTES) / CHUNK : 2 * NS;
+      static_assert(NSLOT >= 3, "ring too small");
+      uint64_t* bars = full_bar;  // full_bar[NS] and empty_bar[NS] are contiguous, all initialised with count 1
+      const size_t blk_bytes = static_cast<size_t>(BLOCK_M) * p.K * 2;
+      const int n_chunks = static_cast<int>((blk_bytes + CHUNK - 1) / CHUNK);
+      const int n_remote = (cp.world - 1) * mbpr;
+      auto dst_of = [&](int q) { return (cp.rank - 1 - q / mbpr + 2 * cp.world) % cp.world; };
+      auto blk_of = [&](int q) { return cp.rank * mbpr + q % mbpr; };
+      auto chunk_bytes = [&](int c) {
+        const size_t off = static_cast<size_t>(c) * CHUNK;
+        return static_cast<uint32_t>(blk_bytes - off < CHUNK ? blk_bytes - off : CHUNK);
+      };
+      auto signal = [&](uint32_t* flag) {
+        asm volatile("fence.proxy.async.global;\n" ::: "memory");
+        __threadfence_system();
+        asm volatile("red.release.sys.global.add.u32 [%0], 1;\n" ::"l"(flag) : "memory");
+      };
+      // One flat stream of chunks over all row blocks of this CTA: the load cursor runs up to NSLOT-1 chunks ahead
+      // of the store cursor, and a finished row block is signalled two stores later (so the completion wait never
+      // drains the pipe).
+      int q_ld = blockIdx.x, c_ld = 0, q_st = blockIdx.x, c_st = 0;
+      uint32_t issued = 0, stored = 0, pend_at = 0;
+      uint32_t* pend_flag = nullptr;
+      while (q_st < n_remote) {
+        while (q_ld < n_remote && issued - stored < static_cast<uint32_t>(NSLOT - 1)) {
+          const uint32_t slot = issued % NSLOT;
+          // the slot was last read by store #(issued - NSLOT); at least one newer store exists (fill bound above)
+          if (issued >= static_cast<uint32_t>(NSLOT)) tma_store_wait_read<1>();
+          const uint8_t* sp = reinterpret_cast<const uint8_t*>(cp.peer_buf[cp.rank]) +
+                              static_cast<size_t>(blk_of(q_ld)) * blk_bytes + static_cast<size_t>(c_ld) * CHUNK;
+          const uint32_t bytes = chunk_bytes(c_ld);
+          mbar_arrive_expect_tx(&bars[slot], bytes);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                           smem_u32(smem + slot * CHUNK)),
+                       "l"(sp), "r"(bytes), "r"(smem_u32(&bars[slot]))
+                       : "memory");
+          ++issued;
+          if (++c_ld == n_chunks) {
+            c_ld = 0;
+            q_ld += n_comm;
+          }
+        }
+        const uint32_t slot = stored % NSLOT;
+        mbar_wait(&bars[slot], (stored / NSLOT) & 1);
+        uint8_t* dp = reinterpret_cast<uint8_t*>(cp.peer_buf[dst_of(q_st)]) + static_cast<size_t>(blk_of(q_st)) * blk_bytes +
+                      static_cast<size_t>(c_st) * CHUNK;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dp),
+                     "r"(smem_u32(smem + slot * CHUNK)), "r"(chunk_bytes(c_st))
+                     : "memory");
+        tma_store_commit();
+        ++stored;
+        if (++c_st == n_chunks) {
+          if (pend_flag != nullptr) {  // (tiny row blocks) the previous one is still unsignalled: complete everything
+            tma_store_wait<0>();
+            signal(pend_flag);
+          }
+          pend_flag = cp.peer_flags[dst_of(q_st)] + blk_of(q_st);
+          pend_at = stored + 2;
+          c_st = 0;
+          q_st += n_comm;
+        }
+        if (pend_flag != nullptr && stored >= pend_at) {
+          tma_store_wait<2>();  // all but the two newest stores are complete -> the pending row block has landed
+          signal(pend_flag);
+          pend_flag = nullptr;
         }
       }
-      __syncthreads();
-      for (int lm = 0; lm < mbpr; ++lm) {
-        const int m_blk = src * mbpr + lm;
-        const size_t base = static_cast<size_t>(m_blk) * nv_blk;
-        const uint4* sp = reinterpret_cast<const uint4*>(cp.peer_buf[src]) + base;
-        uint4* dp = reinterpret_cast<uint4*>(cp.peer_buf[cp.rank]) + base;
-        size_t i = v_lo + threadIdx.x;
-        for (; i + 15 * NUM_THREADS < v_hi; i += 16 * NUM_THREADS) {
-          uint4 t[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) t[j] = ld_stream_u4(sp + i + j * NUM_THREADS);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) dp[i + j * NUM_THREADS] = t[j];
-        }
-        for (; i < v_hi; i += NUM_THREADS) dp[i] = ld_stream_u4(sp + i);
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(cp.chunk_flags + m_blk) : "memory");
+      if (pend_flag != nullptr) {
+        tma_store_wait<0>();
+        signal(pend_flag);
       }
     }
   } else if (warp_idx == 0) {
@@ -196,8 +247,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int mn = tile / p.k_splits;
         const int m_blk = map_m(mn / n_blocks), n_blk = mn % n_blocks;
         if (cp.mode == COMM_AG && m_blk / mbpr != cp.rank) {
-          // rows owned by a peer: wait until the copy CTAs have landed this row block locally
-          while (static_cast<int32_t>(ld_acquire_gpu_u32(cp.chunk_flags + m_blk) - cp.target) < 0) {
+          // rows owned by a peer: wait until that peer's copy CTAs have pushed this row block into our buffer
+          while (static_cast<int32_t>(ld_acquire_sys_u32(cp.peer_flags[cp.rank] + m_blk) - cp.target) < 0) {
           }
           asm volatile("fence.proxy.async.global;\n" ::: "memory");
         }
@@ -326,11 +377,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
             __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
             if (cp.mode == COMM_RS) {
-              // slot [src = rank] of the owner's staging buffer, row index local to the owner
+              // Partial tile -> slot [src = rank] of the owner's staging buffer (P2P stores over NVLink when the
+              // owner is a peer).  In the TMEM layout a lane owns one ROW, so a plain 16-byte store per lane would
+              // put 32 unrelated 16-byte packets on the link.  The 32x32 chunk is transposed across the warp first
+              // (4 lanes per row): every store instruction then writes 8 rows x 64 contiguous bytes, i.e. 4x fewer,
+              // full-sector NVLink write packets.  (M % (128 * world) == 0 in this mode: all rows are valid and the
+              // warp is converged here.)
               const int owner = m_blk / mbpr;
-              const size_t lrow = static_cast<size_t>(cp.rank) * cp.rows_per_rank + (row - owner * cp.rows_per_rank);
-              orow = cp.peer_buf[owner] + cp.staging_parity_off + lrow * p.N + col0;
-            }
+              uint32_t w[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) w[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+              const int sub = lane & 3, rsel = lane >> 2;
+              __nv_bfloat16* sbase = cp.peer_buf[owner] + cp.staging_parity_off;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int src = 8 * j + rsel;
+                uint4 o = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t x0 = __shfl_sync(0xffffffffu, w[4 * k], src), x1 = __shfl_sync(0xffffffffu, w[4 * k + 1], src),
+                                 x2 = __shfl_sync(0xffffffffu, w[4 * k + 2], src), x3 = __shfl_sync(0xffffffffu, w[4 * k + 3], src);
+                  if (sub == k) o = make_uint4(x0, x1, x2, x3);
+                }
+                const int row_j = row - lane + src;
+                const size_t lrow = static_cast<size_t>(cp.rank) * cp.rows_per_rank + (row_j - owner * cp.rows_per_rank);
+                *reinterpret_cast<uint4*>(sbase + lrow * p.N + col0 + sub * 8) = o;
+              }
+            } else {
             if (p.pre_out != nullptr) {
               __nv_bfloat16* prow = p.pre_out + static_cast<size_t>(row) * p.ldo + col0;
 #pragma unroll
@@ -376,6 +449,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 *reinterpret_cast<uint4*>(orow + i) = q;
               }
             }
+            }  // !COMM_RS
           } else if constexpr (EPI == EPI_F32) {
             float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
 #pragma unroll

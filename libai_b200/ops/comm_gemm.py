@@ -4,7 +4,7 @@
     row parallel    (sequence-parallel output):  y_shard  = reduce_scatter(x · Wᵀ)        → GEMM→RS
 
 One kernel does both the math and the transfer (``csrc/gemm_sm100.cu`` COMM_AG / COMM_RS): copy
-CTAs pull peer row blocks while tcgen05 tiles of the local rows are already running; the RS epilogue
+CTAs push the local row blocks to the peers while tcgen05 tiles of the local rows are already running; the RS epilogue
 stores partial tiles straight into the owner's staging slot over NVLink and the owners reduce as
 arrivals are counted.  The backward passes are the duals (AG→GEMM ↔ GEMM→RS) plus a wgrad that
 re-gathers the sharded operand with a P2P push kernel.  The NCCL versions in
@@ -34,16 +34,14 @@ class _TPState:
         self.ag: Dict[Tuple[int, int], dict] = {}
         self.rs: Dict[Tuple[int, int], dict] = {}
 
-    # gathered operand buffers [2 parities][M, K] + local arrival counters
+    # gathered operand buffers [2 parities][M, K] + per-row-block arrival counters in the symmetric flag buffer
+    # (the pushing peer bumps them)
     def ag_state(self, M: int, K: int) -> dict:
         key = (M, K)
         if key not in self.ag:
             buf = self.ws.buffer(("ag", M, K), 2 * M * K * 2)
-            self.ag[key] = dict(
-                buf=buf, calls=0,
-                chunk_flags=[torch.zeros(M // _BM, dtype=torch.int32, device=self.ws.device) for _ in range(2)],
-                targets=[0, 0],
-            )
+            offs = [self.ws.alloc_flags(M // _BM), self.ws.alloc_flags(M // _BM)]
+            self.ag[key] = dict(buf=buf, calls=0, flag_offs=offs, targets=[0, 0])
         return self.ag[key]
 
     # staging [2 parities][world][M/world, N] + arrival counters living in the symmetric flag buffer
@@ -86,10 +84,10 @@ def ag_gemm(x_shard: torch.Tensor, w: torch.Tensor, bias, act, group, layout: in
     gathered = s["buf"].view(torch.bfloat16, (2, M, K))[par]
     gathered[st.rank * rows : (st.rank + 1) * rows].copy_(x_shard)
     epoch = st.ws.next_epoch()
-    s["targets"][par] += _N_COMM_CTAS
+    s["targets"][par] += 1          # one arrival per remote row block and call (a whole block is copied by one CTA)
     y = ext.gemm_comm(
         gathered, w, layout, bias, _ACT_IDS[act], 1, st.world, st.rank, epoch, s["targets"][par],
-        s["buf"].peer_ptrs(par * M * K * 2), st.ws.flags.peer_ptrs(0), s["chunk_flags"][par], None, 0, _N_COMM_CTAS,
+        s["buf"].peer_ptrs(par * M * K * 2), st.ws.flags.peer_ptrs(s["flag_offs"][par]), None, None, 0, _N_COMM_CTAS,
     )
     count_launch()
     return y, gathered
