@@ -31,7 +31,8 @@ train = dict(
     # gradient bucket size for data-parallel reduction (names kept from the reference)
     nccl_fusion_threshold_mb=16,
     nccl_fusion_max_ops=24,
-    # ZeRO: stage 1 = optimizer state, 2 = + gradients, 3 = + parameters partitioned over DP
+    # ZeRO: fp32 master weights + Adam moments partitioned over DP (fused NVLink reduce-scatter/Adam/all-gather);
+    # stages 2 and 3 are accepted (same numerics) but gradients / bf16 parameters stay replicated for now
     zero_optimization=dict(enabled=False, stage=1),
     checkpointer=dict(period=5000, max_to_keep=100, save_model_after_n_epoch=None),
     test_micro_batch_size=32,
