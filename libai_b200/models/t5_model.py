@@ -17,7 +17,7 @@ from torch import nn
 
 from libai_b200.config import configurable
 from libai_b200.layers import Embedding, LayerNorm, LMLogits, ParallelCrossEntropyLoss, TransformerLayer, VocabEmbedding
-from libai_b200.layers._param import xavier_normal_
+from libai_b200.layers._param import create_parameter, xavier_normal_
 from libai_b200.layers.attention import AttnMaskType
 from libai_b200.utils import distributed as dutil
 
@@ -87,6 +87,49 @@ class T5Model(nn.Module, PipelineStageMixin):
         self.encoder_states = None
         self.past_length = 0
         self.lm_head = LMLogits(vocab_size, bias=True)
+        # tied embedding under pipeline parallelism: see GPTModel (the last stage keeps a synchronised copy)
+        topo = dutil.get_dist_util()
+        self.tied_weight_copy = None
+        if topo.pipeline_parallel_size > 1:
+            self.tied_weight_copy = create_parameter(
+                (vocab_size, hidden_size), init_method, tp_dim=0, layer_idx=-1,
+                shared_with=self.embedding.word_embeddings.weight,
+            )
+            self.tied_weight_copy.shared_from = "embedding.word_embeddings.weight"
+            self.embedding.word_embeddings.weight.is_tied_source = True
+
+    def word_embeddings_weight(self):
+        topo = dutil.get_dist_util()
+        if topo.pipeline_parallel_size > 1 and topo.is_last_stage and not topo.is_first_stage:
+            return self.tied_weight_copy
+        return self.embedding.word_embeddings.weight
+
+    # ---- pipeline protocol -------------------------------------------------------------------------
+    # The running "hidden state" of an encoder-decoder model is the pair (encoder stream, decoder stream).  Both
+    # embeddings live on the first stage, so the decoder-input embedding rides along through the encoder stages;
+    # from the first decoder layer on, the first slot holds the (final-normed) encoder output that every decoder
+    # layer cross-attends to.  Layer indices 0..L-1 are encoder blocks, L..2L-1 decoder blocks
+    # (train.dist.pipeline_num_layers = 2 * hidden_layers).
+    def stage_pre(self, encoder_input_ids, decoder_input_ids, **_):
+        return self.embedding(encoder_input_ids), self.embedding(decoder_input_ids, 0)
+
+    def stage_layers(self):
+        return list(self.encoder.layers) + list(self.decoder.layers)
+
+    def stage_layer_call(self, layer, hidden, batch):
+        enc, dec = hidden
+        if layer.layer_idx < self.hidden_layers:
+            enc = layer(enc, self.extended_attn_mask(batch["encoder_attn_mask"]))
+            if layer.layer_idx == self.hidden_layers - 1:
+                enc = self.encoder.final_layernorm(enc)
+        else:
+            dec = layer(dec, self.extended_attn_mask(batch["decoder_attn_mask"]), enc,
+                        self.extended_attn_mask(batch["encoder_decoder_attn_mask"]))
+        return enc, dec
+
+    def stage_post(self, hidden, **_):
+        _, dec = hidden
+        return self.lm_head(self.decoder.final_layernorm(dec), self.word_embeddings_weight())
 
     @classmethod
     def from_config(cls, cfg):
@@ -122,7 +165,7 @@ class T5Model(nn.Module, PipelineStageMixin):
         if use_cache:
             self.set_cache(encoder_states, past_key_values=presents)
         decoder_states = self.decoder.final_layernorm(h)
-        return self.lm_head(decoder_states, self.embedding.word_embeddings.weight)
+        return self.lm_head(decoder_states, self.word_embeddings_weight())
 
     def set_cache(self, encoder_states, past_key_values):
         self.encoder_states = encoder_states
@@ -153,7 +196,7 @@ class T5Loss(nn.Module):
         return {"masked_lm_loss": torch.sum(per_token.view(-1) * mask.view(-1)) / denom}
 
 
-class T5ForPreTraining(nn.Module):
+class T5ForPreTraining(nn.Module, PipelineStageMixin):
     """T5 with the span-corruption LM loss."""
 
     def __init__(self, cfg) -> None:
@@ -172,10 +215,28 @@ class T5ForPreTraining(nn.Module):
             return self.loss_func(logits, lm_labels, loss_mask)
         return {"prediction_scores": logits}
 
+    # pipeline protocol: delegate to the backbone, add the loss on the last stage
+    def stage_pre(self, **batch):
+        return self.t5_model.stage_pre(**batch)
+
+    def stage_layers(self):
+        return self.t5_model.stage_layers()
+
+    def stage_layer_call(self, layer, hidden, batch):
+        return self.t5_model.stage_layer_call(layer, hidden, batch)
+
+    def stage_post(self, hidden, lm_labels=None, loss_mask=None, **_):
+        logits = self.t5_model.stage_post(hidden)
+        if lm_labels is not None:
+            return self.loss_func(logits, lm_labels, loss_mask)
+        return {"prediction_scores": logits}
+
     @staticmethod
     def set_pipeline_stage_id(model):
+        """API parity: placement is decided at construction through each layer's ``layer_idx``."""
         return model
 
     @staticmethod
     def set_activation_checkpoint(model):
+        model.activation_checkpoint = True
         return model
