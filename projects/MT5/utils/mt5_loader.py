@@ -75,6 +75,11 @@ class T5LoaderHuggerFace(ModelLoaderHuggerFace):
             "pad_token_id": "pad_token_id", "decoder_start_token_id": "decoder_start_token_id",
             "tie_word_embeddings": "tie_word_embeddings",
         })
+        # transformers >= 5 decouples the pre-head rescaling from weight tying (``scale_decoder_outputs``); older
+        # config.json files only have ``tie_word_embeddings`` which implied it.  Our flag controls the rescaling
+        # (whether the head is a separate matrix is decided by the checkpoint contents).
+        if "scale_decoder_outputs" in cfg:
+            self._update_cfg("tie_word_embeddings", bool(cfg["scale_decoder_outputs"]))
         gated = "gated" in str(cfg.get("feed_forward_proj", "relu"))
         self._update_cfg("model_type", "mt5" if gated else "t5")
         if "dropout_rate" in cfg:
