@@ -998,36 +998,76 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-// delta[b, a, s] = sum_d dO[b, a, s, d] * O[b, a, s, d]   (one warp per row)
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o,
-                                  float* __restrict__ delta, int B, int A, int S, int D, long sb, long sa, long ss) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+// delta[b, a, s] = sum_d dO[b, a, s, d] * O[b, a, s, d]
+// D / 8 lanes per row, 16-byte loads; rows are visited in (b, s, a) order = memory order of the [b, s, a, d] tensors, so
+// a warp reads 32 x 16 contiguous bytes per tensor, and every thread keeps 4 rows (8 loads) in flight.
+template <int D>
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o, float* __restrict__ delta,
+                  int B, int A, int S, long sb, long sa, long ss) {
+  constexpr int LPR = D / 8;  // lanes per row
   const long total = static_cast<long>(B) * A * S;
-  if (warp >= total) return;
-  const int s = warp % S, a = (warp / S) % A, b = warp / (static_cast<long>(S) * A);
-  const long off = b * sb + a * sa + s * ss;
-  float acc = 0.f;
-  for (int d = lane * 2; d < D; d += 64) {
-    const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(dout + off + d));
-    const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(o + off + d));
-    acc += x.x * y.x + x.y * y.y;
+  const long gid = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const long gstride = static_cast<long>(gridDim.x) * blockDim.x / LPR;
+  const int sub = static_cast<int>(gid % LPR);
+  const long warp_r0 = (gid - (threadIdx.x % 32)) / LPR;  // loop bound is warp-uniform (the shuffles below need all lanes)
+  for (long base = 0; warp_r0 + base < total; base += 4 * gstride) {
+    const long r0 = gid / LPR + base;
+    uint4 x[4], y[4];
+    long drow[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long r = r0 + u * gstride;
+      const bool ok = r < total;
+      const long rr = ok ? r : 0;
+      const int a = static_cast<int>(rr % A), sq = static_cast<int>((rr / A) % S);
+      const long b = rr / (static_cast<long>(A) * S);
+      const long off = b * sb + a * sa + sq * ss + sub * 8;
+      drow[u] = ok ? (b * A + a) * static_cast<long>(S) + sq : -1;
+      x[u] = ok ? *reinterpret_cast<const uint4*>(dout + off) : make_uint4(0, 0, 0, 0);
+      y[u] = ok ? *reinterpret_cast<const uint4*>(o + off) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 a0 = unpack_bf16(x[u].x), a1 = unpack_bf16(x[u].y), a2 = unpack_bf16(x[u].z), a3 = unpack_bf16(x[u].w);
+      const float2 b0 = unpack_bf16(y[u].x), b1 = unpack_bf16(y[u].y), b2 = unpack_bf16(y[u].z), b3 = unpack_bf16(y[u].w);
+      float acc = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+#pragma unroll
+      for (int m = LPR / 2; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+      if (sub == 0 && drow[u] >= 0) delta[drow[u]] = acc;
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) delta[warp] = acc;
 }
 
-// dq (strided bf16) = dq_accum (fp32 [B, A, S, D])
-__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int A,
-                                       int S, int D, long sb, long sa, long ss) {
-  const long nvec = static_cast<long>(B) * A * S * D / 4;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long e = i * 4;
-    const int d = e % D;
-    const long row = e / D;
-    const int s = row % S, a = (row / S) % A;
-    const long b = row / (static_cast<long>(S) * A);
-    const float4 v = reinterpret_cast<const float4*>(acc)[i];
-    *reinterpret_cast<uint2*>(dq + b * sb + a * sa + s * ss + d) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+// dq (strided bf16) = dq_accum (fp32 [B, A, S, D]); 8 elements per thread (two 16-byte loads, one 16-byte store)
+__global__ void __launch_bounds__(256)
+attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int A, int S, int D, long sb,
+                       long sa, long ss) {
+  const long nvec = static_cast<long>(B) * A * S * D / 8;
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+  for (long i0 = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i0 < nvec; i0 += 2 * stride) {
+    float4 lo[2], hi[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long i = i0 + u * stride;
+      if (i < nvec) {
+        lo[u] = reinterpret_cast<const float4*>(acc)[2 * i];
+        hi[u] = reinterpret_cast<const float4*>(acc)[2 * i + 1];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long i = i0 + u * stride;
+      if (i < nvec) {
+        const long e = i * 8;
+        const int d = static_cast<int>(e % D);
+        const long row = e / D;
+        const int sq = static_cast<int>(row % S), a = static_cast<int>((row / S) % A);
+        const long b = row / (static_cast<long>(S) * A);
+        *reinterpret_cast<uint4*>(dq + b * sb + a * sa + sq * ss + d) =
+            make_uint4(pack_bf16(lo[u].x, lo[u].y), pack_bf16(lo[u].z, lo[u].w), pack_bf16(hi[u].x, hi[u].y), pack_bf16(hi[u].z, hi[u].w));
+      }
+    }
   }
 }
 
@@ -1074,8 +1114,19 @@ extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const
       return -2;
   }
   const long rows = (long)B * A * S;
-  lb::attn_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(
-      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta, B, A, S, D, do_strides[0], do_strides[1], do_strides[2]);
+  {
+    // 4 rows per thread-group and iteration; cap the grid at a few waves
+    const long groups = (rows + 3) / 4;
+    const long lpr = D / 8;
+    long blocks = (groups * lpr + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    if (D == 64)
+      lb::attn_delta_kernel<64><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta, B,
+                                                                   A, S, do_strides[0], do_strides[1], do_strides[2]);
+    else
+      lb::attn_delta_kernel<128><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta, B,
+                                                                    A, S, do_strides[0], do_strides[1], do_strides[2]);
+  }
   lb::AttnBwdParams p;
   p.lse = lse;
   p.delta = delta;
@@ -1095,8 +1146,8 @@ extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const
   p.kv_lens = kv_lens;
   cudaError_t e = (D == 64) ? launch_bwd<64>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd<128>(tq, tk, tv, tdo, tdq, p, s);
   if (e != cudaSuccess) return (int)e;
-  const long nvec = rows * D / 4;
-  int blocks = (int)((nvec + 255) / 256);
+  const long nvec = rows * D / 8;
+  int blocks = (int)((nvec + 511) / 512);
   if (blocks > 148 * 8) blocks = 148 * 8;
   lb::attn_dq_convert_kernel<<<blocks, 256, 0, s>>>(dq_accum, (__nv_bfloat16*)dq, B, A, S, D, p.g_strides[0],
                                                     p.g_strides[1], p.g_strides[2]);

@@ -400,6 +400,9 @@ __global__ void sqnorm_kernel(const float* __restrict__ x, float* __restrict__ o
     const float4 q = reinterpret_cast<const float4*>(x)[i];
     acc += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // the n % 4 tail
+    for (size_t i = nvec * 4; i < n; ++i) acc += x[i] * x[i];
+  }
   acc = warp_sum(acc);
   if (threadIdx.x % 32 == 0) sm[threadIdx.x / 32] = acc;
   __syncthreads();
@@ -527,8 +530,7 @@ extern "C" int lb_adamw(float* master, const float* grad, float* m, float* v, vo
   return (int)cudaGetLastError();
 }
 extern "C" int lb_sqnorm(const float* x, float* out, long n, cudaStream_t s) {
-  if (n % 4) return -1;
-  if (n == 0) return 0;
+  if (n == 0) return 0;  // (the kernel handles the n % 4 tail)
   lb::sqnorm_kernel<<<ew_grid(n / 4, 256), 256, 0, s>>>(x, out, (size_t)n);
   return (int)cudaGetLastError();
 }

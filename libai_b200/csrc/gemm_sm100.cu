@@ -91,9 +91,53 @@ struct StageCfg {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NUM_STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : (BLOCK_N == 128 ? 6 : 8));
-  static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 8 * 2048;  // one 32x32 bf16 chunk (32 rows x 64 B) per epilogue warp
+  static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STAGING_BYTES;
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 };
+
+// ---- epilogue staging: row-per-lane (TMEM layout) <-> 4-lanes-per-row (coalesced global layout) ----------------
+// A 32x32 bf16 chunk is 32 rows x 64 B.  `tcgen05.ld.32x32b` gives every lane one ROW, so a direct 16-byte global
+// access per lane touches 32 different 128-byte lines per instruction (the L1/LSU wavefront count, not the tensor
+// pipe, bounded the K=1024 GEMMs: ncu l1tex 63 %, tensor pipe 39 %).  Staging the chunk through 2 KB of shared
+// memory per warp turns that into 8 rows x 64 contiguous bytes per instruction.  16-byte slots are XOR-swizzled with
+// (row >> 1) & 3 so both the row-wise and the transposed access are bank-conflict free.
+LB_DEVICE uint32_t stg_off(int row, int slot) { return static_cast<uint32_t>(row * 64 + ((slot ^ ((row >> 1) & 3)) << 4)); }
+// lane holds its row as 4 x uint4 -> after the call lane holds slot (lane & 3) of rows 8j + (lane >> 2), j = 0..3
+LB_DEVICE void stg_rows_to_quads(uint8_t* stg, int lane, const uint4 (&rowv)[4], uint4 (&quad)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + stg_off(lane, i)) = rowv[i];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) quad[j] = *reinterpret_cast<const uint4*>(stg + stg_off(8 * j + (lane >> 2), lane & 3));
+  __syncwarp();
+}
+LB_DEVICE void stg_quads_to_rows(uint8_t* stg, int lane, const uint4 (&quad)[4], uint4 (&rowv)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg + stg_off(8 * j + (lane >> 2), lane & 3)) = quad[j];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rowv[i] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, i));
+  __syncwarp();
+}
+// store a staged chunk: slab = pointer to (first row of this warp's 32-row slab, first column of the chunk)
+LB_DEVICE void stg_store_chunk(uint8_t* stg, int lane, const float (&v)[32], __nv_bfloat16* slab, size_t ld,
+                               int rows_valid, int cols_valid) {
+  uint4 rowv[4], quad[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    rowv[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                         pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+  stg_rows_to_quads(stg, lane, rowv, quad);
+  const int sub = lane & 3;
+  if (sub * 8 < cols_valid) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rr = 8 * j + (lane >> 2);
+      if (rr < rows_valid) *reinterpret_cast<uint4*>(slab + static_cast<size_t>(rr) * ld + sub * 8) = quad[j];
+    }
+  }
+}
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -108,6 +152,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + NS;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* staging = smem + NS * Cfg::STAGE_BYTES + 256;  // 8 x 2 KB, one slot per epilogue warp
 
   const int warp_idx = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -346,111 +391,89 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
-        // global operands of this chunk (bias slice: same address for the whole warp = broadcast; pre-activation
-        // row segment for the fused activation backward) are fetched while the TMEM load is in flight
-        uint4 bq[4], pq[4];
-        const bool use_bias = (EPI == EPI_BF16) && p.bias != nullptr && cp.mode != COMM_RS;  // RS: bias added once, in the reduce phase
-        const bool use_pre = (EPI == EPI_BF16) && p.pre_in != nullptr && row_ok;
         if constexpr (EPI == EPI_BF16) {
+          // ---- bf16 output: all global traffic of the chunk goes through the per-warp staging slot, so every
+          // load/store instruction covers 8 rows x 64 contiguous bytes (see stg_* above).  All 32 lanes take part
+          // (rows >= M hold garbage that is never stored).
+          uint8_t* stg = staging + (warp_idx - 2) * 2048;
+          const int slab_row0 = m_blk * BLOCK_M + quad * 32;
+          const int rows_valid = p.M - slab_row0;  // <= 0: nothing of this slab exists
+          const int cols_valid = p.N - col0;       // > 0, multiple of 8 (enforced on the host)
+          const int sub = lane & 3, rsel = lane >> 2;
+          const bool use_bias = p.bias != nullptr && cp.mode != COMM_RS;  // RS: bias added once, in the reduce phase
+          const bool use_pre = p.pre_in != nullptr;
+          // operands fetched while the TMEM load is in flight: bias slice (same address for the whole warp =
+          // broadcast) and the pre-activation tile for the fused activation backward (coalesced, 4 lanes per row)
+          uint4 bq[4], pquad[4], pq[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const bool in = col0 + i * 8 < p.N;  // N % 8 == 0
-            bq[i] = (use_bias && in) ? *reinterpret_cast<const uint4*>(p.bias + col0 + i * 8) : make_uint4(0, 0, 0, 0);
-            pq[i] = (use_pre && in)
-                        ? *reinterpret_cast<const uint4*>(p.pre_in + static_cast<size_t>(row) * p.ldo + col0 + i * 8)
-                        : make_uint4(0, 0, 0, 0);
+          for (int i = 0; i < 4; ++i)
+            bq[i] = (use_bias && i * 8 < cols_valid) ? *reinterpret_cast<const uint4*>(p.bias + col0 + i * 8) : make_uint4(0, 0, 0, 0);
+          if (use_pre) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int rr = 8 * j + rsel;
+              pquad[j] = (rr < rows_valid && sub * 8 < cols_valid)
+                             ? *reinterpret_cast<const uint4*>(p.pre_in + static_cast<size_t>(slab_row0 + rr) * p.ldo + col0 + sub * 8)
+                             : make_uint4(0, 0, 0, 0);
+            }
           }
-        }
-        tmem_ld_wait();
-        if (row_ok) {
+          tmem_ld_wait();
+          if (use_pre) stg_quads_to_rows(stg, lane, pquad, pq);
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if constexpr (EPI == EPI_BF16) {
-            if (use_bias) {
+          if (use_bias) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 a = unpack_bf16(bq[i].x), b = unpack_bf16(bq[i].y), c2 = unpack_bf16(bq[i].z), d = unpack_bf16(bq[i].w);
-                v[i * 8] += a.x; v[i * 8 + 1] += a.y; v[i * 8 + 2] += b.x; v[i * 8 + 3] += b.y;
-                v[i * 8 + 4] += c2.x; v[i * 8 + 5] += c2.y; v[i * 8 + 6] += d.x; v[i * 8 + 7] += d.y;
-              }
+            for (int i = 0; i < 4; ++i) {
+              const float2 a = unpack_bf16(bq[i].x), b = unpack_bf16(bq[i].y), c2 = unpack_bf16(bq[i].z), d = unpack_bf16(bq[i].w);
+              v[i * 8] += a.x; v[i * 8 + 1] += a.y; v[i * 8 + 2] += b.x; v[i * 8 + 3] += b.y;
+              v[i * 8 + 4] += c2.x; v[i * 8 + 5] += c2.y; v[i * 8 + 6] += d.x; v[i * 8 + 7] += d.y;
             }
-            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-            if (cp.mode == COMM_RS) {
-              // Partial tile -> slot [src = rank] of the owner's staging buffer (P2P stores over NVLink when the
-              // owner is a peer).  In the TMEM layout a lane owns one ROW, so a plain 16-byte store per lane would
-              // put 32 unrelated 16-byte packets on the link.  The 32x32 chunk is transposed across the warp first
-              // (4 lanes per row): every store instruction then writes 8 rows x 64 contiguous bytes, i.e. 4x fewer,
-              // full-sector NVLink write packets.  (M % (128 * world) == 0 in this mode: all rows are valid and the
-              // warp is converged here.)
-              const int owner = m_blk / mbpr;
-              uint32_t w[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) w[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-              const int sub = lane & 3, rsel = lane >> 2;
-              __nv_bfloat16* sbase = cp.peer_buf[owner] + cp.staging_parity_off;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int src = 8 * j + rsel;
-                uint4 o = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t x0 = __shfl_sync(0xffffffffu, w[4 * k], src), x1 = __shfl_sync(0xffffffffu, w[4 * k + 1], src),
-                                 x2 = __shfl_sync(0xffffffffu, w[4 * k + 2], src), x3 = __shfl_sync(0xffffffffu, w[4 * k + 3], src);
-                  if (sub == k) o = make_uint4(x0, x1, x2, x3);
-                }
-                const int row_j = row - lane + src;
-                const size_t lrow = static_cast<size_t>(cp.rank) * cp.rows_per_rank + (row_j - owner * cp.rows_per_rank);
-                *reinterpret_cast<uint4*>(sbase + lrow * p.N + col0 + sub * 8) = o;
-              }
-            } else {
-            if (p.pre_out != nullptr) {
-              __nv_bfloat16* prow = p.pre_out + static_cast<size_t>(row) * p.ldo + col0;
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                if (col0 + i < p.N) {
-                  uint4 q = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
-                                       pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
-                  *reinterpret_cast<uint4*>(prow + i) = q;
-                }
-              }
-            }
-            if (p.pre_in != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                if (col0 + i < p.N) {
-                  const uint4 q = pq[i / 8];
-                  const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c2 = unpack_bf16(q.z), d = unpack_bf16(q.w);
-                  if (p.act == ACT_GELU) {  // hot case without the per-element switch
-                    v[i] *= gelu_grad_fast(a.x); v[i + 1] *= gelu_grad_fast(a.y);
-                    v[i + 2] *= gelu_grad_fast(b.x); v[i + 3] *= gelu_grad_fast(b.y);
-                    v[i + 4] *= gelu_grad_fast(c2.x); v[i + 5] *= gelu_grad_fast(c2.y);
-                    v[i + 6] *= gelu_grad_fast(d.x); v[i + 7] *= gelu_grad_fast(d.y);
-                  } else {
-                    v[i] *= act_grad(a.x, p.act); v[i + 1] *= act_grad(a.y, p.act);
-                    v[i + 2] *= act_grad(b.x, p.act); v[i + 3] *= act_grad(b.y, p.act);
-                    v[i + 4] *= act_grad(c2.x, p.act); v[i + 5] *= act_grad(c2.y, p.act);
-                    v[i + 6] *= act_grad(d.x, p.act); v[i + 7] *= act_grad(d.y, p.act);
-                  }
-                }
-              }
-            } else if (p.act == ACT_GELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
-            } else if (p.act != ACT_NONE) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = act_fwd(v[i], p.act);
-            }
+          }
+          if (p.pre_out != nullptr)
+            stg_store_chunk(stg, lane, v, p.pre_out + static_cast<size_t>(slab_row0) * p.ldo + col0, p.ldo, rows_valid, cols_valid);
+          if (use_pre) {
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
-              if (col0 + i < p.N) {  // N % 8 == 0 is enforced on the host
-                uint4 q = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
-                                     pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
-                *reinterpret_cast<uint4*>(orow + i) = q;
+              const uint4 q = pq[i / 8];
+              const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c2 = unpack_bf16(q.z), d = unpack_bf16(q.w);
+              if (p.act == ACT_GELU) {  // hot case without the per-element switch
+                v[i] *= gelu_grad_fast(a.x); v[i + 1] *= gelu_grad_fast(a.y);
+                v[i + 2] *= gelu_grad_fast(b.x); v[i + 3] *= gelu_grad_fast(b.y);
+                v[i + 4] *= gelu_grad_fast(c2.x); v[i + 5] *= gelu_grad_fast(c2.y);
+                v[i + 6] *= gelu_grad_fast(d.x); v[i + 7] *= gelu_grad_fast(d.y);
+              } else {
+                v[i] *= act_grad(a.x, p.act); v[i + 1] *= act_grad(a.y, p.act);
+                v[i + 2] *= act_grad(b.x, p.act); v[i + 3] *= act_grad(b.y, p.act);
+                v[i + 4] *= act_grad(c2.x, p.act); v[i + 5] *= act_grad(c2.y, p.act);
+                v[i + 6] *= act_grad(d.x, p.act); v[i + 7] *= act_grad(d.y, p.act);
               }
             }
-            }  // !COMM_RS
-          } else if constexpr (EPI == EPI_F32) {
+          } else if (p.act == ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          } else if (p.act != ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = act_fwd(v[i], p.act);
+          }
+          __nv_bfloat16* slab = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(slab_row0) * p.ldo + col0;
+          size_t ld = static_cast<size_t>(p.ldo);
+          if (cp.mode == COMM_RS) {
+            // partial tile -> slot [src = rank] of the owner's staging buffer (P2P stores over NVLink when the owner
+            // is a peer); row index local to the owner.  64-byte row segments = full-sector NVLink write packets.
+            const int owner = m_blk / mbpr;
+            const size_t lrow0 = static_cast<size_t>(cp.rank) * cp.rows_per_rank + (slab_row0 - owner * cp.rows_per_rank);
+            slab = cp.peer_buf[owner] + cp.staging_parity_off + lrow0 * p.N + col0;
+            ld = static_cast<size_t>(p.N);
+          }
+          stg_store_chunk(stg, lane, v, slab, ld, rows_valid, cols_valid);
+        } else {
+          tmem_ld_wait();
+          if (row_ok) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if constexpr (EPI == EPI_F32) {
             float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -473,9 +496,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                : "memory");
                 }
               }
-          }
-        }
-      }
+            }
+          }  // row_ok
+        }    // fp32 epilogues
+      }      // chunk loop
       tc_fence_before_sync();
       mbar_arrive(&tmem_empty[acc]);
       if (cp.mode == COMM_RS) {
@@ -711,11 +735,22 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   if (epi == 2) {
     splits = force_splits;
     if (splits <= 0) {
+      // Persistent CTAs take work items round-robin, so the kernel lasts ceil(items / SMs) rounds of one K partition
+      // each: pick the split count that minimises rounds x (k-blocks per partition + a fixed per-item cost for
+      // pipeline fill and the fp32 red.add epilogue).  (A plain ceil(SMs / tiles) overshoots into a second round:
+      // 32 tiles x 5 splits = 160 items on 148 SMs took 2 x 26 k-blocks where 4 splits take 1 x 32.)
       const long tiles = (long)m_blocks * n_blocks;
-      splits = (int)((sms + tiles - 1) / tiles);
-      if (tiles >= sms) splits = 1;
-      // keep at least 4 k-blocks per split so the pipeline fills
-      while (splits > 1 && k_blocks / splits < 4) --splits;
+      double best = 1e30;
+      for (int c = 1; c <= 16 && c <= k_blocks; ++c) {
+        if (c > 1 && k_blocks / c < 4) break;  // keep at least 4 k-blocks per split so the pipeline fills
+        const long rounds = (tiles * c + sms - 1) / sms;
+        const int kps = (k_blocks + c - 1) / c;
+        const double cost = (double)rounds * (kps + (c > 1 ? 6.0 : 3.0));
+        if (cost < best - 1e-9) {
+          best = cost;
+          splits = c;
+        }
+      }
     }
     if (splits > k_blocks) splits = k_blocks;
   }

@@ -214,7 +214,15 @@ class FlatOptimizer(torch.optim.Optimizer):
         def _acc(seg):
             if math.isinf(norm_type):
                 return seg.abs().max() if seg.numel() else torch.zeros((), device=seg.device)
-            return seg.pow(2).sum() if norm_type == 2.0 else seg.abs().pow(norm_type).sum()
+            if norm_type == 2.0:
+                if (seg.numel() and seg.dtype == torch.float32 and seg.is_contiguous() and seg.data_ptr() % 16 == 0
+                        and use_native(seg)):
+                    # one pass over the flat fp32 gradient buffer (K19); `pow(2).sum()` would write and re-read a
+                    # temporary as large as the buffer (1.4 GB for the 345M-parameter benchmark model)
+                    count_launch()
+                    return load_ext().sqnorm(seg).reshape(())
+                return torch.dot(seg.reshape(-1), seg.reshape(-1)) if seg.numel() else torch.zeros((), device=seg.device)
+            return seg.abs().pow(norm_type).sum()
 
         for fg in self._groups:
             if fg is None:
