@@ -238,6 +238,7 @@ def main():
         else:
             loss = None
             for k in range(acc):
+                step._arm_grad_overlap(k == acc - 1)   # same as StepTrainer.run_step: early DP reduce on the last micro-batch
                 out = model(**staged[(i * acc + k) % len(staged)])
                 l = sum(v for kk, v in out.items() if "loss" in kk) / acc
                 l.backward()
@@ -255,9 +256,12 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_enq = time.perf_counter()
     for i in range(args.steps):
         loss = one_step(args.warmup + i)
     e1.record()
+    # host time spent ENQUEUEING the timed steps (no sync inside): close to the device time = the step is launch-bound
+    enqueue_ms = max_over_ranks((time.perf_counter() - t_enq) * 1e3) / args.steps
     barrier()
     launches = ops.launch_count()
     clocks = sampler.stop() if rank == 0 else None
@@ -293,7 +297,8 @@ def main():
                     lval = sum(v for kk, v in (out or {}).items() if "loss" in kk) if out else torch.zeros((), device=dev)
                 else:
                     lval = None
-                    for b in batches:
+                    for j, b in enumerate(batches):
+                        step._arm_grad_overlap(j == len(batches) - 1)
                         out = model(**b)
                         l = sum(v for kk, v in out.items() if "loss" in kk) / acc
                         l.backward()
@@ -346,6 +351,8 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
+            "host_enqueue_ms_per_step": enqueue_ms,
+            "host_cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count(),
             "final_loss": float(loss) if loss is not None and torch.is_tensor(loss) else None,
         }
         print(json.dumps(line))

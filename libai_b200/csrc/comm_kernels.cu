@@ -24,9 +24,11 @@ struct PeerPtrs {
 // streaming 128-bit load (peer or local memory); NOT volatile so that several loads per thread stay in flight
 LB_DEVICE float4 ld_stream_f4(const float4* p) {
   float4 v;
+  // "memory": must not be hoisted above the barrier that follows the flag wait (it reads data other ranks publish)
   asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];\n"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
+               : "l"(p)
+               : "memory");
   return v;
 }
 

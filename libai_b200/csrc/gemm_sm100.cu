@@ -468,36 +468,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           stg_store_chunk(stg, lane, v, slab, ld, rows_valid, cols_valid);
         } else {
+          // ---- fp32 outputs (wgrad: plain store / read-modify-write into main_grad, or red.add for split-K): the
+          // same staging slot, 16 columns (64 B per row) at a time, so every global instruction covers 8 rows x 64
+          // contiguous bytes instead of 32 rows x 16 B.  With <= 148 tiles there is no next tile whose MMAs could hide
+          // this epilogue, so its LSU wavefront count is on the critical path.
           tmem_ld_wait();
-          if (row_ok) {
-            float v[32];
+          uint8_t* stg = staging + (warp_idx - 2) * 2048;
+          const int slab_row0 = m_blk * BLOCK_M + quad * 32;
+          const int rows_valid = p.M - slab_row0;
+          const int sub = lane & 3, rsel = lane >> 2;
+          float* slab = reinterpret_cast<float*>(p.out) + static_cast<size_t>(slab_row0) * p.ldo + col0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            if constexpr (EPI == EPI_F32) {
-            float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+          for (int h = 0; h < 2; ++h) {
+            uint4 rowv[4], quadv[4];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (col0 + i < p.N) {
-                float4 o4 = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                if (p.rmw) {
-                  const float4 old = *reinterpret_cast<const float4*>(orow + i);
-                  o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
+            for (int i = 0; i < 4; ++i) rowv[i] = make_uint4(r[16 * h + 4 * i], r[16 * h + 4 * i + 1], r[16 * h + 4 * i + 2], r[16 * h + 4 * i + 3]);
+            stg_rows_to_quads(stg, lane, rowv, quadv);
+            const int c = 16 * h + 4 * sub;  // first of this lane's 4 columns inside the chunk
+            if (col0 + c < p.N) {           // N % 8 == 0
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int rr = 8 * j + rsel;
+                if (rr < rows_valid) {
+                  float* dst = slab + static_cast<size_t>(rr) * p.ldo + c;
+                  float4 o4 = make_float4(__uint_as_float(quadv[j].x), __uint_as_float(quadv[j].y), __uint_as_float(quadv[j].z),
+                                          __uint_as_float(quadv[j].w));
+                  if constexpr (EPI == EPI_F32) {
+                    if (p.rmw) {
+                      const float4 old = *reinterpret_cast<const float4*>(dst);
+                      o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
+                    }
+                    *reinterpret_cast<float4*>(dst) = o4;
+                  } else {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst), "f"(o4.x), "f"(o4.y), "f"(o4.z), "f"(o4.w)
+                                 : "memory");
+                  }
                 }
-                *reinterpret_cast<float4*>(orow + i) = o4;
               }
             }
-          } else {
-            float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                if (col0 + i < p.N) {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(orow + i), "f"(v[i]), "f"(v[i + 1]),
-                               "f"(v[i + 2]), "f"(v[i + 3])
-                               : "memory");
-                }
-              }
-            }
-          }  // row_ok
+          }
         }    // fp32 epilogues
       }      // chunk loop
       tc_fence_before_sync();

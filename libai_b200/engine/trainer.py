@@ -13,6 +13,7 @@ every ``log_period`` iterations (the reference synchronises every step: trainer.
 from __future__ import annotations
 
 import logging
+import os
 import time
 import weakref
 from typing import Callable, List, Mapping, Optional
@@ -154,6 +155,24 @@ class StepTrainer(TrainerBase):
         self._pipeline = None
         self._ev = None
 
+    def _arm_grad_overlap(self, last_micro_batch: bool):
+        """Overlap the data-parallel gradient reduction with the backward pass of the last micro-batch (the fused
+        NVLink reduce-scatter of the already-final part of the gradient buffer starts at a few block boundaries)."""
+        if not hasattr(self, "_overlap_layers"):
+            self._overlap_layers = ()
+            model = self.model.module if hasattr(self.model, "module") else self.model
+            opt = self.optimizer
+            if (hasattr(opt, "plan_overlap") and hasattr(model, "grad_ready_layers")
+                    and dutil.get_dist_util().device_type == "cuda" and dutil.get_dist_util().data_parallel_size > 1
+                    and os.environ.get("LIBAI_B200_OVERLAP_GRAD_SYNC", "1") != "0"):
+                self._overlap_layers = tuple(opt.plan_overlap())
+            self._overlap_model = model
+        if not self._overlap_layers:
+            return
+        m = self._overlap_model
+        m.grad_ready_layers = self._overlap_layers
+        m.grad_ready_callback = self.optimizer.on_grads_ready if last_micro_batch else None
+
     def _next_batches(self, get_batch: Callable, input_placement_device: str):
         out = []
         mixup = getattr(self.data_loader, "mixup_func", None)
@@ -184,7 +203,8 @@ class StepTrainer(TrainerBase):
         else:
             loss_dict = None
             inv = 1.0 / self.grad_acc_steps
-            for batch in batches:
+            for k, batch in enumerate(batches):
+                self._arm_grad_overlap(k == len(batches) - 1)
                 out = self.model(**batch)
                 loss = sum(v for k, v in out.items() if "loss" in k) * inv
                 if self.loss_scaler is not None:

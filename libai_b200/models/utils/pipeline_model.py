@@ -23,8 +23,28 @@ from torch.utils.checkpoint import checkpoint
 from libai_b200.utils import distributed as dutil
 
 
+class _GradBoundary(torch.autograd.Function):
+    """Identity in forward.  Its backward runs once the backward of everything downstream of this point (block
+    ``layer_idx`` and all later blocks) has been *issued*, i.e. the gradients of their parameters are final for this
+    micro-batch — the optimizer uses the moment to start reducing that part of the flat gradient buffer over NVLink
+    while the remaining backward keeps the tensor cores busy (``FlatOptimizer.on_grads_ready``)."""
+
+    @staticmethod
+    def forward(ctx, hidden, layer_idx, callback):
+        ctx.layer_idx, ctx.callback = layer_idx, callback
+        return hidden.view_as(hidden)
+
+    @staticmethod
+    def backward(ctx, grad):
+        ctx.callback(ctx.layer_idx)
+        return grad, None, None
+
+
 class PipelineStageMixin:
     activation_checkpoint: bool = False
+    # set by the trainer for the last micro-batch of a step (None = no early gradient reduction)
+    grad_ready_callback = None
+    grad_ready_layers = ()
 
     # ---- to be provided by the model -------------------------------------------------------
     def stage_pre(self, **batch):
@@ -45,9 +65,12 @@ class PipelineStageMixin:
         topo = dutil.get_dist_util()
         hidden = self.stage_pre(**batch) if topo.is_first_stage else hidden_in
         use_ckpt = self.activation_checkpoint and torch.is_grad_enabled()
+        cb = self.grad_ready_callback if torch.is_grad_enabled() else None
         for layer in self.stage_layers():
             if not topo.owns_layer(getattr(layer, "layer_idx", 0)):
                 continue
+            if cb is not None and torch.is_tensor(hidden) and getattr(layer, "layer_idx", -1) in self.grad_ready_layers:
+                hidden = _GradBoundary.apply(hidden, layer.layer_idx, cb)
             if use_ckpt:
                 hidden = checkpoint(self.stage_layer_call, layer, hidden, batch, use_reentrant=False)
             else:

@@ -150,10 +150,108 @@ class FlatOptimizer(torch.optim.Optimizer):
             if fg is None:
                 continue
             fg.grad_flat.zero_()
+            fg.reduced_from = fg.hi          # nothing of the owned slice has been reduced yet
+            if getattr(fg, "sq_partial", None) is not None:
+                fg.sq_partial.zero_()
             for p in fg.params:
                 p.grad = None
                 p.grad_added_to_main_grad = False
         self._synced = False
+        self._early_launched = False
+
+    # ---- early (overlapped) data-parallel reduction ------------------------------------------------
+    _LAYER_RE = None
+
+    def plan_overlap(self, num_triggers: int = 4):
+        """Decide at which block boundaries of the backward pass the gradient reduce-scatter of the already-final tail
+        of each flat buffer is started.  Parameters are laid out in registration order (embeddings, block 0 … block
+        L-1, final norm), backward finishes them in reverse, so after the backward of block ``i`` everything from the
+        first parameter of block ``i`` to the end of the buffer is final.  Returns the trigger layer indices (empty
+        when the layout does not allow it: model-parallel fix-ups pending, no fused NVLink path, unknown names)."""
+        import re
+
+        self.setup()
+        topo = dutil.get_dist_util()
+        self._overlap_plan = {}
+        if (topo.dp_group is None or topo.pipeline_parallel_size > 1
+                or (topo.sequence_parallel and topo.tensor_parallel_size > 1)):
+            return ()
+        pat = re.compile(r"\.layers\.(\d+)\.")
+        layers_seen = set()
+        per_group = []
+        for fg in self._groups:
+            if fg is None or fg.symm is None:
+                per_group.append(None)
+                continue
+            idx = []
+            for p in fg.params:
+                m = pat.search(self._param_names.get(id(p), ""))
+                idx.append(int(m.group(1)) if m else None)
+            known = [i for i in idx if i is not None]
+            if not known:
+                per_group.append(None)
+                continue
+            first, last = idx.index(known[0]), len(idx) - 1 - idx[::-1].index(known[-1])
+            # registration order must be monotone in the block index between the first and last block parameter
+            body = [i for i in idx[first:last + 1] if i is not None]
+            if body != sorted(body):
+                per_group.append(None)
+                continue
+            start = {}
+            for k in range(first, last + 1):
+                if idx[k] is not None and idx[k] not in start:
+                    start[idx[k]] = (k, fg.offsets[k])
+            per_group.append(dict(idx=idx, start=start, first=first))
+            layers_seen.update(start)
+        if not layers_seen or all(g is None for g in per_group):
+            return ()
+        n_layers = max(layers_seen) + 1
+        step = max(1, n_layers // (num_triggers + 1))
+        triggers = tuple(sorted({l for l in range(step, n_layers, step)} & layers_seen))
+        self._overlap_plan = dict(groups=per_group, triggers=triggers)
+        return triggers
+
+    def on_grads_ready(self, layer_idx: int):
+        """Called from the backward pass (``_GradBoundary``) of the last micro-batch: gradients of block ``layer_idx``
+        and everything registered after it are final.  Every rank launches the reduce-scatter of the part of ITS slice
+        that lies in that tail on a side stream; the kernel's own flag exchange makes sure the peers got there too."""
+        plan = getattr(self, "_overlap_plan", None)
+        if not plan or layer_idx not in plan["triggers"]:
+            return
+        topo = dutil.get_dist_util()
+        ext = load_ext()
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream()
+        work = []
+        for fg, gp in zip(self._groups, plan["groups"]):
+            if fg is None or gp is None or layer_idx not in gp["start"]:
+                continue
+            k0, off = gp["start"][layer_idx]
+            # everything in the tail must already sit in main_grad (the native backward accumulates there directly;
+            # a parameter still waiting for autograd's AccumulateGrad cannot be reduced early)
+            if not all(p.grad_added_to_main_grad and p.grad is None for p in fg.params[k0:]):
+                return
+            # parameter offsets are multiples of 8 elements and slice bounds multiples of 256: float4-aligned
+            a = min(max(off, fg.lo), fg.reduced_from)
+            work.append((fg, a))
+        if not work:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self._side_stream.wait_event(ev)
+        scale = 1.0 / topo.data_parallel_size if self.dp_grad_reduce == "mean" else 1.0
+        with torch.cuda.stream(self._side_stream):
+            for fg, a in work:
+                ws = fg.symm["ws"]
+                b = fg.reduced_from
+                if getattr(fg, "sq_partial", None) is None:
+                    fg.sq_partial = torch.zeros(1, dtype=torch.float32, device=fg.device)
+                # (an empty range still takes part in the flag exchange: all ranks issue the same launch sequence)
+                ext.zero_reduce_scatter(fg.symm["grad"].peer_ptrs(0), ws.flags.peer_ptrs(0), fg.grad_flat[a:b],
+                                        fg.sq_partial, a, b - a, scale, ws.world, ws.rank, ws.next_epoch())
+                count_launch()
+                fg.reduced_from = a
+        self._early_launched = True
 
     def _collect_autograd_grads(self):
         """Fold ``p.grad`` (produced by the PyTorch reference path) into ``main_grad``."""
@@ -190,12 +288,18 @@ class FlatOptimizer(torch.optim.Optimizer):
                 ext = load_ext()
                 ws = fg.symm["ws"]
                 scale = 1.0 / topo.data_parallel_size if self.dp_grad_reduce == "mean" else 1.0
-                if not hasattr(fg, "sq_partial"):
+                if getattr(fg, "sq_partial", None) is None:
                     fg.sq_partial = torch.zeros(1, dtype=torch.float32, device=fg.device)
-                fg.sq_partial.zero_()
-                ext.zero_reduce_scatter(fg.symm["grad"].peer_ptrs(0), ws.flags.peer_ptrs(0), fg.grad_shard(),
-                                        fg.sq_partial, fg.lo, fg.hi - fg.lo, scale, ws.world, ws.rank, ws.next_epoch())
+                if getattr(self, "_early_launched", False):
+                    # the tail [reduced_from, hi) was reduced during the backward pass on the side stream
+                    torch.cuda.current_stream().wait_stream(self._side_stream)
+                b = getattr(fg, "reduced_from", fg.hi)
+                if b == fg.hi:
+                    fg.sq_partial.zero_()
+                ext.zero_reduce_scatter(fg.symm["grad"].peer_ptrs(0), ws.flags.peer_ptrs(0), fg.grad_flat[fg.lo:b],
+                                        fg.sq_partial, fg.lo, b - fg.lo, scale, ws.world, ws.rank, ws.next_epoch())
                 count_launch()
+                fg.reduced_from = fg.lo
             elif topo.dp_group is not None:
                 if self.dp_grad_reduce == "mean":
                     fg.grad_flat.div_(topo.data_parallel_size)

@@ -237,6 +237,56 @@ def main():
 
     record("ZeRO fused RS+Adam+AG vs NCCL", zero)
 
+    def overlap():
+        """Early reduce-scatter launched from the backward pass (side stream) == end-of-step reduce-scatter on a small
+        GPT trained data-parallel for three steps."""
+        from libai_b200.layers._param import param_defaults
+        from libai_b200.models.gpt_model import GPTForPreTraining
+        from libai_b200.optim import AdamW, get_default_optimizer_params
+
+        cfg = DictConfig(dict(
+            hidden_layers=6, vocab_size=512, hidden_size=256, ffn_hidden_size=1024, num_attention_heads=4,
+            max_seq_length=256, embedding_dropout_prob=0.0, attention_dropout_prob=0.0, output_dropout_prob=0.0,
+            layernorm_epsilon=1e-5, initializer_range=0.02, use_scaled_init_for_output_weights=True,
+            bias_gelu_fusion=True, bias_dropout_fusion=True, scale_mask_softmax_fusion=True,
+            apply_query_key_layer_scaling=False, apply_residual_post_layernorm=False, amp_enabled=True))
+        finals, launched = [], []
+        for use_overlap in (True, False):
+            dutil.reset_dist_util()
+            dutil.setup_dist_util(DictConfig(dict(data_parallel_size=world, tensor_parallel_size=1, pipeline_parallel_size=1)))
+            with param_defaults(dtype=torch.bfloat16, device="cuda", seed=11):
+                model = GPTForPreTraining(cfg)
+            opt = AdamW(get_default_optimizer_params(model, clip_grad_max_norm=1.0, clip_grad_norm_type=2.0), lr=1e-3,
+                        weight_decay=0.01)
+            opt.configure(zero_stage=1, param_names={id(p): n for n, p in model.named_parameters()})
+            opt.setup()
+            triggers = opt.plan_overlap() if use_overlap else ()
+            model.grad_ready_layers = tuple(triggers)
+            n_early = 0
+            for step in range(3):
+                g = torch.Generator(device="cuda").manual_seed(1000 * step + rank)
+                ids = torch.randint(0, 512, (4, 256), device="cuda", generator=g)
+                opt.zero_grad()
+                model.grad_ready_callback = opt.on_grads_ready if use_overlap else None
+                model(ids, ids)["lm_loss"].backward()
+                n_early += int(getattr(opt, "_early_launched", False))
+                if step == 0:   # the reduced gradients themselves (before Adam turns tiny differences into sign flips)
+                    opt.sync_gradients()
+                    torch.cuda.synchronize()
+                    grads0 = torch.cat([fg.grad_shard().clone() for fg in opt._groups if fg is not None])
+                opt.step()
+            torch.cuda.synchronize()
+            finals.append((grads0, torch.cat([p.detach().float().reshape(-1) for p in model.parameters()])))
+            launched.append((list(triggers), n_early))
+        # (split-K wgrad accumulates with fp32 atomics, so two runs agree to rounding, not bit for bit)
+        g_err = rel_err(finals[0][0], finals[1][0])
+        p_diff = float((finals[0][1] - finals[1][1]).abs().mean())
+        return {"ok": g_err < 1e-4 and p_diff < 1e-4 and launched[0][1] == 3 and len(launched[0][0]) > 0,
+                "reduced_grad_rel_err": g_err, "param_mean_abs_diff": p_diff, "trigger_layers": launched[0][0],
+                "steps_with_early_reduce": launched[0][1]}
+
+    record("overlapped grad reduce-scatter == end-of-step", overlap)
+
     if rank == 0:
         out = "gpurun_out/comm_check.json"
         if "--out" in sys.argv:
