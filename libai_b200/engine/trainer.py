@@ -156,15 +156,19 @@ class StepTrainer(TrainerBase):
         self._ev = None
 
     def _arm_grad_overlap(self, last_micro_batch: bool):
-        """Overlap the data-parallel gradient reduction with the backward pass of the last micro-batch (the fused
-        NVLink reduce-scatter of the already-final part of the gradient buffer starts at a few block boundaries)."""
+        """Opt-in (``LIBAI_B200_OVERLAP_GRAD_SYNC=1``): overlap the data-parallel gradient reduction with the backward
+        pass of the last micro-batch (the fused NVLink reduce-scatter of the already-final part of the gradient buffer
+        starts at a few block boundaries).  Measured on B200 it does NOT pay for the 345M benchmark model: the
+        end-of-step reduction costs ~1 ms at 8 GPUs (97 % weak scaling without overlap), while the extra side-stream
+        kernels, their flag exchanges and the added host work cost more (2 GPUs 29.4 → 30.0 ms, 8 GPUs 29.9 → 35.3 ms;
+        `profiles/r20_*`, `profiles/r21_*`).  Kept for models whose gradient volume per step is much larger."""
         if not hasattr(self, "_overlap_layers"):
             self._overlap_layers = ()
             model = self.model.module if hasattr(self.model, "module") else self.model
             opt = self.optimizer
             if (hasattr(opt, "plan_overlap") and hasattr(model, "grad_ready_layers")
                     and dutil.get_dist_util().device_type == "cuda" and dutil.get_dist_util().data_parallel_size > 1
-                    and os.environ.get("LIBAI_B200_OVERLAP_GRAD_SYNC", "1") != "0"):
+                    and os.environ.get("LIBAI_B200_OVERLAP_GRAD_SYNC", "0") == "1"):
                 self._overlap_layers = tuple(opt.plan_overlap())
             self._overlap_model = model
         if not self._overlap_layers:
