@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--zero", type=int, default=-1, help="ZeRO stage; -1 = auto (stage 1 with the fused NVLink kernels when dp > 1)")
     ap.add_argument("--acc", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graphs", type=int, default=1,
+                    help="1 (default): replay the transformer blocks from CUDA graphs (data-parallel layouts only; "
+                         "tensor/pipeline-parallel runs fall back to eager launches)")
     return ap.parse_args()
 
 
@@ -226,6 +229,13 @@ def main():
     torch.cuda.synchronize()
     model, optimizer = trainer.model, trainer.optimizer
     acc = args.acc
+    graphs_on = False
+    if args.graphs and topo.pipeline_parallel_size == 1:
+        from libai_b200.engine.cuda_graphs import enable_for_model
+
+        graphs_on = enable_for_model(model, staged[0])
+        step._graphs_tried, step.graphs_enabled = True, graphs_on
+        optimizer.zero_grad()
 
     def one_step(i):
         optimizer.zero_grad()
@@ -347,6 +357,7 @@ def main():
                 "seq_len": args.seq,
                 "parallelism": par,
                 "l2_policy": "working set (weights+activations+optimizer state >> 126MB L2) exceeds L2 every step",
+                "cuda_graphs": graphs_on,
             },
             "clocks": clocks,
             "e2e": e2e,

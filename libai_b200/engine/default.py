@@ -193,6 +193,8 @@ class DefaultTrainer(TrainerBase):
             self.model, self.train_loader, self.optimizer, cfg.train.num_accumulation_steps,
             log_period=try_get_key(cfg, "train.log_period", default=1), loss_scaler=self.loss_scaler,
         )
+        # NEW: replay the transformer blocks from CUDA graphs (engine/cuda_graphs.py); captured at the first step
+        self._trainer.cuda_graphs = bool(try_get_key(cfg, "train.cuda_graphs.enabled", default=False))
         extra = {"loss_scaler": self.loss_scaler} if self.loss_scaler is not None else {}
         self.checkpointer = Checkpointer(
             self.model, cfg.train.output_dir, optimizer=self.optimizer, lr_scheduler=self.lr_scheduler, **extra

@@ -154,6 +154,9 @@ class StepTrainer(TrainerBase):
         self.loss_scaler = loss_scaler
         self._pipeline = None
         self._ev = None
+        self.cuda_graphs = False       # set by DefaultTrainer from cfg.train.cuda_graphs.enabled
+        self._graphs_tried = False
+        self.graphs_enabled = False
 
     def _arm_grad_overlap(self, last_micro_batch: bool):
         """Opt-in (``LIBAI_B200_OVERLAP_GRAD_SYNC=1``): overlap the data-parallel gradient reduction with the backward
@@ -197,6 +200,13 @@ class StepTrainer(TrainerBase):
                 self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             self._ev[0].record()
 
+        if self.cuda_graphs and not self._graphs_tried and use_events:
+            # first step: capture forward+backward of every transformer block into CUDA graphs (engine/cuda_graphs.py)
+            from libai_b200.engine.cuda_graphs import enable_for_model
+
+            self._graphs_tried = True
+            model = self.model.module if hasattr(self.model, "module") else self.model
+            self.graphs_enabled = enable_for_model(model, batches[0])
         self.optimizer.zero_grad()
         if topo.pipeline_parallel_size > 1:
             if self._pipeline is None:
