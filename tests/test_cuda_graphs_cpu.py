@@ -1,0 +1,41 @@
+"""CUDA-graph capture is guarded: on CPU / unsupported layouts the trainer stays eager and says why."""
+import torch
+from torch import nn
+
+from libai_b200.engine import cuda_graphs
+
+
+class _Block(nn.Module):
+    def __init__(self, p=0.0):
+        super().__init__()
+        self.lin = nn.Linear(8, 8)
+        self.drop = nn.Dropout(p)
+        self.layer_idx = 0
+
+    def forward(self, x):
+        return self.drop(self.lin(x))
+
+
+def test_dropout_detection_and_cpu_guard():
+    assert not cuda_graphs._block_has_dropout(_Block(0.0))
+    assert cuda_graphs._block_has_dropout(_Block(0.1))
+    blk = _Block(0.0)
+    blk.attention_dropout_prob = 0.1
+    assert cuda_graphs._block_has_dropout(blk)
+    # CPU tensors are never captured
+    assert cuda_graphs.graph_transformer_blocks([_Block()], torch.randn(2, 8)) is None
+
+
+def test_launch_count_wrapper_keeps_module_identity():
+    from libai_b200 import ops
+
+    blk = _Block()
+    n0 = ops.launch_count()
+    same = cuda_graphs._with_launch_count(blk, 3, 5)
+    assert same is blk and list(blk.state_dict()) == ["lin.weight", "lin.bias"]
+    blk.train()
+    blk(torch.randn(2, 8))
+    assert ops.launch_count() - n0 == 8
+    with torch.no_grad():
+        blk(torch.randn(2, 8))
+    assert ops.launch_count() - n0 == 11
