@@ -113,8 +113,18 @@ def enable_for_model(model: nn.Module, example_batch: dict) -> bool:
     if shapes.get("n_args", 0) != 1 or not torch.is_tensor(shapes.get("hidden")):
         logger.warning("cuda graphs: blocks take more than the hidden state — not captured")
         return False
-    new = graph_transformer_blocks(list(layers), shapes["hidden"])
+    try:
+        new = graph_transformer_blocks(list(layers), shapes["hidden"])
+    except Exception as e:   # capture is an optimisation: never take the run down with it
+        logger.warning("cuda graphs: capture failed (%s: %s) — staying with eager launches", type(e).__name__, str(e)[:200])
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        model.train(was_training)
+        return False
     if new is None:
+        model.train(was_training)
         return False
     assert all(a is b for a, b in zip(new, layers)), "make_graphed_callables is expected to patch the modules in place"
     model.train(was_training)
