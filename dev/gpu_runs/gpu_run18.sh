@@ -1,4 +1,4 @@
-# usage: bash tools/gpu_run18.sh N  — N-GPU validation: fused collectives at world=N, then the scaling bench layouts
+# usage: bash dev/gpu_runs/gpu_run18.sh N  — N-GPU validation: fused collectives at world=N, then the scaling bench layouts
 set -x
 N=${1:-4}
 mkdir -p gpurun_out
