@@ -14,9 +14,10 @@ int lb_gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, i
 int lb_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows, int H,
                 float eps, int rms, int dtype, int wdtype, cudaStream_t s);
 int lb_norm_bwd_workspace_rows(int rows);
+int lb_norm_bwd_supports_gadd(int H);
 int lb_norm_bwd(const void* gy, const void* x, const void* gamma, const float* mean, const float* rstd, void* gx,
                 float* dgamma, float* dbeta, float* workspace, int rows, int H, int rms, int dtype, int wdtype,
-                int accumulate, cudaStream_t s);
+                int accumulate, const void* gadd, cudaStream_t s);
 int lb_bias_act_fwd(const void* x, const void* bias, void* y, long rows, int N, int act, cudaStream_t s);
 int lb_gemm_bf16_actgrad(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo,
                          int layout, int act, const void* pre_in, cudaStream_t stream);
@@ -219,7 +220,8 @@ std::tuple<Tensor, Tensor, Tensor> norm_fwd(const Tensor& x, const Tensor& gamma
 std::tuple<Tensor, Tensor, Tensor> norm_bwd(const Tensor& gy, const Tensor& x, const Tensor& gamma, const Tensor& mean,
                                             const Tensor& rstd, bool rms, bool has_bias,
                                             const c10::optional<Tensor>& dgamma_accum,
-                                            const c10::optional<Tensor>& dbeta_accum) {
+                                            const c10::optional<Tensor>& dbeta_accum,
+                                            const c10::optional<Tensor>& gadd) {
   c10::cuda::CUDAGuard guard(x.device());
   const int rows = (int)x.size(0), H = (int)x.size(1);
   Tensor gx = at::empty_like(x);
@@ -238,11 +240,15 @@ std::tuple<Tensor, Tensor, Tensor> norm_bwd(const Tensor& gy, const Tensor& x, c
   Tensor dbeta = !has_bias ? at::empty({0}, fopt) : (acc ? dbeta_accum.value() : at::empty({H}, fopt));
   const int wrows = lb_norm_bwd_workspace_rows(rows);
   Tensor ws = at::empty({2 * (int64_t)wrows * H}, fopt);
+  // optional gradient of the skip connection around this norm: added to gx inside the kernel when supported
+  const bool has_add = gadd.has_value() && gadd->defined();
+  const bool fuse_add = has_add && lb_norm_bwd_supports_gadd(H) && gadd->is_contiguous() && gadd->scalar_type() == x.scalar_type();
   check(lb_norm_bwd(gy.data_ptr(), x.data_ptr(), gamma.data_ptr(), rms ? nullptr : mean.data_ptr<float>(),
                     rstd.data_ptr<float>(), gx.data_ptr(), dgamma.data_ptr<float>(),
                     has_bias ? dbeta.data_ptr<float>() : nullptr, ws.data_ptr<float>(), rows, H, rms ? 1 : 0,
-                    dtype_code(x), dtype_code(gamma), acc ? 1 : 0, cur_stream()),
+                    dtype_code(x), dtype_code(gamma), acc ? 1 : 0, fuse_add ? gadd->data_ptr() : nullptr, cur_stream()),
         "norm_bwd");
+  if (has_add && !fuse_add) gx.add_(gadd->to(gx.scalar_type()));
   if (acc) return std::make_tuple(gx, at::empty({0}, fopt), at::empty({0}, fopt));
   return std::make_tuple(gx, dgamma, dbeta);
 }
@@ -487,7 +493,7 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("act_bwd(Tensor gy, Tensor pre, int act) -> Tensor", &act_bwd);
   m.def("colsum(Tensor x, Tensor(a!)? accum=None) -> Tensor", &colsum);
   m.def("norm_fwd(Tensor x, Tensor gamma, Tensor? beta, float eps, bool rms) -> (Tensor, Tensor, Tensor)", &norm_fwd);
-  m.def("norm_bwd(Tensor gy, Tensor x, Tensor gamma, Tensor mean, Tensor rstd, bool rms, bool has_bias, Tensor(a!)? dgamma_accum=None, Tensor(b!)? dbeta_accum=None) -> (Tensor, Tensor, Tensor)", &norm_bwd);
+  m.def("norm_bwd(Tensor gy, Tensor x, Tensor gamma, Tensor mean, Tensor rstd, bool rms, bool has_bias, Tensor(a!)? dgamma_accum=None, Tensor(b!)? dbeta_accum=None, Tensor? gadd=None) -> (Tensor, Tensor, Tensor)", &norm_bwd);
   m.def("bias_act_fwd(Tensor x, Tensor? bias, int act) -> Tensor", &bias_act_fwd);
   m.def("bias_act_bwd(Tensor gy, Tensor x, Tensor? bias, int act) -> Tensor", &bias_act_bwd);
   m.def("bias_residual_fwd(Tensor x, Tensor? bias, Tensor? res) -> Tensor", &bias_residual_fwd);

@@ -89,7 +89,8 @@ template <typename T, typename W, int VPL, bool RMS>
 __global__ void __launch_bounds__(NORM_WARPS * 32)
 norm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, const W* __restrict__ gamma,
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, T* __restrict__ gx,
-                float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, int rows) {
+                float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, int rows,
+                const T* __restrict__ gadd /* optional [rows, H]: gradient of the residual path, added to gx */) {
   constexpr int H = VPL * 256;
   __shared__ float red[NORM_WARPS][32 * 8 + 8];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -132,6 +133,12 @@ norm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, const W* __re
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = rstd * (gw[i][j] - s1 - xh[i][j] * s2);
+      if (gadd != nullptr) {  // the skip connection's gradient rides along: saves autograd's separate add kernel
+        float a[8];
+        Vec8<T>::load(gadd + static_cast<size_t>(row) * H + (i * 32 + lane) * 8, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += a[j];
+      }
       Vec8<T>::store(gxr + (i * 32 + lane) * 8, o);
     }
   }
@@ -276,10 +283,10 @@ bool fwd_dispatch(int vpl, const T* x, const W* g, const W* b, T* y, float* mean
 
 template <typename T, typename W, bool RMS>
 bool bwd_dispatch(int vpl, const T* gy, const T* x, const W* g, const float* mean, const float* rstd, T* gx, float* pdg,
-                  float* pdb, int rows, int grid, cudaStream_t s) {
+                  float* pdb, int rows, int grid, cudaStream_t s, const T* gadd) {
 #define LB_CASE(V)                                                                                                   \
   case V:                                                                                                            \
-    lb::norm_bwd_kernel<T, W, V, RMS><<<grid, lb::NORM_WARPS * 32, 0, s>>>(gy, x, g, mean, rstd, gx, pdg, pdb, rows); \
+    lb::norm_bwd_kernel<T, W, V, RMS><<<grid, lb::NORM_WARPS * 32, 0, s>>>(gy, x, g, mean, rstd, gx, pdg, pdb, rows, gadd); \
     return true;
   switch (vpl) {
     LB_CASE(1) LB_CASE(2) LB_CASE(3) LB_CASE(4) LB_CASE(5) LB_CASE(6) LB_CASE(8) LB_CASE(10) LB_CASE(12) LB_CASE(16)
@@ -325,12 +332,19 @@ extern "C" int lb_norm_fwd(const void* x, const void* gamma, const void* beta, v
 
 // workspace: float[2 * grid_cap * H] where grid_cap = lb_norm_bwd_workspace_rows(); dgamma/dbeta fp32 [H]
 extern "C" int lb_norm_bwd_workspace_rows(int rows) { return norm_grid(rows); }
+// the fused "+ residual gradient" is implemented by the register-cached kernel only (H = 256 * {1..6, 8, 10, 12, 16})
+extern "C" int lb_norm_bwd_supports_gadd(int H) {
+  if (H % 256 != 0) return 0;
+  const int v = H / 256;
+  return (v >= 1 && v <= 6) || v == 8 || v == 10 || v == 12 || v == 16;
+}
 
 extern "C" int lb_norm_bwd(const void* gy, const void* x, const void* gamma, const float* mean, const float* rstd,
                            void* gx, float* dgamma, float* dbeta, float* workspace, int rows, int H, int rms, int dtype,
-                           int wdtype, int accumulate, cudaStream_t s) {
+                           int wdtype, int accumulate, const void* gadd, cudaStream_t s) {
   if (rows == 0) return 0;
   const bool fast = (H % 256 == 0) && (H / 256 <= 16);
+  if (gadd != nullptr && !lb_norm_bwd_supports_gadd(H)) return -3;  // caller adds the residual gradient itself
   const int grid = norm_grid(rows);
   bool done = false;
   float* pdg = workspace;
@@ -339,9 +353,9 @@ extern "C" int lb_norm_bwd(const void* gy, const void* x, const void* gamma, con
   {                                                                                                                  \
     if (fast) {                                                                                                      \
       done = rms ? bwd_dispatch<T, W, true>(H / 256, (const T*)gy, (const T*)x, (const W*)gamma, mean, rstd, (T*)gx, \
-                                            pdg, pdb, rows, grid, s)                                                 \
+                                            pdg, pdb, rows, grid, s, (const T*)gadd)                                 \
                  : bwd_dispatch<T, W, false>(H / 256, (const T*)gy, (const T*)x, (const W*)gamma, mean, rstd,        \
-                                             (T*)gx, pdg, pdb, rows, grid, s);                                       \
+                                             (T*)gx, pdg, pdb, rows, grid, s, (const T*)gadd);                       \
       if (done) {                                                                                                    \
         lb::colreduce_kernel<<<dim3((H + 31) / 32, dbeta != nullptr ? 2 : 1), 256, 0, s>>>(pdg, dgamma, pdb, dbeta, grid, \
                                                                                            H, accumulate);           \

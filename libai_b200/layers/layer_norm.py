@@ -47,6 +47,13 @@ class LayerNorm(nn.Module):
             return y.view(x.shape)
         return OF.layer_norm(x, self.weight, self.bias, self.eps)
 
+    def forward_with_skip(self, x):
+        """``(norm(x), x_for_the_residual_path)``: in a pre-LN block the gradient of the skip connection is then added
+        inside the LayerNorm backward kernel instead of by a separate autograd add."""
+        if len(self.normalized_shape) != 1 or self.weight is None:
+            return self.forward(x), x
+        return OF.layer_norm_with_skip(x, self.weight, self.bias, self.eps)
+
     def extra_repr(self) -> str:
         return "{normalized_shape}, eps={eps}, elementwise_affine={elementwise_affine}".format(**self.__dict__)
 

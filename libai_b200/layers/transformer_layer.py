@@ -95,8 +95,11 @@ class TransformerLayer(nn.Module):
             cross_past = past_key_value[2:] if len(past_key_value) > 2 else None
             cross_past = cross_past or None
 
-        ln = self.input_layernorm(hidden_states)
-        residual = ln if self.apply_residual_post_layernorm else hidden_states
+        if self.apply_residual_post_layernorm:
+            ln = self.input_layernorm(hidden_states)
+            residual = ln
+        else:   # pre-LN: the skip gradient is folded into the LayerNorm backward kernel
+            ln, residual = self.input_layernorm.forward_with_skip(hidden_states)
         attn = self._branch(
             lambda residual, **kw: self.self_attention(ln, residual=residual, **kw),
             residual, attention_mask=attention_mask, past_key_value=self_past, use_cache=use_cache,
@@ -106,7 +109,11 @@ class TransformerLayer(nn.Module):
             attn, presents = attn
         hidden_states = attn
 
-        ln = self.post_attention_layernorm(hidden_states)
+        if self.apply_residual_post_layernorm or self.is_decoder:
+            ln = self.post_attention_layernorm(hidden_states)
+            post_skip = hidden_states
+        else:
+            ln, post_skip = self.post_attention_layernorm.forward_with_skip(hidden_states)
         if self.is_decoder:
             residual = ln if self.apply_residual_post_layernorm else hidden_states
             cross = self._branch(
@@ -119,8 +126,11 @@ class TransformerLayer(nn.Module):
                 presents = tuple(presents) + tuple(cross_kv)
             hidden_states = cross
             ln = self.post_cross_attention_layernorm(hidden_states)
-
-        residual = ln if self.apply_residual_post_layernorm else hidden_states
+            residual = ln if self.apply_residual_post_layernorm else hidden_states
+        elif self.apply_residual_post_layernorm:
+            residual = ln
+        else:
+            residual = post_skip
         output = self._branch(lambda residual: self.mlp(ln, residual=residual), residual)
         if use_cache:
             return output, presents

@@ -213,8 +213,12 @@ def matmul_nt(a, b):
 # LayerNorm / RMSNorm (optionally fused with the preceding residual add)
 # --------------------------------------------------------------------------------------
 class _LayerNormFn(torch.autograd.Function):
+    """``with_skip``: additionally return the input itself as a second output.  A pre-LN block uses the same tensor for
+    the norm and for the skip connection; autograd would sum the two gradients with a separate kernel — here both
+    arrive in one ``backward`` call and the skip gradient is added inside the LayerNorm backward kernel."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, rms):
+    def forward(ctx, x, weight, bias, eps, rms, with_skip=False):
         ext = load_ext()
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         y, mean, rstd = ext.norm_fwd(x2, weight, bias, eps, rms)
@@ -223,25 +227,39 @@ class _LayerNormFn(torch.autograd.Function):
         ctx.rms = rms
         ctx.has_bias = bias is not None
         ctx.bias_param = bias
+        ctx.with_skip = with_skip
+        if with_skip:
+            return y.view(x.shape), x.view_as(x)
         return y.view(x.shape)
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, gskip=None):
         ext = load_ext()
         x2, weight, mean, rstd = ctx.saved_tensors
+        if gy is None:          # only the skip output was used
+            return gskip, None, None, None, None, None
         g2 = gy.reshape(-1, gy.shape[-1]).contiguous()
+        gadd = None if gskip is None else gskip.reshape(-1, gskip.shape[-1]).contiguous()
         count_launch(2)
         wg = getattr(weight, "main_grad", None)
         bg = getattr(ctx.bias_param, "main_grad", None) if ctx.has_bias else None
         if wg is not None and wg.dtype == torch.float32 and (not ctx.has_bias or bg is not None):
             # dγ / dβ are reduced straight into the fp32 main-grad slices (one kernel for both)
-            gx, _, _ = ext.norm_bwd(g2, x2, weight, mean, rstd, ctx.rms, ctx.has_bias, wg, bg)
+            gx, _, _ = ext.norm_bwd(g2, x2, weight, mean, rstd, ctx.rms, ctx.has_bias, wg, bg, gadd)
             weight.grad_added_to_main_grad = True
             if ctx.has_bias:
                 ctx.bias_param.grad_added_to_main_grad = True
-            return gx.view(gy.shape), None, None, None, None
-        gx, gw, gb = ext.norm_bwd(g2, x2, weight, mean, rstd, ctx.rms, ctx.has_bias, None, None)
-        return gx.view(gy.shape), gw.to(weight.dtype), (gb.to(weight.dtype) if ctx.has_bias else None), None, None
+            return gx.view(gy.shape), None, None, None, None, None
+        gx, gw, gb = ext.norm_bwd(g2, x2, weight, mean, rstd, ctx.rms, ctx.has_bias, None, None, gadd)
+        return (gx.view(gy.shape), gw.to(weight.dtype), (gb.to(weight.dtype) if ctx.has_bias else None), None, None,
+                None)
+
+
+def layer_norm_with_skip(x, weight, bias, eps: float = 1e-5):
+    """``(layer_norm(x), x)`` where the second output carries the skip connection (see ``_LayerNormFn``)."""
+    if use_native(x) and x.dtype in (torch.bfloat16, torch.float32) and weight is not None and x.requires_grad:
+        return _LayerNormFn.apply(x, weight, bias, eps, False, True)
+    return layer_norm(x, weight, bias, eps), x
 
 
 def layer_norm(x, weight, bias, eps: float = 1e-5):

@@ -262,6 +262,27 @@ def main():
         dba = torch.full((1024,), -2.0, device="cuda")
         gx1, _, _ = ext.norm_bwd(gy, x, g, mean, rstd, False, True, dga, dba)
         e += [rel_err(dga, dg0 + 1.0), rel_err(dba, db0 - 2.0), rel_err(gx1, gx0)]
+        # skip-connection gradient folded into the LayerNorm backward (fast path H=1024; fallback path H=320)
+        gskip = torch.randn_like(x)
+        gx2, _, _ = ext.norm_bwd(gy, x, g, mean, rstd, False, True, None, None, gskip)
+        e.append(rel_err(gx2, gx0.float() + gskip.float()))
+        xs = torch.randn(512, 320, device="cuda").bfloat16()
+        gs, bs = g[:320].contiguous(), b[:320].contiguous()
+        _, mean_s, rstd_s = ext.norm_fwd(xs, gs, bs, 1e-5, False)
+        gys, gsk = torch.randn_like(xs), torch.randn_like(xs)
+        a0, _, _ = ext.norm_bwd(gys, xs, gs, mean_s, rstd_s, False, True, None, None)
+        a1, _, _ = ext.norm_bwd(gys, xs, gs, mean_s, rstd_s, False, True, None, None, gsk)
+        e.append(rel_err(a1, a0.float() + gsk.float()))
+        # autograd level: (norm(x), x) with both outputs used == norm(x) and x used separately
+        from libai_b200.ops import functional as OFn
+
+        xa = x[:1024].clone().requires_grad_(True)
+        xb = x[:1024].clone().requires_grad_(True)
+        w1, w2 = torch.randn_like(xa), torch.randn_like(xa)
+        ln, skip = OFn.layer_norm_with_skip(xa, g, b)
+        ((ln.float() * w1.float()).sum() + (skip.float() * w2.float()).sum()).backward()
+        ((OFn.layer_norm(xb, g, b).float() * w1.float()).sum() + (xb.float() * w2.float()).sum()).backward()
+        e.append(rel_err(xa.grad, xb.grad))
         ms = timeit(lambda: ext.colsum(x, acc))
         x2 = torch.randn(8192, 4096, device="cuda").bfloat16()
         acc2 = torch.zeros(4096, device="cuda")
