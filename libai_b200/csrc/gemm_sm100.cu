@@ -706,6 +706,15 @@ cudaError_t launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, cons
 // layout: 0 = NT (A[M,K], B[N,K]); 1 = NN (A[M,K], B[K,N]); 2 = TN (A[K,M], B[K,N])
 // epi:    0 = bf16 store (+bias, act, optional pre-activation copy); 1 = fp32 store; 2 = fp32 atomic accumulate
 // Returns 0 on success, a negative code for unsupported arguments, or a cudaError_t (> 0).
+static bool wgrad_rmw() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LIBAI_B200_WGRAD_RMW");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo, int layout,
                      int epi, const void* bias, int act, void* pre_out, const void* pre_in, int force_bn,
                      int force_splits, const lb::CommParams& cp, cudaStream_t stream) {
@@ -772,9 +781,11 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   p.k_splits = (k_blocks + p.k_per_split - 1) / p.k_per_split;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.rmw = 0;
-  if (epi == 2 && p.k_splits == 1) {
-    // a single K partition owns the whole tile: accumulate with a plain read-modify-write instead of
-    // L2 atomics (fp32 atomics are throughput-limited at the L2 slices)
+  if (epi == 2 && p.k_splits == 1 && wgrad_rmw()) {
+    // a single K partition owns the whole tile: accumulate with a plain read-modify-write instead of L2 atomics.
+    // Off by default since the epilogue became coalesced: `red.add.v4` is fire-and-forget, while the read of the old
+    // tile sits exposed at the end of a one-tile-per-CTA GEMM (profiles/r28_wgrad_sweep.json: 4096x1024x8192
+    // 2-way split with red.add 54 us vs single partition with rmw 67 us).  LIBAI_B200_WGRAD_RMW=1 restores it.
     epi = 1;
     p.rmw = 1;
   }
