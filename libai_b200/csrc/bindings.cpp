@@ -13,6 +13,8 @@ int lb_gemm_bf16(const void* a, const void* b, void* out, int M, int N, int K, i
                  int epi, const void* bias, int act, void* pre_out, int force_bn, int force_splits, cudaStream_t s);
 int lb_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows, int H,
                 float eps, int rms, int dtype, int wdtype, cudaStream_t s);
+int lb_gemm_bf16_bias_residual(const void* x, const void* w, void* out, int M, int N, int K, int lda, int ldb,
+                               const void* bias, const void* residual, cudaStream_t s);
 int lb_norm_bwd_workspace_rows(int rows);
 int lb_norm_bwd_supports_gadd(int H);
 int lb_norm_bwd(const void* gy, const void* x, const void* gamma, const float* mean, const float* rstd, void* gx,
@@ -131,6 +133,27 @@ Tensor dgrad_actgrad(const Tensor& gy, const Tensor& w, const Tensor& pre, int64
                              (int)w.stride(0), (int)N, 1, (int)act, pre.data_ptr(), cur_stream()),
         "dgrad_actgrad");
   return out;
+}
+
+// y = x @ w^T + bias + residual (one kernel)
+Tensor linear_bias_residual(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& bias, const Tensor& residual) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1), "linear_bias_residual: shape mismatch");
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && residual.scalar_type() == at::kBFloat16,
+              "linear_bias_residual: bf16 expected");
+  TORCH_CHECK(x.stride(1) == 1 && w.stride(1) == 1 && residual.is_contiguous(), "linear_bias_residual: row-major operands");
+  const int64_t M = x.size(0), K = x.size(1), N = w.size(0);
+  TORCH_CHECK(residual.dim() == 2 && residual.size(0) == M && residual.size(1) == N, "linear_bias_residual: residual must be [M, N]");
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = at::empty({M, N}, x.options());
+  const void* bias_ptr = nullptr;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->scalar_type() == at::kBFloat16 && bias->numel() == N, "linear_bias_residual: bias must be bf16 [N]");
+    bias_ptr = bias->data_ptr();
+  }
+  check(lb_gemm_bf16_bias_residual(x.data_ptr(), w.data_ptr(), y.data_ptr(), (int)M, (int)N, (int)K, (int)x.stride(0),
+                                   (int)w.stride(0), bias_ptr, residual.data_ptr(), cur_stream()),
+        "linear_bias_residual");
+  return y;
 }
 
 // y = act(x @ w^T + bias); optionally also returns the pre-activation (for backward)
@@ -488,6 +511,7 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("device_barrier(int[] flag_ptrs, int world, int rank, int slot, int epoch) -> ()", &device_barrier);
   m.def("p2p_allgather(Tensor shard, int[] out_ptrs, int[] flag_ptrs, Tensor(a!) done_counter, int world, int rank, int epoch) -> ()", &p2p_allgather);
   m.def("gemm(Tensor a, Tensor b, int layout, Tensor? bias, Tensor? out, bool accumulate, ScalarType out_dtype) -> Tensor", &gemm);
+  m.def("linear_bias_residual(Tensor x, Tensor w, Tensor? bias, Tensor residual) -> Tensor", &linear_bias_residual);
   m.def("gemm_tuned(Tensor a, Tensor b, int layout, int bn, int splits, bool fp32_out) -> Tensor", &gemm_tuned);
   m.def("linear_fwd(Tensor x, Tensor w, Tensor? bias, int act, bool need_pre) -> (Tensor, Tensor)", &linear_fwd);
   m.def("act_bwd(Tensor gy, Tensor pre, int act) -> Tensor", &act_bwd);

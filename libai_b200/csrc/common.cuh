@@ -229,7 +229,8 @@ LB_DEVICE float2 unpack_bf16(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
-enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_GELU_TANH = 2, ACT_RELU = 3, ACT_SILU = 4, ACT_QUICK_GELU = 5 };
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_GELU_TANH = 2, ACT_RELU = 3, ACT_SILU = 4, ACT_QUICK_GELU = 5,
+                 ACT_RESADD = 6 /* GEMM epilogue only: out = acc (+ bias) + pre_in, i.e. the residual add */ };
 
 // erfc(|x|/sqrt2) and exp(-x^2/2) from one MUFU.EX2 + one MUFU.RCP (Abramowitz-Stegun 7.1.26, |err(erf)| < 1.5e-7 -
 // three orders of magnitude below bf16 resolution).  The libm erff costs ~60 instructions with a divergent branch,

@@ -437,7 +437,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int i = 0; i < 32; i += 8) {
               const uint4 q = pq[i / 8];
               const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c2 = unpack_bf16(q.z), d = unpack_bf16(q.w);
-              if (p.act == ACT_GELU) {  // hot case without the per-element switch
+              if (p.act == ACT_RESADD) {  // row-parallel output projection: y = x·Wᵀ + bias + residual in one pass
+                v[i] += a.x; v[i + 1] += a.y; v[i + 2] += b.x; v[i + 3] += b.y;
+                v[i + 4] += c2.x; v[i + 5] += c2.y; v[i + 6] += d.x; v[i + 7] += d.y;
+              } else if (p.act == ACT_GELU) {  // hot case without the per-element switch
                 v[i] *= gelu_grad_fast(a.x); v[i + 1] *= gelu_grad_fast(a.y);
                 v[i + 2] *= gelu_grad_fast(b.x); v[i + 3] *= gelu_grad_fast(b.y);
                 v[i + 4] *= gelu_grad_fast(c2.x); v[i + 5] *= gelu_grad_fast(c2.y);
@@ -838,6 +841,15 @@ extern "C" int lb_gemm_bf16_actgrad(const void* a, const void* b, void* out, int
   lb::CommParams cp;
   memset(&cp, 0, sizeof(cp));
   return gemm_impl(a, b, out, M, N, K, lda, ldb, ldo, layout, 0, nullptr, act, nullptr, pre_in, 0, 0, cp, stream);
+}
+
+// y[M,N] = x[M,K]·w[N,K]ᵀ + bias[N] + residual[M,N]   (bias+residual add of the transformer block in the GEMM epilogue;
+// the residual tile is fetched coalesced through the epilogue staging slot while the TMEM load is in flight)
+extern "C" int lb_gemm_bf16_bias_residual(const void* x, const void* w, void* out, int M, int N, int K, int lda, int ldb,
+                                          const void* bias, const void* residual, cudaStream_t stream) {
+  lb::CommParams cp;
+  memset(&cp, 0, sizeof(cp));
+  return gemm_impl(x, w, out, M, N, K, lda, ldb, N, 0, 0, bias, lb::ACT_RESADD, nullptr, residual, 0, 0, cp, stream);
 }
 
 // Tensor-parallel fused collective GEMMs (NT layout, bf16 output).

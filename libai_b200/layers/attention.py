@@ -149,6 +149,11 @@ class MultiheadAttention(nn.Module):
                 ).reshape(bsz, -1, a * d)
                 if sp and hidden_states.dim() == 2:
                     context = context.reshape(-1, a * d)
+                topo = dutil.get_dist_util()
+                if (residual is not None and topo.tensor_parallel_size == 1 and context.dtype == torch.bfloat16
+                        and (self.output_dropout_prob == 0.0 or not self.training)):
+                    # bias + residual in the epilogue of the output projection
+                    return OF.linear_bias_residual(context, self.dense.weight, self.dense.bias, residual)
                 output, bias = self.dense(context)
                 return OF.bias_dropout_add(output, bias, residual, self.output_dropout_prob, self.training)
             qkv = qkv_packed.permute(0, 2, 1, 3)

@@ -6,6 +6,7 @@ row-parallel linear, bias+dropout.  The bias+GELU runs in the epilogue of the fi
 / ``bias_dropout_fusion`` are accepted for config compatibility (both paths compute the same
 function).
 """
+import torch
 from torch import nn
 
 from libai_b200.ops import functional as OF
@@ -50,6 +51,12 @@ class MLP(nn.Module):
         if not topo.sequence_parallel and not topo.fused_tp_comm:
             # both GEMMs in one autograd node: GELU' runs in the epilogue of the second layer's dgrad
             x = mappings.copy_to_tp(hidden_states)
+            if (residual is not None and topo.tensor_parallel_size == 1
+                    and (self.output_dropout_prob == 0.0 or not self.training) and x.dtype == torch.bfloat16):
+                # no reduction and no dropout between the second GEMM and the residual add: bias + residual go
+                # into that GEMM's epilogue
+                return OF.mlp(x, self.dense_h_to_4h.weight, self.dense_h_to_4h.bias, self.dense_4h_to_h.weight, "gelu",
+                              self.dense_4h_to_h.bias, residual)
             out = OF.mlp(x, self.dense_h_to_4h.weight, self.dense_h_to_4h.bias, self.dense_4h_to_h.weight, "gelu")
             out, bias = mappings.reduce_from_tp(out), self.dense_4h_to_h.bias
         else:

@@ -151,19 +151,25 @@ class _MLPFn(torch.autograd.Function):
     separate bias+activation backward pass over the ``[tokens, ffn]`` tensor disappears."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, act):
+    def forward(ctx, x, w1, b1, w2, act, b2=None, residual=None):
         ext = load_ext()
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         h, pre = ext.linear_fwd(x2, w1, b1, _ACT_IDS[act], True)
-        y, _ = ext.linear_fwd(h, w2, None, 0, False)
+        if residual is not None:
+            # second bias and the block's residual add ride in the epilogue of the second GEMM
+            y = ext.linear_bias_residual(h, w2, b2, residual.reshape(-1, w2.shape[0]).contiguous())
+        else:
+            y, _ = ext.linear_fwd(h, w2, b2, 0, False)
         count_launch(2)
         ctx.act = act
         ctx.save_for_backward(x2, w1, w2, pre, h)
         ctx.x_shape = x.shape
         ctx.has_bias = b1 is not None
         ctx.bias_param = b1
+        ctx.bias2_param = b2
+        ctx.has_res = residual is not None
         return y.view(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
@@ -194,14 +200,69 @@ class _MLPFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = ext.gemm(dpre, w1, 1, None, None, False, torch.bfloat16).view(ctx.x_shape)
             count_launch()
-        return gx, gw1, gb1, gw2, None
+        gb2 = None
+        if ctx.bias2_param is not None and ctx.needs_input_grad[5]:
+            gb2 = _bias_grad(ext, g2, ctx.bias2_param)
+        return gx, gw1, gb1, gw2, None, gb2, (gy if ctx.has_res else None)
 
 
-def mlp(x, w1, b1, w2, act: str = "gelu"):
-    """``act(x @ w1ᵀ + b1) @ w2ᵀ`` (the second bias is left to the fused bias+dropout+residual op)."""
+def mlp(x, w1, b1, w2, act: str = "gelu", b2=None, residual=None):
+    """``act(x @ w1ᵀ + b1) @ w2ᵀ``; with ``residual`` also ``+ b2 + residual`` in the second GEMM's epilogue
+    (without it the second bias is left to the fused bias+dropout+residual op)."""
     if use_native(x, w1) and _gemm_ok(x, w1) and _gemm_ok(x.new_empty(1, w1.shape[0]), w2):
+        if residual is not None:
+            return _MLPFn.apply(x, w1, b1, w2, act, b2, residual)
         return _MLPFn.apply(x, w1, b1, w2, act)
-    return linear(linear(x, w1, b1, act), w2)
+    y = linear(linear(x, w1, b1, act), w2, b2)
+    return y if residual is None else y + residual
+
+
+class _LinearResidualFn(torch.autograd.Function):
+    """``x @ wᵀ + bias + residual`` with bias and residual added in the GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, residual):
+        ext = load_ext()
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y = ext.linear_bias_residual(x2, w, bias, residual.reshape(-1, w.shape[0]).contiguous())
+        count_launch()
+        ctx.bias_param = bias
+        ctx.save_for_backward(x2, w)
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        ext = load_ext()
+        x2, w = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ext.gemm(g2, w, 1, None, None, False, torch.bfloat16).view(ctx.x_shape)
+            count_launch()
+        if ctx.needs_input_grad[1]:
+            main_grad = getattr(w, "main_grad", None)
+            if main_grad is not None:
+                ext.gemm(g2, x2, 2, None, main_grad, True, torch.float32)
+                w.grad_added_to_main_grad = True
+            else:
+                gw = ext.gemm(g2, x2, 2, None, None, False, torch.float32).to(w.dtype)
+            count_launch()
+        if ctx.bias_param is not None and ctx.needs_input_grad[2]:
+            gb = _bias_grad(ext, g2, ctx.bias_param)
+        return gx, gw, gb, gy
+
+
+def linear_bias_residual(x, w, bias, residual):
+    """``x @ wᵀ + bias + residual`` (output projection of a block, dropout-free)."""
+    if use_native(x, w) and _gemm_ok(x, w) and residual is not None and residual.dtype == torch.bfloat16:
+        return _LinearResidualFn.apply(x, w, bias, residual)
+    y = linear(x, w, bias)
+    return y if residual is None else y + residual
 
 
 def matmul_nt(a, b):

@@ -178,6 +178,46 @@ def main():
 
     record("mlp fused fwd/bwd", mlp_fn)
 
+    def bias_residual_epilogue():
+        """x·Wᵀ + bias + residual in the GEMM epilogue (raw op, autograd op, and inside the fused MLP node)."""
+        from libai_b200.ops import functional as OFn
+
+        M, K, N = 2048 + 64, 1024, 768
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") * 0.03).bfloat16()
+        b = torch.randn(N, device="cuda").bfloat16()
+        r = torch.randn(M, N, device="cuda").bfloat16()
+        ref = x.float() @ w.float().t() + b.float() + r.float()
+        e = [rel_err(ext.linear_bias_residual(x, w, b, r), ref), rel_err(ext.linear_bias_residual(x, w, None, r), ref - b.float())]
+        xa, wa, ba, ra = (t.clone().requires_grad_(True) for t in (x, w, b, r))
+        xb, wb, bb, rb = (t.clone().requires_grad_(True) for t in (x, w, b, r))
+        gy = torch.randn(M, N, device="cuda").bfloat16()
+        OFn.linear_bias_residual(xa, wa, ba, ra).backward(gy)
+        (OFn.linear(xb, wb, bb) + rb).backward(gy)
+        e += [rel_err(xa.grad, xb.grad), rel_err(wa.grad, wb.grad), rel_err(ba.grad, bb.grad), rel_err(ra.grad, rb.grad)]
+        F1 = 512
+        w1 = (torch.randn(F1, K, device="cuda") * 0.03).bfloat16().requires_grad_(True)
+        b1 = torch.randn(F1, device="cuda").bfloat16().requires_grad_(True)
+        w2 = (torch.randn(K, F1, device="cuda") * 0.03).bfloat16().requires_grad_(True)
+        b2 = torch.randn(K, device="cuda").bfloat16().requires_grad_(True)
+        res = torch.randn(M, K, device="cuda").bfloat16().requires_grad_(True)
+        xin = x.clone().requires_grad_(True)
+        y1 = OFn.mlp(xin, w1, b1, w2, "gelu", b2, res)
+        g = torch.randn_like(y1)
+        y1.backward(g)
+        got = [t.grad.clone() for t in (xin, w1, b1, w2, b2, res)]
+        for t in (xin, w1, b1, w2, b2, res):
+            t.grad = None
+        y0 = OFn.mlp(xin, w1, b1, w2, "gelu") + b2 + res
+        y0.backward(g)
+        e.append(rel_err(y1, y0))
+        e += [rel_err(a, t.grad) for a, t in zip(got, (xin, w1, b1, w2, b2, res))]
+        ms_fused = timeit(lambda: ext.linear_bias_residual(x, w, b, r))
+        ms_sep = timeit(lambda: ext.bias_residual_fwd(ext.linear_fwd(x, w, None, 0, False)[0], b, r))
+        return {"ok": max(e) < 2e-2, "errs": e, "fused_ms": ms_fused, "gemm_then_bias_residual_ms": ms_sep}
+
+    record("bias+residual GEMM epilogue", bias_residual_epilogue)
+
     # ------------------------------------------------------------------ norms
     for rms in (False, True):
         for H in (1024, 768, 4096, 200):
