@@ -33,6 +33,8 @@ int lb_rope_qkv(const void* x, const float* cosv, const float* sinv, void* y, lo
 int lb_rope(const void* x, const float* cosv, const float* sinv, void* y, long rows, int S, int D, int backward,
             cudaStream_t s);
 int lb_colsum(const void* x, float* out, int M, int N, int accumulate, cudaStream_t s);
+int lb_embedding_fwd(const int64_t* ids, const void* table, void* out, long T, int H, long vocab_start, long rows, cudaStream_t s);
+int lb_embedding_bwd(const int64_t* ids, const void* gy, float* grad, long T, int H, long vocab_start, long rows, cudaStream_t s);
 int lb_ce_stats(const void* logits, const int64_t* labels, float* mx, float* se, float* tgt, int T, int V,
                 long vocab_start, int dtype, cudaStream_t s);
 int lb_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* gloss, void* dlogits, int T,
@@ -209,6 +211,31 @@ Tensor act_bwd(const Tensor& gy, const Tensor& pre, int64_t act) {
 
 // column sums of a bf16 [M, N] tensor.  With `accum` (fp32 [N], e.g. a bias' slice of the flat main-grad buffer) the
 // sums are added into it and an empty tensor is returned; otherwise a fresh bf16 [N] tensor.
+// embedding lookup on a (vocabulary shard of a) bf16 table; ids int64 (any shape) -> [ids.numel(), H]
+Tensor embedding_fwd(const Tensor& ids, const Tensor& table, int64_t vocab_start) {
+  c10::cuda::CUDAGuard guard(table.device());
+  TORCH_CHECK(ids.scalar_type() == at::kLong && ids.is_contiguous() && ids.is_cuda(), "embedding_fwd: contiguous int64 CUDA ids");
+  TORCH_CHECK(table.dim() == 2 && table.is_contiguous() && table.scalar_type() == at::kBFloat16, "embedding_fwd: contiguous bf16 table");
+  const int64_t T = ids.numel(), H = table.size(1);
+  Tensor out = at::empty({T, H}, table.options());
+  check(lb_embedding_fwd(ids.data_ptr<int64_t>(), table.data_ptr(), out.data_ptr(), (long)T, (int)H, (long)vocab_start,
+                         (long)table.size(0), cur_stream()),
+        "embedding_fwd");
+  return out;
+}
+// grad[ids - vocab_start] += gy   (grad: the parameter's fp32 main-grad view, same shape as the table)
+void embedding_bwd(const Tensor& ids, const Tensor& gy, Tensor grad, int64_t vocab_start) {
+  c10::cuda::CUDAGuard guard(gy.device());
+  TORCH_CHECK(ids.scalar_type() == at::kLong && ids.is_contiguous(), "embedding_bwd: contiguous int64 ids");
+  TORCH_CHECK(gy.dim() == 2 && gy.is_contiguous() && gy.scalar_type() == at::kBFloat16 && gy.size(0) == ids.numel(),
+              "embedding_bwd: gy must be contiguous bf16 [ids.numel(), H]");
+  TORCH_CHECK(grad.dim() == 2 && grad.is_contiguous() && grad.scalar_type() == at::kFloat && grad.size(1) == gy.size(1),
+              "embedding_bwd: grad must be contiguous fp32 [rows, H]");
+  check(lb_embedding_bwd(ids.data_ptr<int64_t>(), gy.data_ptr(), grad.data_ptr<float>(), (long)ids.numel(), (int)gy.size(1),
+                         (long)vocab_start, (long)grad.size(0), cur_stream()),
+        "embedding_bwd");
+}
+
 Tensor colsum(const Tensor& x, const c10::optional<Tensor>& accum) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && x.scalar_type() == at::kBFloat16, "colsum: contiguous bf16 [M,N]");
@@ -512,6 +539,8 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("p2p_allgather(Tensor shard, int[] out_ptrs, int[] flag_ptrs, Tensor(a!) done_counter, int world, int rank, int epoch) -> ()", &p2p_allgather);
   m.def("gemm(Tensor a, Tensor b, int layout, Tensor? bias, Tensor? out, bool accumulate, ScalarType out_dtype) -> Tensor", &gemm);
   m.def("linear_bias_residual(Tensor x, Tensor w, Tensor? bias, Tensor residual) -> Tensor", &linear_bias_residual);
+  m.def("embedding_fwd(Tensor ids, Tensor table, int vocab_start) -> Tensor", &embedding_fwd);
+  m.def("embedding_bwd(Tensor ids, Tensor gy, Tensor(a!) grad, int vocab_start) -> ()", &embedding_bwd);
   m.def("gemm_tuned(Tensor a, Tensor b, int layout, int bn, int splits, bool fp32_out) -> Tensor", &gemm_tuned);
   m.def("linear_fwd(Tensor x, Tensor w, Tensor? bias, int act, bool need_pre) -> (Tensor, Tensor)", &linear_fwd);
   m.def("act_bwd(Tensor gy, Tensor pre, int act) -> Tensor", &act_bwd);

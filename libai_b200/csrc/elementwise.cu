@@ -413,6 +413,35 @@ __global__ void sqnorm_kernel(const float* __restrict__ x, float* __restrict__ o
   }
 }
 
+// ---- embedding ---------------------------------------------------------------------------------------------------
+// out[t, :] = table[ids[t] - vocab_start, :]  (zero row when the id belongs to another vocabulary shard)
+__global__ void __launch_bounds__(128) embedding_fwd_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
+                                                            __nv_bfloat16* __restrict__ out, int H, long vocab_start, long rows) {
+  const long t = blockIdx.x;
+  const long r = ids[t] - vocab_start;
+  const bool inside = r >= 0 && r < rows;
+  const uint4* src = reinterpret_cast<const uint4*>(table + (inside ? r : 0) * H);
+  uint4* dst = reinterpret_cast<uint4*>(out + t * H);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = inside ? src[i] : make_uint4(0, 0, 0, 0);
+}
+
+// grad_table[ids[t] - vocab_start, :] += gy[t, :]   (fp32 main-grad buffer, vector reductions: no sort, no temporary,
+// and the tied LM-head wgrad accumulates into the same buffer)
+__global__ void __launch_bounds__(128) embedding_bwd_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ gy,
+                                                            float* __restrict__ grad, int H, long vocab_start, long rows) {
+  const long t = blockIdx.x;
+  const long r = ids[t] - vocab_start;
+  if (r < 0 || r >= rows) return;
+  const uint4* src = reinterpret_cast<const uint4*>(gy + t * H);
+  float* dst = grad + r * H;
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 q = src[i];
+    const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst + i * 8), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst + i * 8 + 4), "f"(c.x), "f"(c.y), "f"(d.x), "f"(d.y) : "memory");
+  }
+}
+
 }  // namespace lb
 
 namespace {
@@ -527,6 +556,20 @@ extern "C" int lb_adamw(float* master, const float* grad, float* m, float* v, vo
   if (n == 0) return 0;
   lb::adamw_kernel<<<ew_grid(n / 4, 256), 256, 0, s>>>(master, grad, m, v, (bf16*)lp_out, scale, (size_t)n, lr, b1, b2,
                                                        eps, wd, bc1, bc2, decoupled);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_embedding_fwd(const int64_t* ids, const void* table, void* out, long T, int H, long vocab_start, long rows,
+                                cudaStream_t s) {
+  if (T == 0) return 0;
+  if (H % 8) return -1;
+  lb::embedding_fwd_kernel<<<(unsigned)T, 128, 0, s>>>(ids, (const bf16*)table, (bf16*)out, H, vocab_start, rows);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_embedding_bwd(const int64_t* ids, const void* gy, float* grad, long T, int H, long vocab_start, long rows,
+                                cudaStream_t s) {
+  if (T == 0) return 0;
+  if (H % 8) return -1;
+  lb::embedding_bwd_kernel<<<(unsigned)T, 128, 0, s>>>(ids, (const bf16*)gy, grad, H, vocab_start, rows);
   return (int)cudaGetLastError();
 }
 extern "C" int lb_sqnorm(const float* x, float* out, long n, cudaStream_t s) {

@@ -51,7 +51,7 @@ class Embedding(nn.Module):
         self._fill_padding_idx_with_zero()
 
     def forward(self, input_ids):
-        return torch.nn.functional.embedding(input_ids, self.weight)
+        return OF.embedding(input_ids, self.weight) if input_ids.is_cuda else torch.nn.functional.embedding(input_ids, self.weight)
 
     def _fill_padding_idx_with_zero(self) -> None:
         if self.padding_idx is not None and self.weight.device.type != "meta":
@@ -100,11 +100,8 @@ class VocabEmbedding(nn.Module):
     def forward(self, input_ids, scatter_to_sequence_parallel: bool = False):
         topo = dutil.get_dist_util()
         if topo.tensor_parallel_size == 1:
-            return torch.nn.functional.embedding(input_ids, self.weight)
-        local = input_ids - self.vocab_start
-        inside = (local >= 0) & (local < self.vocab_per_rank)
-        out = torch.nn.functional.embedding(local.clamp(0, self.vocab_per_rank - 1), self.weight)
-        out = out * inside.unsqueeze(-1).to(out.dtype)
+            return OF.embedding(input_ids, self.weight) if input_ids.is_cuda else torch.nn.functional.embedding(input_ids, self.weight)
+        out = OF.embedding(input_ids, self.weight, self.vocab_start)   # zero rows for ids of other vocabulary shards
         if scatter_to_sequence_parallel and topo.sequence_parallel:
             return mappings.reduce_scatter_to_sp(out.reshape(-1, out.shape[-1]))
         return mappings.reduce_from_tp(out)
@@ -131,7 +128,8 @@ class SinePositionalEmbedding(nn.Module):
         self.register_buffer("position_embedding", table.to(param_device()) if owned else table.to("meta"), persistent=False)
 
     def forward(self, position_ids):
-        return torch.nn.functional.embedding(position_ids, self.position_embedding)
+        return (OF.embedding(position_ids, self.position_embedding) if position_ids.is_cuda
+                else torch.nn.functional.embedding(position_ids, self.position_embedding))
 
     def extra_repr(self) -> str:
         return f"num_embeddings={self.num_embeddings}, embedding_dim={self.embedding_dim}"

@@ -586,9 +586,44 @@ def vocab_parallel_cross_entropy(logits, labels, vocab_start: int = 0, group=Non
 # --------------------------------------------------------------------------------------
 # embedding
 # --------------------------------------------------------------------------------------
+class _EmbeddingFn(torch.autograd.Function):
+    """Row gather; the backward scatters ``gy`` straight into the table's fp32 ``main_grad`` with vector reductions
+    (no sort / segment-reduce / temporary gradient the size of the table, and no later fold of ``p.grad``)."""
+
+    @staticmethod
+    def forward(ctx, ids, table, vocab_start):
+        ext = load_ext()
+        flat = ids.reshape(-1).contiguous()
+        out = ext.embedding_fwd(flat, table, vocab_start)
+        count_launch()
+        ctx.save_for_backward(flat)
+        ctx.table = table
+        ctx.vocab_start = vocab_start
+        return out.view(*ids.shape, table.shape[1])
+
+    @staticmethod
+    def backward(ctx, gy):
+        (flat,) = ctx.saved_tensors
+        table = ctx.table
+        g2 = gy.reshape(-1, gy.shape[-1]).contiguous()
+        ext = load_ext()
+        count_launch()
+        main_grad = getattr(table, "main_grad", None)
+        if main_grad is not None and main_grad.dtype == torch.float32:
+            ext.embedding_bwd(flat, g2, main_grad, ctx.vocab_start)
+            table.grad_added_to_main_grad = True
+            return None, None, None
+        grad = torch.zeros(table.shape, dtype=torch.float32, device=table.device)
+        ext.embedding_bwd(flat, g2, grad, ctx.vocab_start)
+        return None, grad.to(table.dtype), None
+
+
 def embedding(ids, table, vocab_start: int = 0):
     """Row gather with zero rows for ids outside ``[vocab_start, vocab_start + rows)``."""
     rows = table.shape[0]
+    if (use_native(table) and table.dtype == torch.bfloat16 and table.dim() == 2 and table.shape[1] % 8 == 0
+            and table.is_contiguous() and ids.dtype == torch.long):
+        return _EmbeddingFn.apply(ids, table, int(vocab_start))
     local = ids - vocab_start
     inside = (local >= 0) & (local < rows)
     out = F.embedding(local.clamp(0, rows - 1), table)
