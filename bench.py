@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--graphs", type=int, default=1,
                     help="1 (default): replay the transformer blocks from CUDA graphs (data-parallel layouts only; "
                          "tensor/pipeline-parallel runs fall back to eager launches)")
+    ap.add_argument("--fp8", type=int, default=0,
+                    help="1: forward GEMMs with E4M3 operands (experiment; the headline number is the bf16 default — "
+                         "the JSON line then says dtype fp8-fwd/bf16-bwd)")
     return ap.parse_args()
 
 
@@ -229,6 +232,10 @@ def main():
     torch.cuda.synchronize()
     model, optimizer = trainer.model, trainer.optimizer
     acc = args.acc
+    if args.fp8:
+        from libai_b200 import ops as _ops
+
+        _ops.set_fp8(True)
     graphs_on = False
     if args.graphs and topo.pipeline_parallel_size == 1:
         from libai_b200.engine.cuda_graphs import enable_for_model
@@ -347,7 +354,7 @@ def main():
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": (value / base) if base else None,
-            "dtype": "bf16",
+            "dtype": "bf16" if not args.fp8 else "fp8(e4m3)-fwd/bf16-bwd",
             "data": "synthetic tokens, random-init weights",
             "impl": args.impl,
             "config": {

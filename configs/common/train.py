@@ -31,6 +31,9 @@ train = dict(
     # NEW: capture forward+backward of every transformer block into CUDA graphs at the first step and replay them
     # (≈800 kernel launches per step become 48 graph launches; needs dp-only layout, static shapes, dropout 0)
     cuda_graphs=dict(enabled=False),
+    # NEW: forward GEMMs of the linear layers with E4M3 operands (per-tensor dynamic scaling, tcgen05 kind::f8f6f4,
+    # fp32 accumulation, bf16 outputs); backward GEMMs stay bf16.  Opt-in: see docs/source/tutorials/basics/Kernels.md
+    fp8=dict(enabled=False),
     # gradient bucket size for data-parallel reduction (names kept from the reference)
     nccl_fusion_threshold_mb=16,
     nccl_fusion_max_ops=24,

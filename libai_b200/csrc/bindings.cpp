@@ -15,6 +15,9 @@ int lb_norm_fwd(const void* x, const void* gamma, const void* beta, void* y, flo
                 float eps, int rms, int dtype, int wdtype, cudaStream_t s);
 int lb_gemm_bf16_bias_residual(const void* x, const void* w, void* out, int M, int N, int K, int lda, int ldb,
                                const void* bias, const void* residual, cudaStream_t s);
+int lb_gemm_fp8(const void* xq, const void* wq, void* out, int M, int N, int K, const void* bias, int act, void* pre_out,
+                const void* residual, const float* deq_x, const float* deq_w, cudaStream_t s);
+int lb_quant_e4m3(const void* x, void* q, void* amax_scratch, float* deq, long n, cudaStream_t s);
 int lb_norm_bwd_workspace_rows(int rows);
 int lb_norm_bwd_supports_gadd(int H);
 int lb_norm_bwd(const void* gy, const void* x, const void* gamma, const float* mean, const float* rstd, void* gx,
@@ -179,6 +182,52 @@ std::tuple<Tensor, Tensor> linear_fwd(const Tensor& x, const Tensor& w, const c1
                      cur_stream()),
         "linear_fwd");
   return std::make_tuple(y, pre.defined() ? pre : at::empty({0}, x.options()));
+}
+
+// per-tensor E4M3 quantisation of a contiguous bf16 tensor: returns (q [same shape, float8_e4m3fn], deq fp32 [1]) with
+// x ≈ q * deq (deq = amax / 448); two kernels, no host synchronisation
+std::tuple<Tensor, Tensor> quantize_e4m3(const Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && x.scalar_type() == at::kBFloat16, "quantize_e4m3: contiguous bf16 CUDA tensor");
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor q = at::empty(x.sizes(), x.options().dtype(at::kFloat8_e4m3fn));
+  Tensor scratch = at::empty({2}, x.options().dtype(at::kFloat));   // [0] = dequantisation scale, [1] = amax bits
+  check(lb_quant_e4m3(x.data_ptr(), q.data_ptr(), scratch.data_ptr<float>() + 1, scratch.data_ptr<float>(), (long)x.numel(),
+                      cur_stream()),
+        "quantize_e4m3");
+  return std::make_tuple(q, scratch.narrow(0, 0, 1));
+}
+
+// fp8 forward: y = act((xq @ wqᵀ) * deq_x * deq_w + bias) in bf16, optional bf16 pre-activation copy
+std::tuple<Tensor, Tensor> linear_fp8_fwd(const Tensor& xq, const Tensor& wq, const Tensor& deq_x, const Tensor& deq_w,
+                                          const c10::optional<Tensor>& bias, int64_t act, bool want_pre,
+                                          const c10::optional<Tensor>& residual) {
+  TORCH_CHECK(xq.is_cuda() && xq.dim() == 2 && wq.dim() == 2 && xq.size(1) == wq.size(1), "linear_fp8_fwd: shape mismatch");
+  TORCH_CHECK(xq.scalar_type() == at::kFloat8_e4m3fn && wq.scalar_type() == at::kFloat8_e4m3fn, "linear_fp8_fwd: e4m3 operands");
+  TORCH_CHECK(xq.is_contiguous() && wq.is_contiguous(), "linear_fp8_fwd: contiguous operands");
+  TORCH_CHECK(deq_x.scalar_type() == at::kFloat && deq_w.scalar_type() == at::kFloat && deq_x.is_cuda() && deq_w.is_cuda(),
+              "linear_fp8_fwd: fp32 device scales");
+  const int64_t M = xq.size(0), K = xq.size(1), N = wq.size(0);
+  TORCH_CHECK(K % 16 == 0 && N % 8 == 0, "linear_fp8_fwd: K % 16 == 0 and N % 8 == 0 required");
+  c10::cuda::CUDAGuard guard(xq.device());
+  auto opts = xq.options().dtype(at::kBFloat16);
+  Tensor y = at::empty({M, N}, opts);
+  Tensor pre = want_pre ? at::empty({M, N}, opts) : Tensor();
+  const void* bias_ptr = nullptr;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->scalar_type() == at::kBFloat16 && bias->numel() == N, "linear_fp8_fwd: bias must be bf16 [N]");
+    bias_ptr = bias->data_ptr();
+  }
+  const void* res_ptr = nullptr;
+  if (residual.has_value() && residual->defined()) {
+    TORCH_CHECK(residual->scalar_type() == at::kBFloat16 && residual->is_contiguous() && residual->numel() == M * N,
+                "linear_fp8_fwd: residual must be contiguous bf16 [M, N]");
+    res_ptr = residual->data_ptr();
+  }
+  check(lb_gemm_fp8(xq.data_ptr(), wq.data_ptr(), y.data_ptr(), (int)M, (int)N, (int)K, bias_ptr, (int)act,
+                    pre.defined() ? pre.data_ptr() : nullptr, res_ptr, deq_x.data_ptr<float>(), deq_w.data_ptr<float>(),
+                    cur_stream()),
+        "linear_fp8_fwd");
+  return std::make_tuple(y, pre.defined() ? pre : at::empty({0}, opts));
 }
 
 // raw entry used by tests / autotuning: explicit tile-N and split-K
@@ -543,6 +592,8 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("embedding_bwd(Tensor ids, Tensor gy, Tensor(a!) grad, int vocab_start) -> ()", &embedding_bwd);
   m.def("gemm_tuned(Tensor a, Tensor b, int layout, int bn, int splits, bool fp32_out) -> Tensor", &gemm_tuned);
   m.def("linear_fwd(Tensor x, Tensor w, Tensor? bias, int act, bool need_pre) -> (Tensor, Tensor)", &linear_fwd);
+  m.def("quantize_e4m3(Tensor x) -> (Tensor, Tensor)", &quantize_e4m3);
+  m.def("linear_fp8_fwd(Tensor xq, Tensor wq, Tensor deq_x, Tensor deq_w, Tensor? bias, int act, bool need_pre, Tensor? residual=None) -> (Tensor, Tensor)", &linear_fp8_fwd);
   m.def("act_bwd(Tensor gy, Tensor pre, int act) -> Tensor", &act_bwd);
   m.def("colsum(Tensor x, Tensor(a!)? accum=None) -> Tensor", &colsum);
   m.def("norm_fwd(Tensor x, Tensor gamma, Tensor? beta, float eps, bool rms) -> (Tensor, Tensor, Tensor)", &norm_fwd);

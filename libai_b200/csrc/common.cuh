@@ -135,6 +135,15 @@ LB_DEVICE void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// 8-bit float operands (E4M3/E5M2 selected by the instruction descriptor), 32 elements of K per instruction
+LB_DEVICE void umma_f8_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // A operand from TMEM (used by attention: P stays in tensor memory)
 LB_DEVICE void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -215,6 +224,11 @@ LB_DEVICE uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, 
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n, bool a_mn_major, bool b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
          ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// kind::f8f6f4 with E4M3 x E4M3 inputs (a_format = b_format = 0), fp32 accumulation, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(uint32_t m, uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 // apply_rotary_pos_emb (projects/Llama/llama.py:31-43), sparse_softmax_cross_entropy
 // (libai/layers/cross_entropy.py:44), flow.optim.AdamW multi-tensor update (configs/common/optim.py).
 #include "common.cuh"
+#include <cuda_fp8.h>
 
 namespace lb {
 
@@ -575,5 +576,74 @@ extern "C" int lb_embedding_bwd(const int64_t* ids, const void* gy, float* grad,
 extern "C" int lb_sqnorm(const float* x, float* out, long n, cudaStream_t s) {
   if (n == 0) return 0;  // (the kernel handles the n % 4 tail)
   lb::sqnorm_kernel<<<ew_grid(n / 4, 256), 256, 0, s>>>(x, out, (size_t)n);
+  return (int)cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp8 (E4M3) per-tensor quantisation for the fp8 forward GEMM: amax pass + cast pass, no host synchronisation
+//   amax : max |x| over the tensor (atomicMax on the bit pattern: non-negative floats order like unsigned ints)
+//   cast : q = sat_e4m3(x * 448 / amax); deq[0] = amax / 448
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void amax_bf16_kernel(const uint4* __restrict__ x, long n8, const __nv_bfloat16* __restrict__ tail, int ntail,
+                                 unsigned* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    const uint4 v = x[i];
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // |bf16| pairs: clear both sign bits, the larger half decides
+      const unsigned a = w[j] & 0x7FFF7FFFu;
+      m = fmaxf(m, __uint_as_float(a << 16));
+      m = fmaxf(m, __uint_as_float(a & 0xFFFF0000u));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < ntail) m = fmaxf(m, fabsf(__bfloat162float(tail[threadIdx.x])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+}
+
+__global__ void quant_e4m3_kernel(const uint4* __restrict__ x, long n8, const __nv_bfloat16* __restrict__ tail, int ntail,
+                                  const unsigned* __restrict__ amax_bits, uint2* __restrict__ q, uint8_t* __restrict__ qtail,
+                                  float* __restrict__ deq) {
+  const float amax = fmaxf(__uint_as_float(*amax_bits), 1e-12f);
+  const float scale = 448.0f / amax;
+  if (blockIdx.x == 0 && threadIdx.x == 0) deq[0] = amax / 448.0f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    const uint4 v = x[i];
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    unsigned short h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = make_float2(__uint_as_float(w[j] << 16) * scale, __uint_as_float(w[j] & 0xFFFF0000u) * scale);
+      h[j] = __nv_cvt_float2_to_fp8x2(f, __NV_SATFINITE, __NV_E4M3);
+    }
+    q[i] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < ntail)
+    qtail[threadIdx.x] = __nv_cvt_float_to_fp8(__bfloat162float(tail[threadIdx.x]) * scale, __NV_SATFINITE, __NV_E4M3);
+}
+}  // namespace
+
+// x: bf16 [n] (16-byte aligned), q: e4m3 bytes [n] (8-byte aligned), amax_scratch: one zero-initialised-by-us uint32,
+// deq: one float (the dequantisation scale).
+extern "C" int lb_quant_e4m3(const void* x, void* q, void* amax_scratch, float* deq, long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(q) & 7)) return -1;
+  const long n8 = n / 8;
+  const int ntail = (int)(n - n8 * 8);
+  const __nv_bfloat16* tail = reinterpret_cast<const __nv_bfloat16*>(x) + n8 * 8;
+  cudaMemsetAsync(amax_scratch, 0, sizeof(unsigned), s);
+  long blocks = (n8 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  amax_bf16_kernel<<<(int)blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(x), n8, tail, ntail,
+                                              reinterpret_cast<unsigned*>(amax_scratch));
+  quant_e4m3_kernel<<<(int)blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(x), n8, tail, ntail,
+                                               reinterpret_cast<const unsigned*>(amax_scratch),
+                                               reinterpret_cast<uint2*>(q), reinterpret_cast<uint8_t*>(q) + n8 * 8, deq);
   return (int)cudaGetLastError();
 }

@@ -41,6 +41,13 @@ struct GemmParams {
   const __nv_bfloat16* pre_in;  // optional [M, ldo]: out = acc * act'(pre_in)  (dgrad fused with the activation backward)
   int ldo;                    // leading dimension of out (elements)
   int rmw;                    // EPI_F32: out += acc (plain read-modify-write; a tile is owned by one CTA)
+  // fp8 (E4M3) operands, K-major only.  The byte layout of a [rows, K] e4m3 matrix equals that of a [rows, K/2] bf16
+  // matrix, so the TMA maps, the 128-byte swizzle rows and the 32-byte descriptor advance per MMA are unchanged (K
+  // above is in bf16-equivalent units = bytes / 2); only the MMA kind (kind::f8f6f4, 32 elements of K per instruction)
+  // and the dequantisation scale in the epilogue differ.
+  int fp8;
+  const float* deq_a;         // per-tensor dequantisation scales (device scalars): out = acc * deq_a[0] * deq_b[0]
+  const float* deq_b;
 };
 
 // Fused collective modes (tensor parallel): peer pointers refer to NVLink peer-mapped symmetric memory.
@@ -327,7 +334,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp_idx == 1) {
     // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    const bool fp8 = p.fp8 != 0;
+    const uint32_t idesc = fp8 ? make_idesc_e4m3(BLOCK_M, BLOCK_N) : make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -354,7 +362,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                      : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 0, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                      : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 0, 1024);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (fp8) umma_f8_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);   // accumulator complete
@@ -377,6 +386,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr int CHUNKS_PER_HALF = BLOCK_N / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const float alpha = p.fp8 ? __ldg(p.deq_a) * __ldg(p.deq_b) : 1.0f;
     for (int tile = cta; tile < num_tiles; tile += cta_stride) {
       const int mn = tile / p.k_splits;
       const int m_blk = map_m(mn / n_blocks), n_blk = mn % n_blocks;
@@ -422,6 +432,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.fp8) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= alpha;
+          }
           if (use_bias) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -720,7 +734,8 @@ static bool wgrad_rmw() {
 
 static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo, int layout,
                      int epi, const void* bias, int act, void* pre_out, const void* pre_in, int force_bn,
-                     int force_splits, const lb::CommParams& cp, cudaStream_t stream) {
+                     int force_splits, const lb::CommParams& cp, cudaStream_t stream, const float* deq_a = nullptr,
+                     const float* deq_b = nullptr) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (N % 8) || (ldo % 4)) return -1;
   const bool a_mn = (layout == 2);
@@ -797,6 +812,9 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   p.pre_out = reinterpret_cast<__nv_bfloat16*>(pre_out);
   p.pre_in = reinterpret_cast<const __nv_bfloat16*>(pre_in);
   p.ldo = ldo;
+  p.fp8 = (deq_a != nullptr && deq_b != nullptr) ? 1 : 0;
+  p.deq_a = deq_a;
+  p.deq_b = deq_b;
 
   CUtensorMap ta, tb;
   if (!operand_tmap(&ta, a, a_mn, M, K, lda, lb::BLOCK_M)) return -2;
@@ -832,6 +850,23 @@ extern "C" int lb_gemm_bf16(const void* a, const void* b, void* out, int M, int 
   memset(&cp, 0, sizeof(cp));
   return gemm_impl(a, b, out, M, N, K, lda, ldb, ldo, layout, epi, bias, act, pre_out, nullptr, force_bn, force_splits, cp,
                    stream);
+}
+
+// fp8 forward GEMM: y[M,N] (bf16) = act((xq[M,K] · wq[N,K]ᵀ) * deq_x * deq_w + bias); xq / wq hold E4M3 bytes, K % 16 == 0.
+// The operands are handed to the kernel as bf16 matrices with K/2 columns (identical bytes, see GemmParams::fp8).
+// With `residual` ([M, N] bf16) the epilogue is bias + residual add instead of an activation.
+extern "C" int lb_gemm_fp8(const void* xq, const void* wq, void* out, int M, int N, int K, const void* bias, int act,
+                           void* pre_out, const void* residual, const float* deq_x, const float* deq_w,
+                           cudaStream_t stream) {
+  if ((K % 16) != 0 || deq_x == nullptr || deq_w == nullptr) return -7;
+  lb::CommParams cp;
+  memset(&cp, 0, sizeof(cp));
+  if (residual != nullptr) {
+    act = lb::ACT_RESADD;
+    pre_out = nullptr;
+  }
+  return gemm_impl(xq, wq, out, M, N, K / 2, K / 2, K / 2, N, 0, 0, bias, act, pre_out, residual, 0, 0, cp, stream, deq_x,
+                   deq_w);
 }
 
 // dgrad fused with the activation backward: out[M,N] = (A·B) * act'(pre_in[M,N])   (bf16 output, ldo = row stride

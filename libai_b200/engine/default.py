@@ -195,6 +195,10 @@ class DefaultTrainer(TrainerBase):
         )
         # NEW: replay the transformer blocks from CUDA graphs (engine/cuda_graphs.py); captured at the first step
         self._trainer.cuda_graphs = bool(try_get_key(cfg, "train.cuda_graphs.enabled", default=False))
+        if try_get_key(cfg, "train.fp8.enabled", default=False):
+            from libai_b200 import ops
+
+            ops.set_fp8(True)   # NEW: E4M3 forward GEMMs (ops/functional.py:_linear_fwd_any)
         extra = {"loss_scaler": self.loss_scaler} if self.loss_scaler is not None else {}
         self.checkpointer = Checkpointer(
             self.model, cfg.train.output_dir, optimizer=self.optimizer, lr_scheduler=self.lr_scheduler, **extra

@@ -102,3 +102,32 @@ def launch_count() -> int:
 def reset_launch_count() -> None:
     global _LAUNCH_COUNT
     _LAUNCH_COUNT = 0
+
+
+# --------------------------------------------------------------------------------------
+# fp8 (E4M3) forward GEMMs — opt-in (``train.fp8.enabled`` / ``LIBAI_B200_FP8=1``)
+# --------------------------------------------------------------------------------------
+_FP8 = os.environ.get("LIBAI_B200_FP8", "0") == "1"
+_FP8_EPOCH = 0
+
+
+def set_fp8(enabled: bool) -> None:
+    """Run the forward GEMMs of the linear layers with E4M3 operands (per-tensor dynamic scaling, fp32 accumulation
+    in TMEM, bf16 outputs); backward GEMMs stay bf16 on the saved bf16 operands."""
+    global _FP8
+    _FP8 = bool(enabled)
+
+
+def fp8_enabled() -> bool:
+    return _FP8
+
+
+def fp8_weight_epoch() -> int:
+    return _FP8_EPOCH
+
+
+def bump_fp8_weight_epoch() -> None:
+    """Invalidate cached quantised weights (called by the optimizers after they rewrote the parameters in place —
+    the native update kernels do not bump ``Tensor._version``)."""
+    global _FP8_EPOCH
+    _FP8_EPOCH += 1

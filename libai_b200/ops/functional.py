@@ -19,6 +19,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import count_launch, load_ext, use_native
+from .. import ops
 
 # --------------------------------------------------------------------------------------
 # activations (reference math)
@@ -73,6 +74,43 @@ def _gemm_ok(x: torch.Tensor, w: torch.Tensor) -> bool:
 
 
 
+_FP8_WEIGHTS: dict = {}
+
+
+def _fp8_ok(x2: torch.Tensor, w: torch.Tensor) -> bool:
+    return ops.fp8_enabled() and x2.shape[-1] % 16 == 0 and w.is_contiguous()
+
+
+def _fp8_weight(ext, w):
+    """E4M3 copy of a weight + its dequantisation scale, cached until the optimizer rewrites the parameters
+    (``ops.bump_fp8_weight_epoch``) or the tensor is modified through PyTorch (``_version``).  Inside a CUDA-graph
+    capture the quantisation is always issued (and captured): a cached tensor would pin stale addresses."""
+    if torch.cuda.is_current_stream_capturing():
+        count_launch(2)
+        return ext.quantize_e4m3(w.detach())
+    key = (ops.fp8_weight_epoch(), w._version, w.data_ptr())
+    hit = _FP8_WEIGHTS.get(id(w))
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    wq, dw = ext.quantize_e4m3(w.detach())
+    count_launch(2)
+    _FP8_WEIGHTS[id(w)] = (key, wq, dw)
+    return wq, dw
+
+
+def _linear_fwd_any(ext, x2, w, bias, act_id, need_pre, residual=None):
+    """Forward GEMM of a linear layer: E4M3 operands when the fp8 path is on, bf16 otherwise."""
+    if _fp8_ok(x2, w):
+        xq, dx = ext.quantize_e4m3(x2)
+        wq, dw = _fp8_weight(ext, w)
+        count_launch(3)
+        return ext.linear_fp8_fwd(xq, wq, dx, dw, bias, act_id, need_pre, residual)
+    count_launch()
+    if residual is not None:
+        return ext.linear_bias_residual(x2, w, bias, residual), None
+    return ext.linear_fwd(x2, w, bias, act_id, need_pre)
+
+
 def _bias_grad(ext, g2, bias):
     """Column sums of ``g2`` as the gradient of ``bias``: accumulated straight into ``bias.main_grad`` (fp32 slice of
     the optimizer's flat gradient buffer) when the parameter owns one – no temporary, no bf16 round trip, no
@@ -98,8 +136,7 @@ class _LinearFn(torch.autograd.Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         need_pre = act not in (None, "none") and (x.requires_grad or w.requires_grad)
-        y, pre = ext.linear_fwd(x2, w, bias, _ACT_IDS[act], need_pre)
-        count_launch()
+        y, pre = _linear_fwd_any(ext, x2, w, bias, _ACT_IDS[act], need_pre)
         ctx.act = act
         ctx.has_bias = bias is not None
         ctx.bias_param = bias
@@ -156,13 +193,10 @@ class _MLPFn(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        h, pre = ext.linear_fwd(x2, w1, b1, _ACT_IDS[act], True)
-        if residual is not None:
-            # second bias and the block's residual add ride in the epilogue of the second GEMM
-            y = ext.linear_bias_residual(h, w2, b2, residual.reshape(-1, w2.shape[0]).contiguous())
-        else:
-            y, _ = ext.linear_fwd(h, w2, b2, 0, False)
-        count_launch(2)
+        h, pre = _linear_fwd_any(ext, x2, w1, b1, _ACT_IDS[act], True)
+        # with a residual, the second bias and the block's residual add ride in the epilogue of the second GEMM
+        res2 = residual.reshape(-1, w2.shape[0]).contiguous() if residual is not None else None
+        y, _ = _linear_fwd_any(ext, h, w2, b2, 0, False, res2)
         ctx.act = act
         ctx.save_for_backward(x2, w1, w2, pre, h)
         ctx.x_shape = x.shape
@@ -226,8 +260,7 @@ class _LinearResidualFn(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        y = ext.linear_bias_residual(x2, w, bias, residual.reshape(-1, w.shape[0]).contiguous())
-        count_launch()
+        y, _ = _linear_fwd_any(ext, x2, w, bias, 0, False, residual.reshape(-1, w.shape[0]).contiguous())
         ctx.bias_param = bias
         ctx.save_for_backward(x2, w)
         ctx.x_shape = x.shape

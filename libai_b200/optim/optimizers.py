@@ -27,6 +27,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.distributed as dist
 
+from libai_b200 import ops
 from libai_b200.ops import count_launch, load_ext, use_native
 from libai_b200.ops import impl as ops_impl
 from libai_b200.parallel import state as pstate
@@ -398,6 +399,7 @@ class FlatOptimizer(torch.optim.Optimizer):
             self.found_inf = False
             return None
         self._step_count += 1
+        ops.bump_fp8_weight_epoch()     # parameters are rewritten in place: cached E4M3 weight copies are stale
         topo = dutil.get_dist_util()
         for g, fg in zip(self.param_groups, self._groups):
             if fg is None:
@@ -473,6 +475,7 @@ class FlatOptimizer(torch.optim.Optimizer):
 
     def load_state_dict(self, sd):
         self.setup()
+        ops.bump_fp8_weight_epoch()
         self._step_count = int(sd.get("step", 0))
         for g, saved in zip(self.param_groups, sd.get("param_groups", [])):
             for k, v in saved.items():

@@ -251,6 +251,49 @@ def main():
 
     record("embedding gather / scatter-add", embedding_native)
 
+    def fp8_forward_gemm():
+        """E4M3 forward GEMM (tcgen05 kind::f8f6f4): exact against an fp32 matmul of the *dequantised* operands (the
+        only error left is the bf16 rounding of the output), close to the bf16 GEMM, plus quantiser checks and timing."""
+        e = {}
+        x = torch.randn(777, 1040, device="cuda").bfloat16() * 3
+        xq, dx = ext.quantize_e4m3(x)
+        amax = x.float().abs().max()
+        e["deq_scale"] = abs(float(dx) * 448 / float(amax) - 1)
+        e["quant_vs_torch"] = rel_err(xq.float() * dx, (x.float() * (448 / amax)).to(torch.float8_e4m3fn).float() * dx)
+        e["quant_roundtrip"] = rel_err(xq.float() * dx, x)              # e4m3: 3 mantissa bits -> a few percent
+        odd = torch.randn(1003, device="cuda").bfloat16()               # tail path (n % 8 != 0)
+        oq, do = ext.quantize_e4m3(odd)
+        e["quant_tail"] = rel_err(oq.float() * do, (odd.float() * (448 / odd.float().abs().max())).to(torch.float8_e4m3fn).float() * do)
+        res = {}
+        for (M, N, K) in [(777, 520, 1040), (8192, 3072, 1024), (8192, 4096, 1024), (8192, 1024, 4096)]:
+            x = torch.randn(M, K, device="cuda").bfloat16()
+            w = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+            b = torch.randn(N, device="cuda").bfloat16()
+            r = torch.randn(M, N, device="cuda").bfloat16()
+            xq, dx = ext.quantize_e4m3(x)
+            wq, dw = ext.quantize_e4m3(w)
+            ref = (xq.float() * dx) @ (wq.float() * dw).t()
+            y, _ = ext.linear_fp8_fwd(xq, wq, dx, dw, None, 0, False, None)
+            e[f"{M}x{N}x{K}"] = rel_err(y, ref)
+            yb, pre = ext.linear_fp8_fwd(xq, wq, dx, dw, b, 1, True, None)     # bias + GELU, pre-activation copy
+            e[f"{M}x{N}x{K}_bias_gelu"] = max(rel_err(pre, ref + b.float()), rel_err(yb, torch.nn.functional.gelu(ref + b.float())))
+            yr, _ = ext.linear_fp8_fwd(xq, wq, dx, dw, b, 0, False, r)
+            e[f"{M}x{N}x{K}_residual"] = rel_err(yr, ref + b.float() + r.float())
+            e[f"{M}x{N}x{K}_vs_bf16_gemm"] = rel_err(y, x.float() @ w.float().t())
+            if M >= 8192:
+                flops = 2.0 * M * N * K
+                ms8 = timeit(lambda: ext.linear_fp8_fwd(xq, wq, dx, dw, None, 0, False, None))
+                ms16 = timeit(lambda: ext.linear_fwd(x, w, None, 0, False))
+                msq = timeit(lambda: ext.quantize_e4m3(x))
+                res[f"{M}x{N}x{K}"] = {"fp8_ms": ms8, "fp8_pflops": flops / ms8 / 1e12, "bf16_ms": ms16,
+                                       "bf16_pflops": flops / ms16 / 1e12, "quantize_x_ms": msq}
+        exact = [v for k, v in e.items() if "x" in k and "vs_bf16" not in k and not k.startswith("quant")]
+        ok = (max(exact) < 1e-2 and e["deq_scale"] < 1e-5 and e["quant_vs_torch"] < 1e-6 and e["quant_tail"] < 1e-6
+              and e["quant_roundtrip"] < 0.06 and all(v < 0.08 for k, v in e.items() if "vs_bf16" in k))
+        return {"ok": ok, "errs": e, "timing": res}
+
+    record("fp8 forward GEMM", fp8_forward_gemm)
+
     # ------------------------------------------------------------------ norms
     for rms in (False, True):
         for H in (1024, 768, 4096, 200):

@@ -134,6 +134,55 @@ def test_cuda_graph_blocks_match_eager():
     assert abs(n_graph - n_eager) <= 0.1 * n_eager, (n_eager, n_graph)     # replayed kernels are still counted
 
 
+def test_fp8_forward_gemms_train_like_bf16():
+    """``ops.set_fp8(True)``: the linear layers' forward GEMMs take E4M3 operands (quantise + tcgen05 kind::f8f6f4
+    kernel); losses track the bf16 run, eagerly (cached weight copies refreshed per optimizer step) and under CUDA
+    graphs (quantisation captured)."""
+    from libai_b200 import ops
+    from libai_b200.config import DictConfig
+    from libai_b200.engine.cuda_graphs import enable_for_model
+    from libai_b200.layers._param import param_defaults
+    from libai_b200.models import GPTForPreTraining
+    from libai_b200.optim import AdamW, get_default_optimizer_params
+    from libai_b200.utils import distributed as dutil
+
+    os.environ["LIBAI_B200_IMPL"] = "native"
+    cfg = DictConfig(dict(
+        hidden_layers=2, vocab_size=512, hidden_size=256, ffn_hidden_size=1024, num_attention_heads=4, max_seq_length=256,
+        embedding_dropout_prob=0.0, attention_dropout_prob=0.0, output_dropout_prob=0.0, layernorm_epsilon=1e-5,
+        initializer_range=0.02, use_scaled_init_for_output_weights=True, bias_gelu_fusion=True, bias_dropout_fusion=True,
+        scale_mask_softmax_fusion=True, apply_query_key_layer_scaling=False, apply_residual_post_layernorm=False,
+        amp_enabled=True))
+    runs = {}
+    try:
+        for mode in ("bf16", "fp8", "fp8+graphs"):
+            ops.set_fp8(mode != "bf16")
+            dutil.reset_dist_util()
+            dutil.setup_dist_util(DictConfig(dict(data_parallel_size=1, tensor_parallel_size=1, pipeline_parallel_size=1)))
+            with param_defaults(dtype=torch.bfloat16, device="cuda", seed=3):
+                model = GPTForPreTraining(cfg).train()
+            opt = AdamW(get_default_optimizer_params(model, clip_grad_max_norm=1.0, clip_grad_norm_type=2.0), lr=1e-3)
+            opt.configure(param_names={id(p): n for n, p in model.named_parameters()})
+            opt.setup()
+            g = torch.Generator(device="cuda").manual_seed(7)
+            batches = [torch.randint(0, 512, (4, 256), device="cuda", generator=g) for _ in range(6)]
+            if mode.endswith("graphs"):
+                assert enable_for_model(model, dict(input_ids=batches[0], labels=batches[0]))
+            losses = []
+            for ids in batches:
+                opt.zero_grad()
+                loss = model(ids, ids)["lm_loss"]
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+            runs[mode] = losses
+    finally:
+        ops.set_fp8(False)
+    assert all(abs(a - b) < 5e-2 for a, b in zip(runs["bf16"], runs["fp8"])), runs
+    assert all(abs(a - b) < 2e-2 for a, b in zip(runs["fp8"], runs["fp8+graphs"])), runs
+    assert runs["fp8"][-1] < runs["fp8"][0] and runs["fp8"] != runs["bf16"]
+
+
 def test_smoke_entry_point():
     sys.path.insert(0, REPO)
     import __graft_entry__
