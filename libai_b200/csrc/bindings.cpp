@@ -190,7 +190,7 @@ std::tuple<Tensor, Tensor> quantize_e4m3(const Tensor& x) {
   TORCH_CHECK(x.is_cuda() && x.is_contiguous() && x.scalar_type() == at::kBFloat16, "quantize_e4m3: contiguous bf16 CUDA tensor");
   c10::cuda::CUDAGuard guard(x.device());
   Tensor q = at::empty(x.sizes(), x.options().dtype(at::kFloat8_e4m3fn));
-  Tensor scratch = at::empty({2}, x.options().dtype(at::kFloat));   // [0] = dequantisation scale, [1] = amax bits
+  Tensor scratch = at::zeros({2}, x.options().dtype(at::kFloat));   // [0] = dequantisation scale, [1] = amax bits (zeroed)
   check(lb_quant_e4m3(x.data_ptr(), q.data_ptr(), scratch.data_ptr<float>() + 1, scratch.data_ptr<float>(), (long)x.numel(),
                       cur_stream()),
         "quantize_e4m3");

@@ -628,7 +628,8 @@ __global__ void quant_e4m3_kernel(const uint4* __restrict__ x, long n8, const __
 }
 }  // namespace
 
-// x: bf16 [n] (16-byte aligned), q: e4m3 bytes [n] (8-byte aligned), amax_scratch: one zero-initialised-by-us uint32,
+// x: bf16 [n] (16-byte aligned), q: e4m3 bytes [n] (8-byte aligned), amax_scratch: one uint32 the caller has zeroed
+// (a kernel-node fill rather than a memset node keeps captured graphs homogeneous),
 // deq: one float (the dequantisation scale).
 extern "C" int lb_quant_e4m3(const void* x, void* q, void* amax_scratch, float* deq, long n, cudaStream_t s) {
   if (n <= 0) return 0;
@@ -636,7 +637,6 @@ extern "C" int lb_quant_e4m3(const void* x, void* q, void* amax_scratch, float* 
   const long n8 = n / 8;
   const int ntail = (int)(n - n8 * 8);
   const __nv_bfloat16* tail = reinterpret_cast<const __nv_bfloat16*>(x) + n8 * 8;
-  cudaMemsetAsync(amax_scratch, 0, sizeof(unsigned), s);
   long blocks = (n8 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;

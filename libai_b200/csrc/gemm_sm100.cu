@@ -146,7 +146,7 @@ LB_DEVICE void stg_store_chunk(uint8_t* stg, int lane, const float (&v)[32], __n
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool FP8 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p,
             CommParams cp) {
@@ -334,8 +334,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp_idx == 1) {
     // ======================= MMA issuer =======================
-    const bool fp8 = p.fp8 != 0;
-    const uint32_t idesc = fp8 ? make_idesc_e4m3(BLOCK_M, BLOCK_N) : make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    // (FP8 is a template parameter so the bf16 instantiations carry no trace of it)
+    constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(BLOCK_M, BLOCK_N) : make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -362,7 +362,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                      : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 0, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                      : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 0, 1024);
-            if (fp8) umma_f8_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (FP8) umma_f8_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
@@ -386,7 +386,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr int CHUNKS_PER_HALF = BLOCK_N / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const float alpha = p.fp8 ? __ldg(p.deq_a) * __ldg(p.deq_b) : 1.0f;
+    float alpha = 1.0f;
+    if constexpr (FP8) alpha = __ldg(p.deq_a) * __ldg(p.deq_b);
     for (int tile = cta; tile < num_tiles; tile += cta_stride) {
       const int mn = tile / p.k_splits;
       const int m_blk = map_m(mn / n_blocks), n_blk = mn % n_blocks;
@@ -432,7 +433,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (p.fp8) {
+          if constexpr (FP8) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= alpha;
           }
@@ -688,11 +689,11 @@ bool operand_tmap(CUtensorMap* m, const void* ptr, bool mn_major, int rows_or_co
   return lb_host::make_tmap_bf16(m, ptr, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN, bool AMN, bool BMN, int EPI>
+template <int BN, bool AMN, bool BMN, int EPI, bool FP8 = false>
 cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const lb::GemmParams& p, const lb::CommParams& cp,
                        int grid, cudaStream_t stream) {
   using Cfg = lb::StageCfg<BN>;
-  auto kern = lb::gemm_kernel<BN, AMN, BMN, EPI>;
+  auto kern = lb::gemm_kernel<BN, AMN, BMN, EPI, FP8>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -703,18 +704,18 @@ cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const lb::G
   return cudaGetLastError();
 }
 
-template <bool AMN, bool BMN, int EPI>
+template <bool AMN, bool BMN, int EPI, bool FP8 = false>
 cudaError_t launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const lb::GemmParams& p,
                       const lb::CommParams& cp, int grid, cudaStream_t s) {
   switch (bn) {
     case 256:
-      return launch_cfg<256, AMN, BMN, EPI>(ta, tb, p, cp, grid, s);
+      return launch_cfg<256, AMN, BMN, EPI, FP8>(ta, tb, p, cp, grid, s);
     case 192:
-      return launch_cfg<192, AMN, BMN, EPI>(ta, tb, p, cp, grid, s);
+      return launch_cfg<192, AMN, BMN, EPI, FP8>(ta, tb, p, cp, grid, s);
     case 128:
-      return launch_cfg<128, AMN, BMN, EPI>(ta, tb, p, cp, grid, s);
+      return launch_cfg<128, AMN, BMN, EPI, FP8>(ta, tb, p, cp, grid, s);
     default:
-      return launch_cfg<64, AMN, BMN, EPI>(ta, tb, p, cp, grid, s);
+      return launch_cfg<64, AMN, BMN, EPI, FP8>(ta, tb, p, cp, grid, s);
   }
 }
 
@@ -827,7 +828,10 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   }
 
   cudaError_t e;
-  if (layout == 0) {
+  if (p.fp8) {
+    if (layout != 0 || epi != 0 || cp.mode != lb::COMM_NONE) return -7;
+    e = launch_bn<false, false, lb::EPI_BF16, true>(bn, ta, tb, p, cp, grid, stream);
+  } else if (layout == 0) {
     if (epi == 0) e = launch_bn<false, false, lb::EPI_BF16>(bn, ta, tb, p, cp, grid, stream);
     else if (epi == 1) e = launch_bn<false, false, lb::EPI_F32>(bn, ta, tb, p, cp, grid, stream);
     else e = launch_bn<false, false, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, cp, grid, stream);
