@@ -274,13 +274,15 @@ def main():
     barrier()
     e0.record()
     t_enq = time.perf_counter()
-    nvtx = os.environ.get("LIBAI_B200_NVTX", "0") == "1"   # `ncu --nvtx --nvtx-include "bench_step/"` → exactly the timed steps
+    # `ncu --nvtx --nvtx-include "bench_step"` → exactly the timed steps.  A start/end range (process-wide), not
+    # push/pop (per thread): the backward kernels are launched from the autograd engine's thread.
+    nvtx = os.environ.get("LIBAI_B200_NVTX", "0") == "1"
     for i in range(args.steps):
-        if nvtx:
-            torch.cuda.nvtx.range_push("bench_step")
+        rid = torch.cuda.nvtx.range_start("bench_step") if nvtx else None
         loss = one_step(args.warmup + i)
         if nvtx:
-            torch.cuda.nvtx.range_pop()
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_end(rid)
     e1.record()
     # host time spent ENQUEUEING the timed steps (no sync inside): close to the device time = the step is launch-bound
     enqueue_ms = max_over_ranks((time.perf_counter() - t_enq) * 1e3) / args.steps
