@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--graphs", type=int, default=1,
                     help="1 (default): replay the transformer blocks from CUDA graphs (data-parallel layouts only; "
                          "tensor/pipeline-parallel runs fall back to eager launches)")
+    ap.add_argument("--fused-bias-grad", type=int, default=-1,
+                    help="1/0: bias gradient of the MLP's first linear inside the dgrad epilogue (-1: library default)")
     ap.add_argument("--fp8", type=int, default=0,
                     help="1: forward GEMMs with E4M3 operands (experiment; the headline number is the bf16 default — "
                          "the JSON line then says dtype fp8-fwd/bf16-bwd)")
@@ -236,6 +238,10 @@ def main():
         from libai_b200 import ops as _ops
 
         _ops.set_fp8(True)
+    if args.fused_bias_grad >= 0:
+        from libai_b200 import ops as _ops
+
+        _ops.set_fused_bias_grad(bool(args.fused_bias_grad))
     graphs_on = False
     if args.graphs and topo.pipeline_parallel_size == 1:
         from libai_b200.engine.cuda_graphs import enable_for_model

@@ -25,7 +25,7 @@ int lb_norm_bwd(const void* gy, const void* x, const void* gamma, const float* m
                 int accumulate, const void* gadd, cudaStream_t s);
 int lb_bias_act_fwd(const void* x, const void* bias, void* y, long rows, int N, int act, cudaStream_t s);
 int lb_gemm_bf16_actgrad(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo,
-                         int layout, int act, const void* pre_in, cudaStream_t stream);
+                         int layout, int act, const void* pre_in, float* colsum, cudaStream_t stream);
 int lb_bias_act_bwd(const void* gy, const void* x, const void* bias, void* gx, long rows, int N, int act,
                     cudaStream_t s);
 int lb_bias_residual(const void* x, const void* bias, const void* res, void* y, long rows, int N, cudaStream_t s);
@@ -125,7 +125,9 @@ Tensor gemm(const Tensor& a, const Tensor& b, int64_t layout, const c10::optiona
 
 // dpre = (gy @ w) * act'(pre): the dgrad GEMM of the layer that consumed act(pre), with the activation backward
 // applied in its epilogue (gy [M,N], w [N,K] row-major, pre [M,K]).
-Tensor dgrad_actgrad(const Tensor& gy, const Tensor& w, const Tensor& pre, int64_t act) {
+// With `bias_grad` (fp32 [N], e.g. the bias' slice of main_grad) the column sums of the result are accumulated into it
+// by the GEMM epilogue.
+Tensor dgrad_actgrad(const Tensor& gy, const Tensor& w, const Tensor& pre, int64_t act, const c10::optional<Tensor>& bias_grad) {
   TORCH_CHECK(gy.is_cuda() && gy.dim() == 2 && w.dim() == 2 && pre.dim() == 2, "dgrad_actgrad: 2-D CUDA tensors");
   TORCH_CHECK(gy.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && pre.scalar_type() == at::kBFloat16,
               "dgrad_actgrad: bf16 expected");
@@ -134,8 +136,14 @@ Tensor dgrad_actgrad(const Tensor& gy, const Tensor& w, const Tensor& pre, int64
   TORCH_CHECK(w.size(0) == K && pre.size(0) == M && pre.size(1) == N, "dgrad_actgrad: shape mismatch");
   c10::cuda::CUDAGuard guard(gy.device());
   Tensor out = at::empty({M, N}, gy.options());
+  float* colsum = nullptr;
+  if (bias_grad.has_value() && bias_grad->defined()) {
+    TORCH_CHECK(bias_grad->scalar_type() == at::kFloat && bias_grad->is_contiguous() && bias_grad->numel() == N && bias_grad->is_cuda(),
+                "dgrad_actgrad: bias_grad must be a contiguous fp32 CUDA tensor [N]");
+    colsum = bias_grad->data_ptr<float>();
+  }
   check(lb_gemm_bf16_actgrad(gy.data_ptr(), w.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, (int)gy.stride(0),
-                             (int)w.stride(0), (int)N, 1, (int)act, pre.data_ptr(), cur_stream()),
+                             (int)w.stride(0), (int)N, 1, (int)act, pre.data_ptr(), colsum, cur_stream()),
         "dgrad_actgrad");
   return out;
 }
@@ -603,7 +611,7 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("bias_residual_fwd(Tensor x, Tensor? bias, Tensor? res) -> Tensor", &bias_residual_fwd);
   m.def("swiglu_fwd(Tensor gate, Tensor up) -> Tensor", &swiglu_fwd);
   m.def("swiglu_bwd(Tensor gy, Tensor gate, Tensor up) -> (Tensor, Tensor)", &swiglu_bwd);
-  m.def("dgrad_actgrad(Tensor gy, Tensor w, Tensor pre, int act) -> Tensor", &dgrad_actgrad);
+  m.def("dgrad_actgrad(Tensor gy, Tensor w, Tensor pre, int act, Tensor(a!)? bias_grad=None) -> Tensor", &dgrad_actgrad);
   m.def("rope(Tensor x, Tensor cos, Tensor sin, bool backward) -> Tensor", &rope);
   m.def("rope_qkv(Tensor(a!) qkv, Tensor cos, Tensor sin, int pos_offset, bool backward, bool inplace) -> Tensor(a!)", &rope_qkv);
   m.def("ce_stats(Tensor logits, Tensor labels, int vocab_start) -> (Tensor, Tensor, Tensor)", &ce_stats);

@@ -45,6 +45,9 @@ struct GemmParams {
   // matrix, so the TMA maps, the 128-byte swizzle rows and the 32-byte descriptor advance per MMA are unchanged (K
   // above is in bf16-equivalent units = bytes / 2); only the MMA kind (kind::f8f6f4, 32 elements of K per instruction)
   // and the dequantisation scale in the epilogue differ.
+  // optional fp32 [N] vector receiving the column sums of the bf16 output (`red.add`): the bias gradient of the layer
+  // whose output gradient this GEMM produces (dgrad fused with the activation backward), without a second pass
+  float* colsum;
   int fp8;
   const float* deq_a;         // per-tensor dequantisation scales (device scalars): out = acc * deq_a[0] * deq_b[0]
   const float* deq_b;
@@ -128,8 +131,11 @@ LB_DEVICE void stg_quads_to_rows(uint8_t* stg, int lane, const uint4 (&quad)[4],
   __syncwarp();
 }
 // store a staged chunk: slab = pointer to (first row of this warp's 32-row slab, first column of the chunk)
+// colsum_dst (optional): fp32 pointer to the chunk's first column; receives the sums over the chunk's valid rows of
+// the bf16-rounded values (4 rows in-register, then the 8 lanes that share a 16-byte column slot, then one red.add.v4
+// pair per slot)
 LB_DEVICE void stg_store_chunk(uint8_t* stg, int lane, const float (&v)[32], __nv_bfloat16* slab, size_t ld,
-                               int rows_valid, int cols_valid) {
+                               int rows_valid, int cols_valid, float* colsum_dst = nullptr) {
   uint4 rowv[4], quad[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -142,6 +148,26 @@ LB_DEVICE void stg_store_chunk(uint8_t* stg, int lane, const float (&v)[32], __n
     for (int j = 0; j < 4; ++j) {
       const int rr = 8 * j + (lane >> 2);
       if (rr < rows_valid) *reinterpret_cast<uint4*>(slab + static_cast<size_t>(rr) * ld + sub * 8) = quad[j];
+    }
+  }
+  if (colsum_dst != nullptr) {  // warp-uniform
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (8 * j + (lane >> 2) < rows_valid) {
+        const float2 a = unpack_bf16(quad[j].x), b = unpack_bf16(quad[j].y), c = unpack_bf16(quad[j].z), d = unpack_bf16(quad[j].w);
+        s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y; s[6] += d.x; s[7] += d.y;
+      }
+    }
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
+    }
+    if ((lane >> 2) == 0 && sub * 8 < cols_valid) {
+      float* dst = colsum_dst + sub * 8;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst + 4), "f"(s[4]), "f"(s[5]), "f"(s[6]), "f"(s[7]) : "memory");
     }
   }
 }
@@ -484,7 +510,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             slab = cp.peer_buf[owner] + cp.staging_parity_off + lrow0 * p.N + col0;
             ld = static_cast<size_t>(p.N);
           }
-          stg_store_chunk(stg, lane, v, slab, ld, rows_valid, cols_valid);
+          stg_store_chunk(stg, lane, v, slab, ld, rows_valid, cols_valid,
+                          (p.colsum != nullptr && cp.mode != COMM_RS) ? p.colsum + col0 : nullptr);
         } else {
           // ---- fp32 outputs (wgrad: plain store / read-modify-write into main_grad, or red.add for split-K): the
           // same staging slot, 16 columns (64 B per row) at a time, so every global instruction covers 8 rows x 64
@@ -736,7 +763,7 @@ static bool wgrad_rmw() {
 static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo, int layout,
                      int epi, const void* bias, int act, void* pre_out, const void* pre_in, int force_bn,
                      int force_splits, const lb::CommParams& cp, cudaStream_t stream, const float* deq_a = nullptr,
-                     const float* deq_b = nullptr) {
+                     const float* deq_b = nullptr, float* colsum = nullptr) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (N % 8) || (ldo % 4)) return -1;
   const bool a_mn = (layout == 2);
@@ -813,6 +840,7 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   p.pre_out = reinterpret_cast<__nv_bfloat16*>(pre_out);
   p.pre_in = reinterpret_cast<const __nv_bfloat16*>(pre_in);
   p.ldo = ldo;
+  p.colsum = (epi == 0) ? colsum : nullptr;
   p.fp8 = (deq_a != nullptr && deq_b != nullptr) ? 1 : 0;
   p.deq_a = deq_a;
   p.deq_b = deq_b;
@@ -875,11 +903,15 @@ extern "C" int lb_gemm_fp8(const void* xq, const void* wq, void* out, int M, int
 
 // dgrad fused with the activation backward: out[M,N] = (A·B) * act'(pre_in[M,N])   (bf16 output, ldo = row stride
 // of both `out` and `pre_in`)
+// `colsum` (optional, fp32 [N], 16-byte aligned): += column sums of `out` = the bias gradient of the layer that produced
+// `pre_in`, accumulated by the epilogue (no separate pass over the [M, N] tensor).
 extern "C" int lb_gemm_bf16_actgrad(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb,
-                                    int ldo, int layout, int act, const void* pre_in, cudaStream_t stream) {
+                                    int ldo, int layout, int act, const void* pre_in, float* colsum, cudaStream_t stream) {
   lb::CommParams cp;
   memset(&cp, 0, sizeof(cp));
-  return gemm_impl(a, b, out, M, N, K, lda, ldb, ldo, layout, 0, nullptr, act, nullptr, pre_in, 0, 0, cp, stream);
+  if (colsum != nullptr && (reinterpret_cast<uintptr_t>(colsum) & 15)) return -8;
+  return gemm_impl(a, b, out, M, N, K, lda, ldb, ldo, layout, 0, nullptr, act, nullptr, pre_in, 0, 0, cp, stream, nullptr,
+                   nullptr, colsum);
 }
 
 // y[M,N] = x[M,K]·w[N,K]ᵀ + bias[N] + residual[M,N]   (bias+residual add of the transformer block in the GEMM epilogue;

@@ -232,7 +232,9 @@ class IndexedCachedDataset(IndexedDataset):
         if isinstance(idx, (int, np.integer)):
             self.check_index(idx)
             shape = tuple(int(x) for x in self.sizes[self.dim_offsets[idx] : self.dim_offsets[idx + 1]])
-            start = self.cache_index[int(idx)]
+            start = self.cache_index.get(int(idx))
+            if start is None:          # not prefetched: read through from disk like the lazy dataset
+                return super().__getitem__(idx)
             return self.cache[start : start + int(np.prod(shape))].reshape(shape).copy()
         if isinstance(idx, slice):
             return [self[i] for i in range(*idx.indices(len(self)))]

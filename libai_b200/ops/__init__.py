@@ -131,3 +131,18 @@ def bump_fp8_weight_epoch() -> None:
     the native update kernels do not bump ``Tensor._version``)."""
     global _FP8_EPOCH
     _FP8_EPOCH += 1
+
+
+# --------------------------------------------------------------------------------------
+# bias gradient of the MLP's first linear inside the dgrad epilogue (GEMM column sums via red.add)
+# --------------------------------------------------------------------------------------
+_FUSED_BIAS_GRAD = os.environ.get("LIBAI_B200_FUSED_BIAS_GRAD", "0") == "1"
+
+
+def fused_bias_grad() -> bool:
+    return _FUSED_BIAS_GRAD
+
+
+def set_fused_bias_grad(enabled: bool) -> None:
+    global _FUSED_BIAS_GRAD
+    _FUSED_BIAS_GRAD = bool(enabled)

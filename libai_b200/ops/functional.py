@@ -213,7 +213,15 @@ class _MLPFn(torch.autograd.Function):
         g2 = gy.reshape(-1, gy.shape[-1])
         if not g2.is_contiguous():
             g2 = g2.contiguous()
-        dpre = ext.dgrad_actgrad(g2, w2, pre, _ACT_IDS[ctx.act])
+        # bias gradient of the first linear = column sums of dpre: accumulated into b1.main_grad by the dgrad epilogue
+        # (red.add from the staged chunk) instead of a separate pass over the [tokens, ffn] tensor
+        b1 = ctx.bias_param
+        fused_gb1 = None
+        if ctx.has_bias and ctx.needs_input_grad[2] and ops.fused_bias_grad():
+            mg = getattr(b1, "main_grad", None)
+            if mg is not None and mg.dtype == torch.float32 and mg.is_contiguous():
+                fused_gb1 = mg
+        dpre = ext.dgrad_actgrad(g2, w2, pre, _ACT_IDS[ctx.act], fused_gb1)
         count_launch()
 
         def wgrad(g, inp, w):
@@ -228,7 +236,9 @@ class _MLPFn(torch.autograd.Function):
         gw2 = wgrad(g2, h, w2) if ctx.needs_input_grad[3] else None
         gw1 = wgrad(dpre, x2, w1) if ctx.needs_input_grad[1] else None
         gb1 = None
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if fused_gb1 is not None:
+            b1.grad_added_to_main_grad = True
+        elif ctx.has_bias and ctx.needs_input_grad[2]:
             gb1 = _bias_grad(ext, dpre, ctx.bias_param)
         gx = None
         if ctx.needs_input_grad[0]:

@@ -178,6 +178,56 @@ def main():
 
     record("mlp fused fwd/bwd", mlp_fn)
 
+    def fused_bias_grad():
+        """Bias gradient (column sums of dpre) accumulated by the dgrad+act' epilogue: raw op against a column sum of
+        its own output (incl. ragged M / N and accumulation into a non-zero buffer), then through the MLP autograd node
+        with main_grad parameters against the unfused path."""
+        from libai_b200 import ops
+        from libai_b200.ops import functional as OF
+
+        e = {}
+        for (M, N, K) in [(777, 520, 256), (8192, 4096, 1024)]:
+            g = torch.randn(M, K, device="cuda").bfloat16()
+            w = (torch.randn(K, N, device="cuda") * 0.05).bfloat16()
+            pre = torch.randn(M, N, device="cuda").bfloat16()
+            acc = torch.full((N,), 0.5, device="cuda")
+            out = ext.dgrad_actgrad(g, w, pre, 1, acc)
+            plain = ext.dgrad_actgrad(g, w, pre, 1, None)
+            e[f"out_unchanged_{M}x{N}"] = rel_err(out, plain)
+            e[f"colsum_{M}x{N}"] = rel_err(acc, out.float().sum(0) + 0.5)
+        g = torch.randn(8192, 1024, device="cuda").bfloat16()
+        w = (torch.randn(1024, 4096, device="cuda") * 0.02).bfloat16()
+        pre = torch.randn(8192, 4096, device="cuda").bfloat16()
+        acc = torch.zeros(4096, device="cuda")
+        ms_fused = timeit(lambda: ext.dgrad_actgrad(g, w, pre, 1, acc))
+        ms_plain = timeit(lambda: ext.dgrad_actgrad(g, w, pre, 1, None))
+        out = ext.dgrad_actgrad(g, w, pre, 1, None)
+        ms_colsum = timeit(lambda: ext.colsum(out, acc))
+
+        def run(fused):
+            ops.set_fused_bias_grad(fused)
+            torch.manual_seed(0)
+            x = torch.randn(1024, 512, device="cuda").bfloat16().requires_grad_(True)
+            ps = [torch.nn.Parameter((torch.randn(2048, 512, device="cuda") * 0.05).bfloat16()),
+                  torch.nn.Parameter((torch.randn(2048, device="cuda") * 0.1).bfloat16()),
+                  torch.nn.Parameter((torch.randn(512, 2048, device="cuda") * 0.05).bfloat16())]
+            for p_ in ps:
+                p_.main_grad = torch.zeros(p_.shape, device="cuda")
+            y = OF.mlp(x, ps[0], ps[1], ps[2], "gelu")
+            y.backward(torch.ones_like(y))
+            assert all(p_.grad is None for p_ in ps)
+            return [x.grad] + [p_.main_grad for p_ in ps]
+
+        try:
+            a, b = run(False), run(True)
+        finally:
+            ops.set_fused_bias_grad(False)
+        e["mlp_node"] = max(rel_err(u, v) for u, v in zip(b, a))
+        return {"ok": max(e.values()) < 2e-3, "errs": e, "dgrad_fused_ms": ms_fused, "dgrad_plain_ms": ms_plain,
+                "separate_colsum_ms": ms_colsum}
+
+    record("fused bias grad", fused_bias_grad)
+
     def bias_residual_epilogue():
         """x·Wᵀ + bias + residual in the GEMM epilogue (raw op, autograd op, and inside the fused MLP node)."""
         from libai_b200.ops import functional as OFn
