@@ -87,6 +87,12 @@ def _build(node, recursive: bool):
     return node
 
 
+def instantiate_cfg(cfg: Any, recursive: bool = True):
+    """Instantiate an already-prepared config node (no keyword merging) — the second half of :func:`instantiate`,
+    public because the reference exposes it (libai/config/instantiate.py:164-201)."""
+    return _build(cfg, recursive)
+
+
 def instantiate(cfg, **kwargs: Any) -> Any:
     """Recursively instantiate ``cfg``; extra ``kwargs`` are merged over the top-level record."""
     if cfg is None:

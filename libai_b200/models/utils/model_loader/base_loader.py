@@ -108,6 +108,10 @@ class LoadPretrainedBase:
         return max(candidates, key=score)
 
 
+# name used by the reference for the common base (libai/models/utils/model_loader/base_loader.py:69)
+ModelLoader = LoadPretrainedBase
+
+
 class ModelLoaderLiBai(LoadPretrainedBase):
     """Load a checkpoint written by ``libai_b200.utils.checkpoint.Checkpointer`` (directory with a ``model`` file,
     or the ``model_XXXXXXX`` directory itself, or a single ``torch.save`` file)."""

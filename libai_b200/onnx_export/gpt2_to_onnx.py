@@ -10,8 +10,16 @@ import torch
 from libai_b200.config import LazyConfig
 from libai_b200.models import GPTForPreTraining
 from libai_b200.models.utils.model_loader import GPT2LoaderLiBai
-from libai_b200.onnx_export.export import export_model
+from libai_b200.onnx_export.export import ExportWrapper, export_model
 from libai_b200.utils import distributed as dist
+
+
+class gpt2Graph(ExportWrapper):
+    """The traced callable: ``input_ids -> logits`` (the reference wraps the eager model in an ``nn.Graph`` of the same
+    name, libai/onnx_export/gpt2_to_onnx.py:41-53; here the static graph is whatever the exporter traces)."""
+
+    def __init__(self, eager_model):
+        super().__init__(eager_model, ["input_ids"], "prediction_scores")
 
 
 def get_model(config_file, checkpoint=None):

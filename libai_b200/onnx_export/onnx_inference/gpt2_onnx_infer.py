@@ -6,6 +6,28 @@ import numpy as np
 import torch
 
 
+class OnnxModel:
+    """onnxruntime session over an exported graph; ``forward(list_of_numpy_inputs)`` feeds the graph inputs in order
+    (reference libai/onnx_export/onnx_inference/gpt2_onnx_infer.py:24-55)."""
+
+    def __init__(self, onnx_filename, providers=None, ort_optimize: bool = True):
+        import onnxruntime as ort
+
+        opt = ort.SessionOptions()
+        opt.graph_optimization_level = (ort.GraphOptimizationLevel.ORT_ENABLE_EXTENDED if ort_optimize
+                                        else ort.GraphOptimizationLevel.ORT_DISABLE_ALL)
+        if providers is None:
+            providers = [p for p in ("TensorrtExecutionProvider", "CUDAExecutionProvider", "CPUExecutionProvider")
+                         if p in ort.get_available_providers()]
+        self.sess = ort.InferenceSession(onnx_filename, sess_options=opt, providers=providers)
+
+    def forward(self, input_list):
+        feeds = {spec.name: np.asarray(arr) for spec, arr in zip(self.sess.get_inputs(), input_list)}
+        return self.sess.run([], feeds)
+
+    __call__ = forward
+
+
 class ExportedLM:
     def __init__(self, path):
         self.path = path

@@ -7,8 +7,17 @@ import torch
 from libai_b200.config import LazyConfig
 from libai_b200.models import T5ForPreTraining
 from libai_b200.models.utils.model_loader.base_loader import ModelLoaderLiBai
-from libai_b200.onnx_export.export import export_model
+from libai_b200.onnx_export.export import ExportWrapper, export_model
 from libai_b200.utils import distributed as dist
+
+
+class t5Graph(ExportWrapper):
+    """The traced callable of the T5 export: the five encoder/decoder inputs -> logits (reference
+    libai/onnx_export/t5_to_onnx.py nn.Graph of the same name)."""
+
+    def __init__(self, eager_model):
+        super().__init__(eager_model, ["encoder_input_ids", "decoder_input_ids", "encoder_attn_mask",
+                                       "decoder_attn_mask", "encoder_decoder_attn_mask"], "prediction_scores")
 
 
 def get_model(config_file, checkpoint=None):

@@ -441,3 +441,82 @@ def tton(tensor, local_only=False, ranks=None):
 def convert_to_distributed_default_setting(t):
     """Reference-API shim (distributed.py:434-447): move a tensor to this rank's device."""
     return t.to(get_device()) if isinstance(t, torch.Tensor) else t
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Placement / SBP vocabulary of the reference (libai/utils/distributed.py:317-393), mapped onto the process-group
+# world: a *placement* is "device type + the ranks of the pipeline stage that owns a layer"; an *sbp signature* is the
+# pair of strings (data-parallel axis, tensor-parallel axis) that `DistTensorData` already carries
+# ("split_<dim>" | "broadcast" | "partial_sum").  Code ported from the reference can keep asking these questions.
+# --------------------------------------------------------------------------------------------------------------
+class Placement:
+    """Device type + global ranks of one pipeline stage (the reference's ``flow.placement`` restricted to what LiBai
+    uses it for: "where does layer *i* live")."""
+
+    __slots__ = ("device_type", "ranks", "mesh")
+
+    def __init__(self, device_type: str, ranks):
+        self.device_type = device_type
+        rows = [list(r) if isinstance(r, (list, tuple)) else [r] for r in ranks]
+        self.mesh = tuple(tuple(int(x) for x in row) for row in rows)       # [dp][tp]
+        self.ranks = tuple(x for row in self.mesh for x in row)
+
+    def __contains__(self, rank: int) -> bool:
+        return int(rank) in self.ranks
+
+    @property
+    def is_local(self) -> bool:
+        """True when the calling process belongs to this placement."""
+        return get_rank() in self.ranks
+
+    @property
+    def device(self) -> torch.device:
+        """The calling process' device for tensors of this placement."""
+        if self.device_type == "cuda":
+            return torch.device("cuda", get_local_rank())
+        return torch.device(self.device_type)
+
+    def __eq__(self, other):
+        return isinstance(other, Placement) and (self.device_type, self.ranks) == (other.device_type, other.ranks)
+
+    def __hash__(self):
+        return hash((self.device_type, self.ranks))
+
+    def __repr__(self):
+        return f"Placement(type={self.device_type!r}, ranks={list(self.ranks)})"
+
+
+def get_layer_placement(layer_idx: int, device_type: Optional[str] = None) -> Placement:
+    """Placement of layer ``layer_idx`` (negative indices count from the last layer, ``-1`` = last stage)."""
+    topo = get_dist_util()
+    device_type = topo.device_type if device_type is None else device_type
+    if device_type == "cuda" and not torch.cuda.is_available():
+        device_type = "cpu"
+    return Placement(device_type, topo.get_layer_ranks(layer_idx))
+
+
+def get_nd_sbp(sbp_list):
+    """Trim a 2-entry signature ``[dp_axis, tp_axis]`` to the axes that exist in the current layout: both for dp×tp,
+    the first for pure data parallel, the second for pure tensor parallel, ``["broadcast"]`` on a single device."""
+    assert isinstance(sbp_list, (list, tuple)) and len(sbp_list) == 2, "a 2-D (data, tensor) signature is expected"
+    assert all(isinstance(s, str) and (s in ("broadcast", "partial_sum") or s.startswith("split_")) for s in sbp_list), sbp_list
+    topo = get_dist_util()
+    if topo.is_data_model_parallel():
+        return list(sbp_list)
+    if topo.is_data_parallel():
+        return list(sbp_list[:1])
+    if topo.is_tensor_model_parallel():
+        return list(sbp_list[1:])
+    return ["broadcast"]
+
+
+def get_hidden_sbp():
+    """Signature of the hidden states between blocks: batch-split over data parallel, replicated over tensor parallel
+    (with ``train.dist.sequence_parallel`` the token dimension is additionally sharded over the TP group inside the
+    blocks — see parallel/mappings.py)."""
+    return get_nd_sbp(["split_0", "broadcast"])
+
+
+def same_sbp(lhs_sbp, rhs_sbp) -> bool:
+    assert len(lhs_sbp) == len(rhs_sbp)
+    return all(a == b for a, b in zip(lhs_sbp, rhs_sbp))

@@ -70,11 +70,31 @@ def _boto3():
         raise ImportError("s3:// paths need boto3, which is not installed in this image") from e
 
 
+def s3_request(func):
+    """Decorator for s3 calls: a 404 from the service becomes ``EnvironmentError("file … not found")``
+    (reference libai/utils/file_utils.py:141-157)."""
+    import functools
+
+    @functools.wraps(func)
+    def wrapper(url, *args, **kwargs):
+        try:
+            return func(url, *args, **kwargs)
+        except Exception as exc:  # botocore.exceptions.ClientError when boto3 is present
+            code = getattr(exc, "response", {}).get("Error", {}).get("Code") if hasattr(exc, "response") else None
+            if code is not None and str(code) == "404":
+                raise EnvironmentError(f"file {url} not found") from exc
+            raise
+
+    return wrapper
+
+
+@s3_request
 def s3_etag(url: str):
     bucket, key = split_s3_path(url)
     return _boto3().resource("s3").Object(bucket, key).e_tag
 
 
+@s3_request
 def s3_get(url: str, temp_file) -> None:
     bucket, key = split_s3_path(url)
     _boto3().resource("s3").Bucket(bucket).download_fileobj(key, temp_file)

@@ -89,3 +89,73 @@ def test_cache_helpers(tmp_path):
         cached_path(str(tmp_path / "missing"))
     with pytest.raises(ValueError):
         cached_path("ftp://example.org/x")
+
+
+def test_placement_and_sbp_vocabulary():
+    """reference libai/utils/distributed.py:317-393 (get_layer_placement / get_nd_sbp / get_hidden_sbp / same_sbp)."""
+    from libai_b200.config import DictConfig
+    from libai_b200.utils import distributed as dist
+
+    dist.reset_dist_util()
+    try:
+        dist.setup_dist_util(DictConfig(dict(data_parallel_size=1, tensor_parallel_size=1, pipeline_parallel_size=1,
+                                             pipeline_num_layers=4, device_type="cpu")))
+        p = dist.get_layer_placement(0)
+        assert p.ranks == (0,) and p.mesh == ((0,),) and p.is_local and 0 in p and p.device.type == "cpu"
+        assert dist.get_layer_placement(-1) == p and "ranks=[0]" in repr(p)
+        assert dist.get_nd_sbp(["split_0", "broadcast"]) == ["broadcast"]      # single device: everything replicated
+        assert dist.get_hidden_sbp() == ["broadcast"]
+        assert dist.same_sbp(["split_0", "broadcast"], ["split_0", "broadcast"])
+        assert not dist.same_sbp(["split_0", "broadcast"], ["broadcast", "broadcast"])
+        # layouts (no process groups needed to ask the questions): fake a dp2 x tp2 x pp2 topology object
+        topo = dist.get_dist_util()
+        topo.data_parallel_size, topo.tensor_parallel_size, topo.pipeline_parallel_size = 2, 2, 2
+        topo._layer_stage_ids = [0, 0, 1, 1]
+        assert dist.get_nd_sbp(["split_0", "split_1"]) == ["split_0", "split_1"]
+        assert dist.get_layer_placement(3).mesh == ((4, 5), (6, 7)) and dist.get_layer_placement(0).ranks == (0, 1, 2, 3)
+        assert not dist.get_layer_placement(3).is_local
+        topo.tensor_parallel_size = 1
+        assert dist.get_nd_sbp(["split_0", "split_1"]) == ["split_0"]
+        topo.data_parallel_size, topo.tensor_parallel_size = 1, 2
+        assert dist.get_nd_sbp(["split_0", "split_1"]) == ["split_1"]
+    finally:
+        dist.reset_dist_util()
+
+
+def test_reference_named_helpers_exist_and_work(tmp_path):
+    """Names a reference user imports directly: instantiate_cfg, ModelLoader, s3_request, gpt2Graph / t5Graph."""
+    import torch
+
+    from libai_b200.config import LazyCall
+    from libai_b200.config.instantiate import instantiate_cfg
+    from libai_b200.models.utils.model_loader.base_loader import LoadPretrainedBase, ModelLoader
+    from libai_b200.onnx_export.gpt2_to_onnx import gpt2Graph
+    from libai_b200.onnx_export.t5_to_onnx import t5Graph
+    from libai_b200.utils.file_utils import s3_request
+
+    lin = instantiate_cfg(LazyCall(torch.nn.Linear)(in_features=3, out_features=2))
+    assert isinstance(lin, torch.nn.Linear) and lin.out_features == 2
+    node = LazyCall(dict)(a=LazyCall(torch.nn.ReLU)())
+    assert isinstance(instantiate_cfg(node)["a"], torch.nn.ReLU)
+    assert not isinstance(instantiate_cfg(node, recursive=False)["a"], torch.nn.ReLU)     # children left as configs
+    assert ModelLoader is LoadPretrainedBase
+
+    class NotFound(Exception):
+        response = {"Error": {"Code": "404"}}
+
+    @s3_request
+    def fetch(url):
+        raise NotFound()
+
+    try:
+        fetch("s3://bucket/key")
+        raise AssertionError("expected EnvironmentError")
+    except EnvironmentError as e:
+        assert "s3://bucket/key" in str(e)
+
+    class Toy(torch.nn.Module):
+        def forward(self, input_ids):
+            return {"prediction_scores": input_ids.float() * 2}
+
+    assert torch.equal(gpt2Graph(Toy())(torch.ones(1, 3, dtype=torch.long)), torch.full((1, 3), 2.0))
+    assert t5Graph(Toy()).input_names[0] == "encoder_input_ids"
