@@ -318,7 +318,7 @@ class DefaultTrainer(TrainerBase):
         if try_get_key(cfg.model, "cfg.amp_enabled") is not None:
             cfg.model.cfg.amp_enabled = bool(try_get_key(cfg, "train.amp.enabled", default=False))
         with param_defaults(dtype=cls.param_dtype(cfg), seed=try_get_key(cfg, "train.seed", default=1234)):
-            model = _build_model(cfg.model)
+            model = cls.construct_model(cfg)
         if try_get_key(cfg, "train.activation_checkpoint.enabled", default=False):
             setter = getattr(type(model), "set_activation_checkpoint", None)
             if setter is not None:
@@ -327,6 +327,12 @@ class DefaultTrainer(TrainerBase):
                 if hasattr(m, "activation_checkpoint"):
                     m.activation_checkpoint = True
         return model
+
+    @classmethod
+    def construct_model(cls, cfg):
+        """Instantiate ``cfg.model`` (called under the parameter dtype / seed defaults).  Override to start from a
+        pretrained checkpoint — ``build_model`` still applies the dtype and activation-checkpoint settings."""
+        return _build_model(cfg.model)
 
     @classmethod
     def build_graph(cls, cfg, model, optimizer=None, lr_scheduler=None, is_train=True):

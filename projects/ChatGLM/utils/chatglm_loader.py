@@ -28,3 +28,52 @@ class ChatGLMLoaderLiBai(ModelLoaderLiBai):
     def __init__(self, model, libai_cfg, pretrained_model_path, **kwargs):
         super().__init__(model, libai_cfg, pretrained_model_path, **kwargs)
         self.base_model_prefix_2 = "transformer"
+
+
+class _LoraMixin:
+    """Load the dense checkpoint, wrap the transformer in a :class:`LoraModel`, then (optionally) load adapter weights
+    saved with ``LoraModel.lora_state_dict()`` (reference projects/ChatGLM/utils/chatglm_loader.py:77-150).
+
+    Extra keyword arguments: ``lora_cfg`` (required) and ``lora_pretrained_model_path`` (a ``torch.save``d adapter
+    state dict, or ``None`` for freshly initialised adapters)."""
+
+    def _init_lora(self, kwargs):
+        self.lora_cfg = kwargs.pop("lora_cfg")
+        self.lora_pretrained_model_path = kwargs.pop("lora_pretrained_model_path", None)
+
+    def load(self):
+        import torch
+
+        from projects.ChatGLM.lora.lora_model import LoraModel
+
+        want_info = self.output_loading_info
+        loaded = super().load()
+        model, info = loaded if want_info else (loaded, None)
+        model.transformer = LoraModel(model.transformer, self.lora_cfg, adapter_name="default")
+        lora_info = {"missing_keys": [], "unexpected_keys": [], "mismatched_keys": [], "error_msgs": []}
+        if self.lora_pretrained_model_path is not None:
+            sd = torch.load(self.lora_pretrained_model_path, map_location="cpu", weights_only=True)
+            own = model.transformer.state_dict()
+            for k, v in sd.items():
+                if k not in own:
+                    lora_info["unexpected_keys"].append(k)
+                elif tuple(own[k].shape) != tuple(v.shape):
+                    lora_info["mismatched_keys"].append(k)
+                else:
+                    own[k].copy_(v.to(own[k].dtype))
+            lora_info["missing_keys"] = [k for k in own if "lora_" in k and k not in sd]
+        if want_info:
+            return model, {k: list(info.get(k, [])) + lora_info[k] for k in lora_info}
+        return model
+
+
+class ChatGLMLoraLoaderHuggerFace(_LoraMixin, ChatGLMLoaderHuggerFace):
+    def __init__(self, model, libai_cfg, pretrained_model_path, **kwargs):
+        self._init_lora(kwargs)
+        super().__init__(model, libai_cfg, pretrained_model_path, **kwargs)
+
+
+class ChatGLMLoraLoaderLiBai(_LoraMixin, ChatGLMLoaderLiBai):
+    def __init__(self, model, libai_cfg, pretrained_model_path, **kwargs):
+        self._init_lora(kwargs)
+        super().__init__(model, libai_cfg, pretrained_model_path, **kwargs)

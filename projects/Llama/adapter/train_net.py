@@ -23,6 +23,9 @@ class AdapterTrainer(DefaultTrainer):
         return model.freeze_backbone()
 
 
+LlamaTrainer = AdapterTrainer      # name used by the reference's adapter entry point
+
+
 def main(args):
     cfg = LazyConfig.load(args.config_file)
     cfg = LazyConfig.apply_overrides(cfg, args.opts)

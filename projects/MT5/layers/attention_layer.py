@@ -1,0 +1,2 @@
+"""Import-path shim: the reference keeps this class in its own file (projects/MT5/layers/attention_layer.py); the implementation lives in projects/MT5/mt5_model.py."""
+from projects.MT5.mt5_model import T5Attention as MultiheadAttention  # noqa: F401

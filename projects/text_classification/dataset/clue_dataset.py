@@ -1,5 +1,6 @@
 """CLUE dataset (reference projects/text_classification/dataset/clue_dataset.py)."""
 from .glue_dataset import _TaskDataset
+from .utils import Split  # noqa: F401  (the reference defines the enum in this module)
 from .utils_clue import clue_output_modes, clue_processors
 
 

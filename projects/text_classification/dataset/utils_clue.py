@@ -74,7 +74,27 @@ class WscProcessor(_Json):
         return out
 
 
-clue_processors = {"afqmc": AfqmcProcessor, "tnews": TnewsProcessor, "iflytek": IflytekProcessor, "cmnli": CmnliProcessor,
+class CopaProcessor(_Json):
+    """COPA (CLUE version): every record yields TWO sentence-pair examples, one per choice — for an "effect" question
+    (premise, choice), for a "cause" question (choice, premise).  Labels follow the reference verbatim (reference
+    utils_clue.py:397-441: both examples of a record carry ``1 if label == 0 else 0``)."""
+
+    def _examples(self, rows, set_type):
+        out = []
+        for i, r in enumerate(rows):
+            label = None if set_type == "test" else str(1 if r["label"] == 0 else 0)
+            for j, choice in enumerate((r["choice0"], r["choice1"])):
+                if r["question"] == "effect":
+                    a, b = r["premise"], choice
+                elif r["question"] == "cause":
+                    a, b = choice, r["premise"]
+                else:
+                    raise ValueError(f"unknown question type {r['question']!r}")
+                out.append(InputExample(f"{set_type}-{2 * i + j}", a, b, label))
+        return out
+
+
+clue_processors = {"copa": CopaProcessor, "afqmc": AfqmcProcessor, "tnews": TnewsProcessor, "iflytek": IflytekProcessor, "cmnli": CmnliProcessor,
                    "ocnli": OcnliProcessor, "csl": CslProcessor, "wsc": WscProcessor}
 clue_output_modes = {k: "classification" for k in clue_processors}
 clue_tasks_num_labels = {k: len(v().get_labels()) for k, v in clue_processors.items()}

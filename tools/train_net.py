@@ -27,7 +27,8 @@ from libai_b200.utils.checkpoint import Checkpointer  # noqa: E402
 logger = logging.getLogger("libai_b200." + __name__)
 
 
-def main(args):
+def main(args, trainer_cls=DefaultTrainer):
+    """``trainer_cls``: a ``DefaultTrainer`` subclass (projects override ``build_model`` & co. and reuse this entry point)."""
     cfg = LazyConfig.load(args.config_file)
     cfg = LazyConfig.apply_overrides(cfg, args.opts)
     default_setup(cfg, args)
@@ -46,16 +47,16 @@ def main(args):
     if args.eval_only:
         tokenizer = None
         if try_get_key(cfg, "tokenization") is not None:
-            tokenizer = DefaultTrainer.build_tokenizer(cfg)
-        model = DefaultTrainer.build_model(cfg)
+            tokenizer = trainer_cls.build_tokenizer(cfg)
+        model = trainer_cls.build_model(cfg)
         Checkpointer(model, save_dir=cfg.train.output_dir).resume_or_load(cfg.train.load_weight, resume=args.resume)
-        test_loader = DefaultTrainer.build_test_loader(cfg, tokenizer)
+        test_loader = trainer_cls.build_test_loader(cfg, tokenizer)
         if len(test_loader) == 0:
             logger.info("No dataset in dataloader.test, please set dataset for dataloader.test")
-        _ = DefaultTrainer.test(cfg, test_loader, model)
+        _ = trainer_cls.test(cfg, test_loader, model)
         return
 
-    trainer = DefaultTrainer(cfg)
+    trainer = trainer_cls(cfg)
     return trainer.train()
 
 
