@@ -42,6 +42,28 @@ def rotary_tables(rotary_dim: int, seq_len: int, base: float = 10000.0, device=N
     return emb.cos().contiguous(), emb.sin().contiguous()
 
 
+class RotaryEmbedding(nn.Module):
+    """``cos, sin = rope(x, seq_len)`` — fp32 tables ``[seq_len, dim]`` on ``x``'s device, cached up to the longest
+    length requested (reference projects/Llama/llama.py:46-63 returns slices of tables the model owns; the attention
+    layers here call :func:`rotary_tables` through the same cache)."""
+
+    def __init__(self, dim, max_position_embeddings=2048, base: float = 10000.0):
+        super().__init__()
+        self.dim, self.max_position_embeddings, self.base = dim, max_position_embeddings, base
+        self._cache = None
+
+    def forward(self, x, seq_len=None, cos_cached=None, sin_cached=None):
+        seq_len = x.shape[-2] if seq_len is None else seq_len
+        if seq_len > self.max_position_embeddings:
+            raise ValueError(f"The maximum supported length is {self.max_position_embeddings}, "
+                             f"and the current length is {seq_len}.")
+        if cos_cached is not None and sin_cached is not None:
+            return cos_cached[:seq_len].to(x.device), sin_cached[:seq_len].to(x.device)
+        if self._cache is None or self._cache[0].shape[0] < seq_len or self._cache[0].device != x.device:
+            self._cache = rotary_tables(self.dim, max(seq_len, 1), self.base, device=x.device)
+        return self._cache[0][:seq_len], self._cache[1][:seq_len]
+
+
 class LlamaMLP(nn.Module):
     def __init__(self, hidden_size, intermediate_size, init_method=xavier_normal_, output_layer_init_method=None, *,
                  layer_idx=0):

@@ -3,13 +3,18 @@ RMSNorm, rotary attention, SwiGLU — on the shared native implementation (``lib
 from libai_b200.config import configurable
 from libai_b200.models.llama_model import (  # noqa: F401
     CasualMask,
+    CrossEntropyLoss,
     LlamaAttention as MultiheadAttention,
     LlamaDecoderLayer as DecoderLayer,
     LlamaForCausalLM as _LlamaForCausalLM,
     LlamaMLP as MLP,
     LlamaModel as AquilaModel,
+    RotaryEmbedding,
     SFTLoss,
 )
+
+AquilaCasualMask = CasualMask
+AquilaDecoderLayer = DecoderLayer
 
 
 class AquilaForCausalLM(_LlamaForCausalLM):

@@ -4,3 +4,6 @@ from projects.common.sft import SFTDataset
 
 class BaichuanDataset(SFTDataset):
     pass
+
+
+AlpacaDataset = BaichuanDataset      # the reference's class name for the same pre-tokenised Alpaca samples

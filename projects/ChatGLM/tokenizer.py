@@ -3,9 +3,17 @@
 ``[gMASK] sop`` prefix, and the chat template builder."""
 import json
 import re
+from enum import Enum
 from typing import Dict, List, Optional
 
 import torch
+
+
+class PaddingStrategy(str, Enum):
+    """Values of the ``padding_strategy`` argument of :meth:`ChatGLMTokenizer._pad`."""
+
+    LONGEST = "longest"
+    MAX_LENGTH = "max_length"
 
 
 class SPTokenizer:
@@ -113,13 +121,18 @@ class ChatGLMTokenizer:
         texts = [text] if isinstance(text, str) else list(text)
         rows = [(self.get_prefix_tokens() if add_bos else []) + self.tokenizer.encode(t)[:max_length] +
                 ([self.eos_token_id] if add_eos else []) for t in texts]
-        width = max(len(r) for r in rows)
-        if self.padding_side == "left":
-            rows = [[self.pad_token_id] * (width - len(r)) + r for r in rows]
-        else:
-            rows = [r + [self.pad_token_id] * (width - len(r)) for r in rows]
-        out = torch.tensor(rows, dtype=torch.long)
+        out = torch.tensor(self._pad(rows), dtype=torch.long)
         return out.to(device) if device and (device != "cuda" or torch.cuda.is_available()) else out
+
+    def _pad(self, encoded_inputs: List[List[int]], max_length: Optional[int] = None,
+             padding_strategy: PaddingStrategy = PaddingStrategy.LONGEST) -> List[List[int]]:
+        """Pad a batch of id lists on ``padding_side`` to the longest row (or to ``max_length``)."""
+        if PaddingStrategy(padding_strategy) == PaddingStrategy.LONGEST or max_length is None:
+            max_length = max(len(r) for r in encoded_inputs)
+        pad = self.pad_token_id
+        if self.padding_side == "left":
+            return [[pad] * (max_length - len(r)) + list(r) for r in encoded_inputs]
+        return [list(r) + [pad] * (max_length - len(r)) for r in encoded_inputs]
 
     def decode(self, ids, skip_special_tokens=True, **kwargs):
         if torch.is_tensor(ids):

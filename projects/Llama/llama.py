@@ -8,6 +8,7 @@ from libai_b200.models.llama_model import (  # noqa: F401
     LlamaForCausalLM,
     LlamaMLP as MLP,
     LlamaModel,
+    RotaryEmbedding,
     SFTLoss,
     rotary_tables,
 )

@@ -179,6 +179,9 @@ class RayDataset(Dataset):
         return self._eval_len()
 
 
+NerfBaseDataset = RayDataset         # base-class name used by the reference (projects/NeRF/datasets/nerf_dataset.py:452)
+
+
 def _load_image(path, img_wh, rgba):
     from PIL import Image
 

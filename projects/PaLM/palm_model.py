@@ -38,6 +38,25 @@ def apply_rotary_pos_emb(pos, t):
     return (t.float() * pos.cos() + rotate_half(t.float()) * pos.sin()).to(t.dtype)
 
 
+class RotaryEmbedding(nn.Module):
+    """``rope(max_seq_len, device=…)`` → rotary angles ``[seq, dim]`` (reference projects/PaLM/palm_model.py)."""
+
+    def __init__(self, dim, *, layer_idx=0):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, max_seq_len, *, device=None):
+        return rotary_positions(max_seq_len, self.dim, device)
+
+
+class SwiGLU(nn.Module):
+    """``silu(gate) * x`` on a tensor whose last dimension holds ``[x, gate]`` halves (the fused kernel when on GPU)."""
+
+    def forward(self, x):
+        x, gate = x.chunk(2, dim=-1)
+        return OF.swiglu(gate.contiguous(), x.contiguous())
+
+
 class FeedForward(nn.Module):
     def __init__(self, dim, mult=4, *, layer_idx=0, init_method=None):
         super().__init__()
