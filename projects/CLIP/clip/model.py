@@ -61,6 +61,18 @@ class ResidualAttentionBlock(nn.Module):
         return x + self.mlp(self.ln_2(x))
 
 
+class MLPClip(nn.Sequential):
+    """CLIP's feed-forward ``c_fc → QuickGELU → c_proj`` as a named module (reference projects/CLIP/clip/model.py:188:
+    the library MLP with the activation swapped for QuickGELU); same parameter names as the block's ``mlp``."""
+
+    def __init__(self, hidden_size, ffn_hidden_size, **_unused):
+        super().__init__(OrderedDict([("c_fc", nn.Linear(hidden_size, ffn_hidden_size)), ("gelu", QuickGELU()),
+                                      ("c_proj", nn.Linear(ffn_hidden_size, hidden_size))]))
+
+
+TransformerLayerClip = ResidualAttentionBlock     # the reference's name for the same pre-LN block
+
+
 class Transformer(nn.Module):
     def __init__(self, width: int, layers: int, heads: int, causal: bool = False):
         super().__init__()

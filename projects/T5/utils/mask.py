@@ -11,3 +11,6 @@ def extended_mask(mask, is_decoder=False):
     if is_decoder:
         m = m & torch.ones(m.shape[-2:], dtype=torch.bool, device=m.device).tril()
     return m
+
+
+from projects.MT5.layers.mask_layer import ExtendedMask  # noqa: E402,F401  (module form of ``extended_mask``)
