@@ -175,3 +175,8 @@ class Linear(nn.Module, LoraLayer):
 
     def __repr__(self) -> str:
         return "lora." + super().__repr__()
+
+
+# The reference splits the adapter-layer protocol into ``BaseTunerLayer`` (generic) and ``LoraLayer`` (LoRA state); with
+# LoRA as the only tuner here, one mixin carries both — the generic name is kept for isinstance checks in user code.
+BaseTunerLayer = LoraLayer

@@ -163,3 +163,8 @@ class LoraModel(nn.Module):
     def lora_state_dict(self):
         """Only the adapter tensors (what a LoRA checkpoint stores)."""
         return {k: v for k, v in self.model.state_dict().items() if self.prefix in k}
+
+
+# Same consolidation on the model side: ``LoraModel`` implements the whole tuner protocol (inject / enable / disable /
+# merge / unload) that the reference declares in an abstract ``BaseTuner``.
+BaseTuner = LoraModel
