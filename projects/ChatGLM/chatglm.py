@@ -61,6 +61,35 @@ def apply_rotary_pos_emb(x: torch.Tensor, cache: torch.Tensor) -> torch.Tensor:
     return torch.cat([out.flatten(3).to(x.dtype), xp], dim=-1)
 
 
+class RotaryEmbedding(nn.Module):
+    """``rope(max_seq_len)`` → the ``[seq, rotary_dim/2, 2]`` (cos, sin) cache consumed by :func:`apply_rotary_pos_emb`
+    (reference projects/ChatGLM/chatglm.py RotaryEmbedding)."""
+
+    def __init__(self, dim, original_impl=False, device=None, dtype=None, base: float = 10000.0):
+        super().__init__()
+        self.dim, self.original_impl, self.base = dim, original_impl, base
+
+    def forward(self, max_seq_len, offset=0, device=None):
+        return rope_cache(max_seq_len, self.dim, self.base, device=device)
+
+
+class CoreAttention(nn.Module):
+    """Scaled-dot-product core on ``[b, heads, s, d]`` tensors → ``[b, s, heads·d]``: the flash kernel when no explicit
+    mask is given (causal for square scores), the masked reference math otherwise."""
+
+    def __init__(self, cfg=None, layer_number=1):
+        super().__init__()
+        self.layer_number = max(1, layer_number)
+        self.attention_dropout = float(cfg.attention_dropout) if cfg is not None else 0.0
+
+    def forward(self, query_layer, key_layer, value_layer, attention_mask=None):
+        b, a, s, d = query_layer.shape
+        causal = attention_mask is None and s == key_layer.shape[2]
+        ctx = OF.attention(query_layer, key_layer, value_layer, causal=causal, scale=1.0 / math.sqrt(d),
+                           mask=attention_mask, dropout_p=self.attention_dropout, training=self.training)
+        return ctx.transpose(1, 2).reshape(b, s, a * d)
+
+
 class SelfAttention(nn.Module):
     def __init__(self, cfg, layer_number):
         super().__init__()
@@ -75,6 +104,7 @@ class SelfAttention(nn.Module):
         self.dense = Linear(proj, cfg.hidden_size, bias=cfg.add_bias_linear, parallel="data", init_method=init,
                             layer_idx=layer_number - 1)
         self.attention_dropout = cfg.attention_dropout
+        self.core_attention = CoreAttention(cfg, layer_number)
 
     def forward(self, hidden, attention_mask, rotary_pos_emb, kv_cache=None, use_cache=True):
         b, s, _ = hidden.shape
@@ -92,10 +122,7 @@ class SelfAttention(nn.Module):
         if g != a:  # multi-query: every group of a/g query heads shares one KV head
             k = k.repeat_interleave(a // g, dim=1)
             v = v.repeat_interleave(a // g, dim=1)
-        causal = attention_mask is None and q.shape[2] == k.shape[2]
-        ctx = OF.attention(q, k, v, causal=causal, scale=1.0 / math.sqrt(d), mask=attention_mask,
-                           dropout_p=self.attention_dropout, training=self.training)
-        return self.dense(ctx.transpose(1, 2).reshape(b, s, a * d)), new_cache
+        return self.dense(self.core_attention(q, k, v, attention_mask)), new_cache
 
 
 class MLP(nn.Module):
@@ -164,7 +191,20 @@ class EmbeddingLayer(nn.Module):
         return self.word_embeddings(input_ids)
 
 
-class ChatGLMModel(nn.Module):
+class ChatGLMPreTrainedModel:
+    """Helpers shared by the ChatGLM model classes (reference projects/ChatGLM/chatglm.py ChatGLMPreTrainedModel:
+    ``_init_weights`` / ``get_masks`` / ``get_position_ids``); a mixin — parameters are initialised by the layer
+    constructors, so ``_init_weights`` has nothing left to do."""
+
+    def _init_weights(self, module: nn.Module):
+        return
+
+    def get_position_ids(self, input_ids):
+        b, s = input_ids.shape
+        return torch.arange(s, dtype=torch.long, device=input_ids.device).unsqueeze(0).repeat(b, 1)
+
+
+class ChatGLMModel(nn.Module, ChatGLMPreTrainedModel):
     def __init__(self, cfg):
         super().__init__()
         self.cfg = cfg
@@ -223,7 +263,7 @@ class ChatGLMModel(nn.Module):
         return hidden, presents
 
 
-class ChatGLMForConditionalGeneration(nn.Module, Generator):
+class ChatGLMForConditionalGeneration(nn.Module, ChatGLMPreTrainedModel, Generator):
     def __init__(self, cfg):
         super().__init__()
         self.cfg = cfg
