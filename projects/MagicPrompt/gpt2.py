@@ -6,6 +6,7 @@ from torch import nn
 from libai_b200.config import configurable
 from libai_b200.inference.generator.generation_utils import Generator
 from libai_b200.models import gpt_model as core
+from libai_b200.models.gpt_model import GPTEmbedding, Transformer  # noqa: F401  (building blocks, same names as the reference module)
 from libai_b200.parallel import mappings
 from libai_b200.utils import distributed as dutil
 
