@@ -34,6 +34,11 @@ train = dict(
     # NEW: forward GEMMs of the linear layers with E4M3 operands (per-tensor dynamic scaling, tcgen05 kind::f8f6f4,
     # fp32 accumulation, bf16 outputs); backward GEMMs stay bf16.  Opt-in: see docs/source/tutorials/basics/Kernels.md
     fp8=dict(enabled=False),
+    # NEW: SIGTERM → write a resumable checkpoint at the next step boundary and stop (all ranks agree via all-reduce)
+    emergency_checkpoint=dict(enabled=False, check_period=1),
+    # NEW: profile iterations [start_iter, start_iter + num_iters): NVTX range "train_step" per step (for ncu / nsys
+    # --nvtx-include) and a torch.profiler Chrome trace under {output_dir}/profiler/
+    profiler=dict(enabled=False, start_iter=10, num_iters=3, torch_profiler=True, nvtx=True),
     # gradient bucket size for data-parallel reduction (names kept from the reference)
     nccl_fusion_threshold_mb=16,
     nccl_fusion_max_ops=24,

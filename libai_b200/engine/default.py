@@ -247,6 +247,15 @@ class DefaultTrainer(TrainerBase):
                     cfg.train.evaluation.eval_metric, mode=cfg.train.evaluation.eval_mode,
                 )
             )
+        # NEW: preemption-safe stop (SIGTERM → checkpoint at the step boundary) and an optional profiling window
+        if try_get_key(cfg, "train.emergency_checkpoint.enabled", default=False):
+            ret.append(hooks.EmergencyCheckpointHook(
+                self.checkpointer, check_period=try_get_key(cfg, "train.emergency_checkpoint.check_period", default=1)))
+        if try_get_key(cfg, "train.profiler.enabled", default=False):
+            p = cfg.train.profiler
+            ret.append(hooks.ProfilerHook(p.get("start_iter", 10), p.get("num_iters", 3),
+                                          os.path.join(cfg.train.output_dir, "profiler"),
+                                          torch_profiler=p.get("torch_profiler", True), nvtx=p.get("nvtx", True)))
         if dutil.is_main_process():
             ret.append(hooks.PeriodicWriter(self.build_writers(), cfg.train.log_period))
         return ret

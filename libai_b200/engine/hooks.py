@@ -22,13 +22,13 @@ from libai_b200.utils.checkpoint import Checkpointer
 from libai_b200.utils.checkpoint import PeriodicCheckpointer as _PeriodicCheckpointer
 from libai_b200.utils.timer import Timer
 
-from .trainer import HookBase
+from .trainer import HookBase, TrainingInterrupted
 
 logger = logging.getLogger(__name__)
 
 __all__ = [
     "CallbackHook", "IterationTimer", "PeriodicWriter", "PeriodicCheckpointer", "BestCheckpointer",
-    "EvalHook", "LRScheduler",
+    "EvalHook", "LRScheduler", "EmergencyCheckpointHook", "ProfilerHook", "TrainingInterrupted",
 ]
 
 
@@ -266,3 +266,112 @@ class LRScheduler(HookBase):
         if hasattr(self.scheduler, "load_state_dict"):
             logger.info("Loading scheduler from state_dict ...")
             self.scheduler.load_state_dict(state_dict)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# NEW (not in the reference): preemption-safe stop and a profiling window
+# ---------------------------------------------------------------------------------------------------------------
+class EmergencyCheckpointHook(HookBase):
+    """SIGTERM (schedulers send it before killing a job) → write a resumable checkpoint at the next step boundary and
+    stop.  The handler only sets a flag; at the end of a step the ranks agree on it (``all_reduce(MAX)`` — the signal may
+    reach only some of them, but the save is collective), save ``model_{iter:07d}`` with the usual ``iteration`` entry so
+    ``--resume`` continues from the following step, and leave the loop through :class:`TrainingInterrupted`."""
+
+    def __init__(self, checkpointer, signals=None, check_period: int = 1):
+        import signal
+
+        self.checkpointer = checkpointer
+        self.signals = tuple(signals) if signals is not None else (signal.SIGTERM,)
+        self.check_period = max(1, int(check_period))
+        self._flag = False
+        self._previous = {}
+
+    def _handler(self, signum, frame):
+        self._flag = True
+        logger.warning("signal %s received: checkpoint + stop at the next step boundary", signum)
+
+    def before_train(self):
+        import signal
+        import threading
+
+        if threading.current_thread() is threading.main_thread():      # signal.signal only works there
+            for sig in self.signals:
+                self._previous[sig] = signal.signal(sig, self._handler)
+
+    def after_train(self):
+        import signal
+
+        for sig, old in self._previous.items():
+            signal.signal(sig, old)
+        self._previous = {}
+
+    def _agreed(self) -> bool:
+        import torch
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return self._flag
+        dev = dutil.get_device() if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([1 if self._flag else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(t.item())
+
+    def after_step(self):
+        if (self.trainer.iter + 1) % self.check_period != 0:
+            return
+        if self._agreed():
+            it = int(self.trainer.iter)
+            self.checkpointer.save(f"model_{it:07d}", iteration=it)
+            raise TrainingInterrupted(f"stopped by signal after iteration {it}; checkpoint model_{it:07d} written")
+
+
+class ProfilerHook(HookBase):
+    """Profile a window of iterations: every step inside ``[start_iter, start_iter + num_iters)`` is wrapped in a
+    process-wide NVTX range ``train_step`` (select it with ``ncu/nsys --nvtx --nvtx-include train_step``; start/end
+    ranges because the backward kernels are launched from the autograd thread) and, with ``torch_profiler=True``,
+    recorded by ``torch.profiler`` into a Chrome trace ``{output_dir}/trace_rank{r}.json``."""
+
+    def __init__(self, start_iter: int, num_iters: int = 3, output_dir: str = ".", torch_profiler: bool = True,
+                 nvtx: bool = True):
+        self.start_iter, self.num_iters = int(start_iter), max(1, int(num_iters))
+        self.output_dir, self.use_torch_profiler, self.use_nvtx = output_dir, torch_profiler, nvtx
+        self._prof, self._range = None, None
+
+    def _inside(self) -> bool:
+        return self.start_iter <= self.trainer.iter < self.start_iter + self.num_iters
+
+    def before_step(self):
+        import torch
+
+        if not self._inside():
+            return
+        if self.use_torch_profiler and self._prof is None:
+            acts = [torch.profiler.ProfilerActivity.CPU]
+            if torch.cuda.is_available():
+                acts.append(torch.profiler.ProfilerActivity.CUDA)
+            self._prof = torch.profiler.profile(activities=acts, record_shapes=False)
+            self._prof.__enter__()
+        if self.use_nvtx and torch.cuda.is_available():
+            self._range = torch.cuda.nvtx.range_start("train_step")
+
+    def after_step(self):
+        import os
+
+        import torch
+
+        if self._range is not None:
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_end(self._range)
+            self._range = None
+        if self._prof is not None and self.trainer.iter + 1 >= self.start_iter + self.num_iters:
+            self._prof.__exit__(None, None, None)
+            os.makedirs(self.output_dir, exist_ok=True)
+            path = os.path.join(self.output_dir, f"trace_rank{dutil.get_rank()}.json")
+            self._prof.export_chrome_trace(path)
+            logger.info("profiler: wrote %s", path)
+            self._prof = None
+
+    def after_train(self):
+        if self._prof is not None:       # training ended inside the window
+            self._prof.__exit__(None, None, None)
+            self._prof = None

@@ -26,6 +26,10 @@ from libai_b200.utils.events import EventStorage, get_event_storage
 __all__ = ["HookBase", "TrainerBase", "StepTrainer", "EagerTrainer", "GraphTrainer"]
 
 
+class TrainingInterrupted(Exception):
+    """Raised by a hook (``EmergencyCheckpointHook``) to leave the training loop cleanly at a step boundary."""
+
+
 class HookBase:
     """Callbacks around the loop::
 
@@ -82,6 +86,9 @@ class TrainerBase:
                     self.after_step()
                 # the loop variable stops at max_iter - 1; after_train hooks expect max_iter
                 self.iter += 1
+            except TrainingInterrupted as stop:     # graceful: emergency checkpoint already written
+                logger.warning("%s", stop)
+                self.interrupted = True
             except Exception:
                 logger.exception("Exception during training:")
                 raise

@@ -86,3 +86,42 @@ def test_two_rank_data_parallel(tmp_path):
     res = run_distributed(_dp_worker, 2, str(tmp_path / "dp2"))
     losses = res[0]
     assert len(losses) >= 6 and all(3.0 < v < 6.0 for v in losses)
+
+
+def test_sigterm_writes_checkpoint_and_resume_matches(tmp_path):
+    """SIGTERM mid-run → emergency checkpoint at the step boundary + clean stop; ``--resume`` then
+    finishes with exactly the weights of an uninterrupted run.  Also exercises the profiling window hook."""
+    import signal
+
+    from libai_b200.engine import DefaultTrainer, hooks
+
+    full_dir, cut_dir = str(tmp_path / "full"), str(tmp_path / "cut")
+    _run(full_dir, ["train.train_iter=10", "train.checkpointer.period=100"])
+
+    orig = DefaultTrainer.build_hooks
+
+    def with_kill(self):
+        hs = orig(self)
+        hs.insert(0, hooks.CallbackHook(after_step=lambda tr: os.kill(os.getpid(), signal.SIGTERM) if tr.iter == 3 else None))
+        return hs
+
+    DefaultTrainer.build_hooks = with_kill
+    try:
+        _run(cut_dir, ["train.train_iter=10", "train.checkpointer.period=100", "train.emergency_checkpoint.enabled=true",
+                       "train.profiler.enabled=true", "train.profiler.start_iter=1", "train.profiler.num_iters=2"])
+    finally:
+        DefaultTrainer.build_hooks = orig
+    saved = sorted(d for d in os.listdir(cut_dir) if d.startswith("model_"))
+    assert "model_0000003" in saved and "model_0000009" not in saved, saved          # stopped right after iteration 3
+    assert open(os.path.join(cut_dir, "last_checkpoint")).read().strip() in ("model_0000003", "model_final")
+    assert os.path.exists(os.path.join(cut_dir, "profiler", "trace_rank0.json"))
+    if os.path.isdir(os.path.join(cut_dir, "model_final")):                           # written by after_train at the stop
+        import shutil
+
+        shutil.rmtree(os.path.join(cut_dir, "model_final"))
+    with open(os.path.join(cut_dir, "last_checkpoint"), "w") as f:
+        f.write("model_0000003")
+    _run(cut_dir, ["train.train_iter=10", "train.checkpointer.period=100"], resume=True)
+    a = torch.load(os.path.join(full_dir, "model_final", "model"), weights_only=False)
+    b = torch.load(os.path.join(cut_dir, "model_final", "model"), weights_only=False)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
