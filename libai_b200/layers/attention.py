@@ -45,6 +45,15 @@ class KeyPaddingMask:
         self.mask_2d = mask_2d
         self.lengths = mask_2d.to(torch.int32).sum(dim=-1).to(torch.int32).contiguous()
         self._dense = None
+        self._prefix = None
+
+    def is_prefix(self) -> bool:
+        """True when every row is a right-padded contiguous prefix (``1…10…0``) — the only shape ``lengths`` can
+        express.  Left padding / holes must take the dense ``m_i·m_j`` path.  Checked once per mask (one small sync)."""
+        if self._prefix is None:
+            m = self.mask_2d.to(torch.int8)
+            self._prefix = bool((m[:, 1:] <= m[:, :-1]).all()) if m.shape[1] > 1 else True
+        return self._prefix
 
     def dense(self) -> torch.Tensor:
         if self._dense is None:
@@ -136,7 +145,9 @@ class MultiheadAttention(nn.Module):
                 raise ValueError("past_key_value and encoder_states cannot be None at the same time.")
         else:
             qkv_packed = self.query_key_value(hidden_states).view(bsz, -1, a, 3 * d)
-            kv_lens = attention_mask.lengths if isinstance(attention_mask, KeyPaddingMask) else None
+            kv_lens = None
+            if isinstance(attention_mask, KeyPaddingMask) and attention_mask.is_prefix():
+                kv_lens = attention_mask.lengths
             if (
                 past_key_value is None and not use_cache
                 and (attention_mask is None or kv_lens is not None)

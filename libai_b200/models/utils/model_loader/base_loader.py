@@ -79,9 +79,11 @@ class LoadPretrainedBase:
                                f"{self.pretrained_model_path}:\n {missing}\n")
             else:
                 logger.info(f"All the weights of {name} were initialized from {self.pretrained_model_path}.")
-            if mismatched:
-                txt = "\n".join(f"- {k}: found shape {a} in the checkpoint and {b} in the model" for k, a, b in mismatched)
-                raise RuntimeError(f"Error(s) in loading state_dict for {name}:\n{txt}")
+        if mismatched:
+            # on EVERY rank (the list is computed identically everywhere): raising on rank 0 only would leave the
+            # others waiting in the next collective
+            txt = "\n".join(f"- {k}: found shape {a} in the checkpoint and {b} in the model" for k, a, b in mismatched)
+            raise RuntimeError(f"Error(s) in loading state_dict for {model.__class__.__name__}:\n{txt}")
         if self.output_loading_info:
             return model, {"missing_keys": missing, "unexpected_keys": unexpected, "mismatched_keys": mismatched}
         return model

@@ -63,6 +63,13 @@ class PipelineStageMixin:
     # ---- generic driver -----------------------------------------------------------------------
     def forward_stage(self, batch: Dict[str, Any], hidden_in=None):
         topo = dutil.get_dist_util()
+        if topo.pipeline_parallel_size > 1 and hidden_in is None and not torch.is_grad_enabled():
+            from libai_b200.parallel import pipeline as _pl
+
+            if not _pl.in_schedule():
+                # plain ``model(**batch)`` under pipeline parallelism (evaluator, inference pipelines, ``test``): run
+                # the whole pipelined forward and return the last stage's output on every rank
+                return _pl.pipelined_forward(self, batch)
         hidden = self.stage_pre(**batch) if topo.is_first_stage else hidden_in
         use_ckpt = self.activation_checkpoint and torch.is_grad_enabled()
         cb = self.grad_ready_callback if torch.is_grad_enabled() else None

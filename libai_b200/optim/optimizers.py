@@ -473,6 +473,19 @@ class FlatOptimizer(torch.optim.Optimizer):
         groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
         return {"state": local, "param_groups": groups, "step": self._step_count}
 
+    def refresh_master(self):
+        """Re-derive the fp32 master weights from the (low-precision) parameters.  Must run after model weights were
+        written behind the optimizer's back (``train.load_weight``, a checkpoint without ``master`` entries): the
+        master copy is what ``step`` updates and writes back, so a stale one silently discards the loaded weights."""
+        if self._groups is None:
+            return self
+        with torch.no_grad():
+            for fg in self._groups:
+                if fg is not None and fg.master is not None:
+                    fg.master.copy_(fg.param_flat[fg.lo : fg.hi])
+        ops.bump_fp8_weight_epoch()
+        return self
+
     def load_state_dict(self, sd):
         self.setup()
         ops.bump_fp8_weight_epoch()
@@ -487,6 +500,10 @@ class FlatOptimizer(torch.optim.Optimizer):
                 continue
             for p, off, name in zip(fg.params, fg.offsets, self._names(fg)):
                 entry = state.get(name)
+                if entry is None and getattr(p, "shared_from", None) is not None:
+                    # tied-weight copy on the last pipeline stage: take the source parameter's state
+                    prefix = name.rsplit(".", 1)[0] + "." if "." in name else ""
+                    entry = state.get(prefix + p.shared_from)
                 if entry is None:
                     continue
                 lo, hi = max(off, fg.lo), min(off + p.numel(), fg.hi)

@@ -155,6 +155,92 @@ class _P2P:
         return self._wrap_inputs(bufs)
 
 
+# ``forward_stage`` called while a schedule drives the stages = one hop of that schedule; called from anywhere else
+# under pp > 1 (evaluator, inference pipelines, ``DefaultTrainer.test``: plain ``model(**batch)``) = a request for the
+# whole pipelined forward, see ``pipelined_forward``.
+_SCHEDULE_DEPTH = 0
+
+
+def in_schedule() -> bool:
+    return _SCHEDULE_DEPTH > 0
+
+
+class _ScheduleScope:
+    def __enter__(self):
+        global _SCHEDULE_DEPTH
+        _SCHEDULE_DEPTH += 1
+
+    def __exit__(self, *exc):
+        global _SCHEDULE_DEPTH
+        _SCHEDULE_DEPTH -= 1
+        return False
+
+
+def _broadcast_from_last_stage(out, topo):
+    """Hand the last stage's result (tensor / tuple / dict of tensors, nested python scalars allowed) to every stage
+    of the pipeline group so that callers see the same value on all ranks."""
+    src = topo.pp_ranks[-1]
+    group = topo.pp_group
+    dev = topo.device
+
+    def describe(o):
+        if torch.is_tensor(o):
+            return ("t", tuple(o.shape), o.dtype)
+        if isinstance(o, dict):
+            return ("d", [(k, describe(v)) for k, v in o.items()])
+        if isinstance(o, (tuple, list)):
+            return ("l" if isinstance(o, list) else "u", [describe(v) for v in o])
+        return ("o", o)
+
+    meta = [describe(out) if topo.is_last_stage else None]
+    dist.broadcast_object_list(meta, src=src, group=group, device=dev if dev.type == "cuda" else None)
+
+    def rebuild(m, o):
+        kind = m[0]
+        if kind == "t":
+            t = o.detach().contiguous() if topo.is_last_stage else torch.empty(m[1], dtype=m[2], device=dev)
+            if t.numel():
+                dist.broadcast(t, src=src, group=group)
+            return t
+        if kind == "d":
+            return {k: rebuild(mv, o[k] if topo.is_last_stage else None) for k, mv in m[1]}
+        if kind in ("l", "u"):
+            vals = [rebuild(mv, o[i] if topo.is_last_stage else None) for i, mv in enumerate(m[1])]
+            return vals if kind == "l" else tuple(vals)
+        return m[1]
+
+    return rebuild(meta[0], out)
+
+
+_INFER_SCHEDULES: Dict[int, "PipelineSchedule1F1B"] = {}
+
+
+@torch.no_grad()
+def pipelined_forward(model, batch: Dict[str, torch.Tensor]):
+    """Whole-pipeline forward for evaluation / inference: every stage runs its blocks, activations hop stage to stage
+    over NCCL/gloo p2p, and the last stage's output is broadcast back so all ranks return it (reference semantics: a
+    global tensor readable everywhere, libai/evaluation/evaluator.py:130-190 ``to_global`` + ``to_local``)."""
+    sched = _INFER_SCHEDULES.get(id(model))
+    if sched is None:
+        sched = _INFER_SCHEDULES[id(model)] = PipelineSchedule1F1B(model)
+        sched.p2p = _P2PDynamic()     # shapes change from call to call (generation, last partial batch)
+    out = sched.forward_only(batch)
+    return _broadcast_from_last_stage(out, sched.topo)
+
+
+class _P2PDynamic(_P2P):
+    """Inference flavour: the shape/dtype handshake is repeated on every hop (payload shapes are not static)."""
+
+    def _fwd_buffers(self):
+        self._recv_meta()
+        return [torch.empty(shape, dtype=dt, device=self.dev) for shape, dt in self.meta_fwd]
+
+    def _fwd_payload(self, out):
+        ts = [t.detach().contiguous() for t in _as_tuple(out)]
+        self._send_meta(ts)
+        return ts
+
+
 class PipelineSchedule1F1B:
     """Runs one optimizer step's worth of micro-batches through the local pipeline stage."""
 
@@ -170,7 +256,8 @@ class PipelineSchedule1F1B:
         if self.topo.sequence_parallel:
             first = next(iter(batch.values()))
             set_sp_shape(first.shape[0], first.shape[1] if first.dim() > 1 else 1)
-        out = self.model.forward_stage(batch, hidden_in)
+        with _ScheduleScope():
+            out = self.model.forward_stage(batch, hidden_in)
         if self.topo.is_last_stage:
             loss = sum(v for k, v in out.items() if "loss" in k) / n_micro
             if self.loss_scaler is not None:
@@ -234,8 +321,13 @@ class PipelineSchedule1F1B:
     @torch.no_grad()
     def forward_only(self, batch: Dict[str, torch.Tensor]):
         """Inference / evaluation through the pipeline; the result lives on the last stage."""
+        if self.topo.sequence_parallel:
+            first = next((v for v in batch.values() if torch.is_tensor(v)), None)
+            if first is not None:
+                set_sp_shape(first.shape[0], first.shape[1] if first.dim() > 1 else 1)
         hidden_in = self.p2p.recv_forward()
-        out = self.model.forward_stage(batch, hidden_in)
+        with _ScheduleScope():
+            out = self.model.forward_stage(batch, hidden_in)
         if not self.topo.is_last_stage:
             self.p2p.send_forward(out)
             return None

@@ -109,10 +109,16 @@ def load_full_state_dict(module: torch.nn.Module, state: Dict[str, torch.Tensor]
         for name, t in own.items():
             if not is_materialized(t):
                 continue  # belongs to another pipeline stage
-            if name not in state:
+            key = name
+            if key not in state and getattr(t, "shared_from", None) is not None:
+                # last-stage copy of a tied weight (pipeline parallelism): a checkpoint written with pp == 1, or an
+                # HF-converted state dict, only carries the source tensor — fill the copy from it so both stay in sync
+                prefix = name.rsplit(".", 1)[0] + "." if "." in name else ""
+                key = prefix + t.shared_from
+            if key not in state:
                 missing.append(name)
                 continue
-            src = state[name]
+            src = state[key]
             if not isinstance(src, torch.Tensor):
                 src = torch.as_tensor(src)
             d = tp_dim_of(t)

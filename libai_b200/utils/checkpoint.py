@@ -84,6 +84,11 @@ class Checkpointer:
         incompatible = self._load_model(ckpt)
         if incompatible is not None:
             self._log_incompatible_keys(incompatible)
+        # the optimizer's fp32 master weights were snapshotted from the pre-load parameters: re-derive them (an
+        # optimizer state with ``master`` entries, loaded below, then overrides this with the exact fp32 values)
+        for obj in self.checkpointables.values():
+            if hasattr(obj, "refresh_master"):
+                obj.refresh_master()
         for key in list(self.checkpointables if checkpointables is None else checkpointables):
             if key in ckpt:
                 self.logger.info(f"Loading {key} from {path}")
@@ -111,8 +116,12 @@ class Checkpointer:
 
     def tag_last_checkpoint(self, last_filename_basename: str) -> None:
         marker = os.path.join(self.save_dir, "last_checkpoint")
-        with open(marker, "w") as f:
+        tmp = marker + ".tmp"
+        with open(tmp, "w") as f:      # atomic: a kill mid-write must not leave an empty marker behind
             f.write(last_filename_basename)
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, marker)
 
     # ------------------------------------------------------------------ internals
     def _load_file(self, path: str) -> Dict[str, Any]:

@@ -90,3 +90,26 @@ def test_clip_and_state_dict_roundtrip():
         mm(x).pow(2).sum().backward()
         oo.step()
     assert max((p - q).abs().max().item() for p, q in zip(m.parameters(), m2.parameters())) < 1e-7
+
+
+def test_checkpointer_load_refreshes_fp32_master(tmp_path):
+    """bf16 parameters + fp32 master: weights loaded through ``Checkpointer.load(..., checkpointables=[])`` (the
+    ``train.load_weight`` path) must be what the first ``step`` updates, not the random-init master snapshot."""
+    import torch
+    from torch import nn
+
+    from libai_b200.optim.optimizers import AdamW
+    from libai_b200.utils.checkpoint import Checkpointer
+
+    torch.manual_seed(0)
+    model = nn.Linear(16, 16).to(torch.bfloat16)
+    opt = AdamW(model.parameters(), lr=1e-3, weight_decay=0.0)
+    opt.configure(zero_stage=0, param_names={id(p): n for n, p in model.named_parameters()})
+    opt.setup()
+    torch.save({"weight": torch.full((16, 16), 5.0), "bias": torch.full((16,), -3.0)}, tmp_path / "w.pt")
+    Checkpointer(model, str(tmp_path), optimizer=opt).load(str(tmp_path / "w.pt"), checkpointables=[])
+    assert float(model.weight.float().mean()) == 5.0
+    opt.zero_grad()
+    model(torch.randn(4, 16, dtype=torch.bfloat16)).float().sum().backward()
+    opt.step()
+    assert abs(float(model.weight.float().mean()) - 5.0) < 0.05 and abs(float(model.bias.float().mean()) + 3.0) < 0.05

@@ -125,3 +125,62 @@ def test_sigterm_writes_checkpoint_and_resume_matches(tmp_path):
     a = torch.load(os.path.join(full_dir, "model_final", "model"), weights_only=False)
     b = torch.load(os.path.join(cut_dir, "model_final", "model"), weights_only=False)
     assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_load_weight_refreshes_master_under_amp(tmp_path):
+    """``train.load_weight`` into a bf16 (AMP) run must survive the first optimizer step — the fp32
+    master copy is re-derived from the loaded parameters instead of keeping the random-init snapshot."""
+    src = str(tmp_path / "src")
+    _run(src, ["train.train_iter=2", "train.checkpointer.period=100"])
+    ckpt = os.path.join(src, "model_final")
+    saved = torch.load(os.path.join(ckpt, "model"), weights_only=False)
+    dst = str(tmp_path / "dst")
+    # lr = 0 → after one step the weights must still equal the loaded ones (bf16-rounded), not a random init
+    _run(dst, ["train.train_iter=1", "train.checkpointer.period=100", "train.amp.enabled=true", f"train.load_weight={ckpt}",
+               "optim.lr=0.0", "optim.weight_decay=0.0", "train.scheduler.warmup_iter=0"])
+    out = torch.load(os.path.join(dst, "model_final", "model"), weights_only=False)
+    k = "GPT_model.transformer.layers.0.mlp.dense_h_to_4h.weight"
+    # (equal up to the bf16 rounding of the parameters; a stale random-init master would be off by ~1e-2)
+    assert (out[k].float() - saved[k].float()).abs().max() < 5e-4, (out[k].float() - saved[k].float()).abs().max()
+
+
+def _pp_eval_worker(rank, world, out_dir):
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    metrics = _run(out_dir, ["train.train_iter=4", "train.checkpointer.period=100", "train.dist.pipeline_parallel_size=2",
+                             "train.num_accumulation_steps=2", "train.evaluation.enabled=true",
+                             "train.evaluation.eval_period=2", "train.evaluation.eval_iter=2"])
+    return [_loss(m) for m in metrics]
+
+
+def test_two_stage_pipeline_train_and_eval(tmp_path):
+    """evaluation under pp > 1 goes through the pipelined forward (stage hop + broadcast of the
+    last stage's outputs) instead of calling ``forward_stage`` with no input on the later stages."""
+    from tests.dist_utils import run_distributed
+
+    out = str(tmp_path / "pp2")
+    run_distributed(_pp_eval_worker, 2, out)
+    assert os.path.isdir(os.path.join(out, "model_final"))
+
+
+def _pp_load_pp1_worker(rank, world, ckpt, out_dir):
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    _run(out_dir, ["train.train_iter=1", "train.checkpointer.period=100", "train.dist.pipeline_parallel_size=2",
+                   "train.num_accumulation_steps=2", f"train.load_weight={ckpt}", "optim.lr=0.0", "optim.weight_decay=0.0"])
+    return 0
+
+
+def test_pp1_checkpoint_into_pp2_fills_tied_copy(tmp_path):
+    """a pp=1 checkpoint has no ``tied_weight_copy``; the last stage's LM-head copy must be filled
+    from the embedding so both stay identical."""
+    from tests.dist_utils import run_distributed
+
+    src = str(tmp_path / "src")
+    _run(src, ["train.train_iter=2", "train.checkpointer.period=100"])
+    ckpt = os.path.join(src, "model_final")
+    out = str(tmp_path / "pp2")
+    run_distributed(_pp_load_pp1_worker, 2, ckpt, out)
+    sd = torch.load(os.path.join(out, "model_final", "model"), weights_only=False)
+    emb = sd["GPT_model.embeddings.token_embeddings.weight"]
+    tied = sd["GPT_model.tied_weight_copy"]
+    ref = torch.load(os.path.join(ckpt, "model"), weights_only=False)["GPT_model.embeddings.token_embeddings.weight"]
+    assert torch.equal(emb, ref) and torch.equal(tied, ref)
