@@ -44,14 +44,24 @@ def parse_args():
     ap.add_argument("--hidden", type=int, default=1024)
     ap.add_argument("--heads", type=int, default=16)
     ap.add_argument("--seq", type=int, default=1024)
-    ap.add_argument("--tp", type=int, default=1)
-    ap.add_argument("--pp", type=int, default=1)
+    ap.add_argument("--tp", type=int, default=1, help="tensor-parallel size of the PRIMARY layout (sequence parallel + "
+                    "collectives fused into the GEMM kernels); per-DP-rank micro-batch is scaled so that the global batch "
+                    "stays --micro-batch x --gpus")
+    ap.add_argument("--pp", type=int, default=1, help="pipeline-parallel size of the primary layout (1F1B, 4 micro-batches per stage)")
+    ap.add_argument("--layout", default="", help="shorthand for the primary layout: dp | tp2 | tp4 | pp2 | 3d (= tp2 x pp2 x dp(N/4) + ZeRO-1)")
+    ap.add_argument("--extras", type=int, default=1,
+                    help="1 (default): after the primary (data-parallel) measurement also measure the tensor-parallel / "
+                         "3-D layouts that fit --gpus in the same launch and report them under `layouts`")
+    ap.add_argument("--extra-steps", type=int, default=8)
+    ap.add_argument("--ref-same-box", type=int, default=1,
+                    help="1 (default): also time baseline/pytorch_baseline.py (stock PyTorch: SDPA, fused AdamW, DDP, bf16 "
+                         "autocast) in this launch and report it as `ref_same_box`")
     ap.add_argument("--zero", type=int, default=-1, help="ZeRO stage; -1 = auto (stage 1 with the fused NVLink kernels when dp > 1)")
     ap.add_argument("--acc", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--graphs", type=int, default=1,
-                    help="1 (default): replay the transformer blocks from CUDA graphs (data-parallel layouts only; "
-                         "tensor/pipeline-parallel runs fall back to eager launches)")
+                    help="1 (default = train.cuda_graphs.enabled default): replay the transformer blocks from CUDA graphs "
+                         "(data-parallel and fused tensor-parallel layouts; pipeline-parallel runs launch eagerly)")
     ap.add_argument("--fused-bias-grad", type=int, default=-1,
                     help="1/0: bias gradient of the MLP's first linear inside the dgrad epilogue (-1: library default)")
     ap.add_argument("--fp8", type=int, default=0,
@@ -150,11 +160,42 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # native / ref arms
 # ---------------------------------------------------------------------------------------------------
-def build_cfg(args, world):
+def layout_of(args, world, name=""):
+    """(tp, pp, acc, zero) of a named layout; the global batch is always --micro-batch x world samples per step."""
+    name = name or args.layout
+    tp, pp = args.tp, args.pp
+    if name in ("tp2", "tp4", "tp8"):
+        tp, pp = int(name[2:]), 1
+    elif name == "pp2":
+        tp, pp = 1, 2
+    elif name == "3d":
+        tp, pp = 2, 2
+    elif name == "dp":
+        tp, pp = 1, 1
+    assert world % (tp * pp) == 0, f"layout {name or (tp, pp)} does not fit {world} GPUs"
+    dp = world // (tp * pp)
+    acc = args.acc if pp == 1 else max(args.acc, 4)          # 1F1B: 4 micro-batches in flight per step
+    zero = args.zero if args.zero >= 0 else (1 if dp > 1 else 0)
+    # samples per DP rank and step = micro_batch x tp x pp (a model-parallel group of tp*pp GPUs carries their share)
+    micro = args.micro_batch * tp * pp // acc
+    assert micro >= 1 and micro * acc == args.micro_batch * tp * pp, "micro-batch not divisible by the accumulation count"
+    return dict(tp=tp, pp=pp, dp=dp, acc=acc, zero=zero, micro=micro)
+
+
+def layout_name(lay):
+    par = f"dp{lay['dp']}"
+    if lay["tp"] > 1:
+        par += f"_tp{lay['tp']}_sp_fused-comm-gemm"
+    if lay["pp"] > 1:
+        par += f"_pp{lay['pp']}_1f1b-x{lay['acc']}"
+    if lay["zero"]:
+        par += f"_zero{lay['zero']}"
+    return par
+
+
+def build_cfg(args, lay):
     from libai_b200.config import LazyConfig
 
-    if args.zero < 0:
-        args.zero = 1 if world // (args.tp * args.pp) > 1 else 0
     cfg = LazyConfig.load(os.path.join(REPO, "configs", "gpt2_synthetic.py"))
     m = cfg.model.cfg
     m.hidden_layers, m.hidden_size, m.num_attention_heads = args.layers, args.hidden, args.heads
@@ -164,22 +205,237 @@ def build_cfg(args, world):
         ds.seq_length = args.seq
         ds.vocab_size = m.vocab_size
     cfg.dataloader.train.num_workers = 2
-    cfg.train.train_micro_batch_size = args.micro_batch
-    cfg.train.num_accumulation_steps = args.acc
+    cfg.train.train_micro_batch_size = lay["micro"]
+    cfg.train.num_accumulation_steps = lay["acc"]
     cfg.train.global_batch_size = None
     cfg.train.train_iter = 10 ** 6
-    cfg.train.log_period = 10 ** 9
+    cfg.train.log_period = 1            # the end-to-end loop reads the loss on the host every step
     cfg.train.amp.enabled = True
     cfg.train.evaluation.enabled = False
     cfg.train.checkpointer.period = 10 ** 9
     cfg.train.output_dir = os.path.join(REPO, "output", "bench")
-    cfg.train.dist.tensor_parallel_size = args.tp
-    cfg.train.dist.pipeline_parallel_size = args.pp
+    cfg.train.cuda_graphs.enabled = bool(args.graphs)
+    cfg.train.dist.tensor_parallel_size = lay["tp"]
+    cfg.train.dist.pipeline_parallel_size = lay["pp"]
     cfg.train.dist.pipeline_num_layers = args.layers
-    cfg.train.dist.data_parallel_size = world // (args.tp * args.pp)
-    cfg.train.zero_optimization.enabled = args.zero > 0
-    cfg.train.zero_optimization.stage = max(args.zero, 1)
+    cfg.train.dist.data_parallel_size = lay["dp"]
+    # tensor parallelism = token-sharded activations + AG->GEMM / GEMM->RS kernels ("auto" resolves to this for GPT-2;
+    # spelled out so that the bench line can state it)
+    cfg.train.dist.sequence_parallel = lay["tp"] > 1
+    cfg.train.dist.fused_tp_comm = lay["tp"] > 1
+    cfg.train.zero_optimization.enabled = lay["zero"] > 0
+    cfg.train.zero_optimization.stage = max(lay["zero"], 1)
     return cfg
+
+
+def measure_native(args, lay, world, rank, local_rank, steps, warmup, with_e2e, clock_sampler=None):
+    """Build the trainer for ``lay`` through the public API, time ``steps`` optimizer steps on the device (CUDA events,
+    max over ranks) and optionally the end-to-end loop through ``trainer.run_step()``."""
+    import gc
+    import logging
+
+    import torch
+    import torch.distributed as dist
+
+    from libai_b200 import ops
+    from libai_b200.engine import DefaultTrainer, default_setup
+    from libai_b200.utils import distributed as dutil
+    from libai_b200.utils.events import EventStorage
+
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    h2d_counter = {"bytes": 0}
+
+    class BenchTrainer(DefaultTrainer):
+        """``get_batch`` is a documented override point: count the bytes of every host→device input copy."""
+
+        @classmethod
+        def get_batch(cls, data, input_placement_device="cuda", mixup_func=None):
+            h2d_counter["bytes"] += sum(v.tensor.numel() * v.tensor.element_size() for v in data.get_fields().values()
+                                        if not v.tensor.is_cuda)
+            return super().get_batch(data, input_placement_device, mixup_func)
+
+    dutil.reset_dist_util()
+    cfg = build_cfg(args, lay)
+    default_setup(cfg, argparse.Namespace(resume=False, config_file=""))
+    logging.getLogger("libai_b200").setLevel(logging.WARNING)
+    torch.manual_seed(cfg.train.seed + rank)
+    trainer = BenchTrainer(cfg)  # public API: builds model, optimizer, scheduler, loader, hooks
+    step = trainer._trainer      # the StepTrainer behind trainer.run_step()
+    topo = dutil.get_dist_util()
+    tokens_per_step = cfg.train.global_batch_size * args.seq
+    assert cfg.train.global_batch_size == args.micro_batch * world, (cfg.train.global_batch_size, args.micro_batch, world)
+    if args.fp8:
+        ops.set_fp8(True)
+    if args.fused_bias_grad >= 0:
+        ops.set_fused_bias_grad(bool(args.fused_bias_grad))
+
+    # ---- device-timed: batches staged on the device, CUDA events around exactly K trainer steps ---------------------
+    staged = []
+    it = iter(trainer.train_loader)
+    for _ in range(lay["acc"] * 4):
+        staged.append(DefaultTrainer.get_batch(next(it), "cuda"))
+    torch.cuda.synchronize()
+    acc = lay["acc"]
+
+    def one_step(i):
+        return step.train_on_batches([staged[(i * acc + k) % len(staged)] for k in range(acc)])
+
+    for i in range(warmup):
+        one_step(i)
+    barrier()
+    if clock_sampler is not None:
+        clock_sampler.start()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    t_enq = time.perf_counter()
+    # `ncu --nvtx --nvtx-include "bench_step"` → exactly the timed steps.  A start/end range (process-wide), not
+    # push/pop (per thread): the backward kernels are launched from the autograd engine's thread.
+    nvtx = os.environ.get("LIBAI_B200_NVTX", "0") == "1"
+    loss = None
+    for i in range(steps):
+        rid = torch.cuda.nvtx.range_start("bench_step") if nvtx else None
+        loss = one_step(warmup + i)
+        if nvtx:
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_end(rid)
+    e1.record()
+    # host time spent ENQUEUEING the timed steps (no sync inside): close to the device time = the step is launch-bound
+    enqueue_ms = max_over_ranks((time.perf_counter() - t_enq) * 1e3) / steps
+    barrier()
+    launches = ops.launch_count()
+    clocks = clock_sampler.stop() if clock_sampler is not None else None
+    dev_ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    res = {
+        "value": tokens_per_step / (dev_ms * 1e-3),
+        "ms_per_step": dev_ms,
+        "parallelism": layout_name(lay),
+        "global_batch": cfg.train.global_batch_size,
+        "micro_batch_per_dp_rank": lay["micro"],
+        "accumulation": lay["acc"],
+        "cuda_graphs": bool(step.graphs_enabled),
+        "gpu_launches": launches,
+        "host_enqueue_ms_per_step": enqueue_ms,
+        "clocks": clocks,
+        "final_loss": None,
+    }
+    if loss:
+        lv = sum(v for k, v in loss.items() if "loss" in k)
+        res["final_loss"] = float(lv)
+
+    # ---- end to end through the trainer API: loader (pinned host) → H2D → step → loss D2H, every step ---------------
+    if with_e2e:
+        with EventStorage(0) as storage:
+            trainer.storage = storage
+            for i in range(max(2, min(warmup, 3))):
+                trainer.iter = i
+                trainer.run_step()
+            barrier()
+            h2d_counter["bytes"] = 0
+            t0 = time.perf_counter()
+            for i in range(steps):
+                trainer.iter = 10 + i
+                storage.iter = 10 + i
+                # run_step = next(loader) [pinned host memory] → get_batch (H2D) → fwd/bwd/optimizer → write_metrics
+                # (log_period = 1: the loss is reduced to rank 0 and read on the host, which synchronises the step)
+                trainer.run_step()
+            barrier()
+            wall = time.perf_counter() - t0
+            last = storage.latest().get("total_loss")
+        wall = max_over_ranks(wall)
+        res["e2e"] = {
+            "value": tokens_per_step * steps / wall,
+            "unit": "tokens/s",
+            "h2d_bytes_per_step": h2d_counter["bytes"] // steps,
+            "d2h_bytes_per_step": 4 * len(loss or {"lm_loss": 0}),
+            "last_loss": float(last[0]) if last is not None else None,
+            "api": "DefaultTrainer.run_step() with train.log_period=1",
+        }
+    # ---- tear down so that the next layout starts from a clean process-group / symmetric-memory state --------------
+    del trainer, step, staged, it
+    from libai_b200.ops import comm_gemm
+    from libai_b200.parallel import symm_mem
+
+    comm_gemm.reset_states()
+    symm_mem._WORKSPACES.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    barrier()
+    return res
+
+
+def measure_pytorch_baseline(args, world, rank, local_rank, steps, warmup):
+    """Stock-PyTorch comparator (baseline/pytorch_baseline.py), same model/config/global batch, same launch."""
+    import importlib.util
+
+    import torch
+    import torch.distributed as dist
+
+    spec = importlib.util.spec_from_file_location("pytorch_baseline", os.path.join(REPO, "baseline", "pytorch_baseline.py"))
+    pb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pb)
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(1234)
+    model, opt = pb.build(args.layers, args.hidden, args.heads, 50304, args.seq, dev, world, local_rank)
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    host = [torch.randint(0, 50304, (args.micro_batch, args.seq + 1), generator=g).pin_memory() for _ in range(4)]
+    staged = [h.to(dev) for h in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def mx(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(warmup):
+        b = staged[i % 4]
+        pb.train_step(model, opt, b[:, :-1], b[:, 1:])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        b = staged[i % 4]
+        loss = pb.train_step(model, opt, b[:, :-1], b[:, 1:])
+    e1.record()
+    barrier()
+    dev_ms = mx(e0.elapsed_time(e1)) / steps
+    # end to end: pinned host → device copy of the step's tokens + loss read on the host, every step
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        b = host[i % 4].to(dev, non_blocking=True)
+        lv = float(pb.train_step(model, opt, b[:, :-1], b[:, 1:]))
+    barrier()
+    wall = mx(time.perf_counter() - t0)
+    tokens = args.micro_batch * world * args.seq
+    out = {"impl": "stock PyTorch (SDPA, cuBLAS bf16 autocast, fused AdamW, DDP/NCCL) — baseline/pytorch_baseline.py",
+           "value": tokens / (dev_ms * 1e-3), "ms_per_step": dev_ms, "e2e_value": tokens * steps / wall,
+           "unit": "tokens/s", "final_loss": lv}
+    del model, opt, staged
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -198,164 +454,39 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
     assert torch.cuda.is_available(), "bench.py needs a GPU"
     torch.cuda.set_device(local_rank)
+    from libai_b200.utils import distributed as _dutil
 
-    import logging
+    _dutil.init_process_group("cuda")        # torchrun environment → NCCL (+ gloo for host objects)
 
-    from libai_b200 import ops
-    from libai_b200.engine import DefaultTrainer, default_setup
-    from libai_b200.utils import distributed as dutil
+    primary = layout_of(args, world)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    main_res = measure_native(args, primary, world, rank, local_rank, args.steps, args.warmup, not args.no_e2e, sampler)
 
-    cfg = build_cfg(args, world)
-    default_setup(cfg, argparse.Namespace(resume=False, config_file=""))
-    logging.getLogger("libai_b200").setLevel(logging.WARNING)
-    torch.manual_seed(cfg.train.seed + rank)
-    trainer = DefaultTrainer(cfg)  # public API: builds model, optimizer, scheduler, loader, hooks
-    step = trainer._trainer
-    topo = dutil.get_dist_util()
-    dev = torch.device("cuda", local_rank)
-    tokens_per_step = cfg.train.global_batch_size * args.seq
+    layouts = {main_res["parallelism"]: {k: main_res[k] for k in ("value", "ms_per_step", "cuda_graphs", "gpu_launches",
+                                                                  "host_enqueue_ms_per_step", "global_batch")}}
+    if args.extras and args.impl == "native" and not args.layout and args.tp == 1 and args.pp == 1:
+        # the model-parallel layouts that fit this GPU count, same global batch, same launch (BASELINE.json configs:
+        # "TP=2 DP=4", "TP=2 PP=2 DP=2 + ZeRO-1")
+        names = {2: ["tp2"], 4: ["tp2", "3d"], 8: ["tp2", "3d"]}.get(world, [])
+        for name in names:
+            lay = layout_of(args, world, name)
+            try:
+                r = measure_native(args, lay, world, rank, local_rank, args.extra_steps, max(3, min(args.warmup, 4)), False)
+                layouts[r["parallelism"]] = {k: r[k] for k in ("value", "ms_per_step", "cuda_graphs", "gpu_launches",
+                                                               "host_enqueue_ms_per_step", "global_batch", "final_loss")}
+                layouts[r["parallelism"]]["steps"] = args.extra_steps
+            except Exception as e:  # an extra layout must never take the headline measurement down
+                layouts[name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+                if world > 1:
+                    raise      # a rank-local failure would leave the others in a collective: fail loudly instead
 
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local_rank])
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-timed: batches staged on the device, CUDA events around exactly K steps ----------------
-    staged = []
-    it = iter(trainer.train_loader)
-    for _ in range(args.acc * 4):
-        staged.append(DefaultTrainer.get_batch(next(it), "cuda"))
-    torch.cuda.synchronize()
-    model, optimizer = trainer.model, trainer.optimizer
-    acc = args.acc
-    if args.fp8:
-        from libai_b200 import ops as _ops
-
-        _ops.set_fp8(True)
-    if args.fused_bias_grad >= 0:
-        from libai_b200 import ops as _ops
-
-        _ops.set_fused_bias_grad(bool(args.fused_bias_grad))
-    graphs_on = False
-    if args.graphs and topo.pipeline_parallel_size == 1:
-        from libai_b200.engine.cuda_graphs import enable_for_model
-
-        graphs_on = enable_for_model(model, staged[0])
-        step._graphs_tried, step.graphs_enabled = True, graphs_on
-        optimizer.zero_grad()
-
-    def one_step(i):
-        optimizer.zero_grad()
-        if topo.pipeline_parallel_size > 1:
-            from libai_b200.parallel.pipeline import PipelineSchedule1F1B
-
-            if step._pipeline is None:
-                step._pipeline = PipelineSchedule1F1B(model)
-            loss = step._pipeline.run([staged[(i * acc + k) % len(staged)] for k in range(acc)])
-        else:
-            loss = None
-            for k in range(acc):
-                step._arm_grad_overlap(k == acc - 1)   # same as StepTrainer.run_step: early DP reduce on the last micro-batch
-                out = model(**staged[(i * acc + k) % len(staged)])
-                l = sum(v for kk, v in out.items() if "loss" in kk) / acc
-                l.backward()
-                loss = l.detach()
-        optimizer.step()
-        return loss
-
-    for i in range(args.warmup):
-        one_step(i)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ops.reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    t_enq = time.perf_counter()
-    # `ncu --nvtx --nvtx-include "bench_step"` → exactly the timed steps.  A start/end range (process-wide), not
-    # push/pop (per thread): the backward kernels are launched from the autograd engine's thread.
-    nvtx = os.environ.get("LIBAI_B200_NVTX", "0") == "1"
-    for i in range(args.steps):
-        rid = torch.cuda.nvtx.range_start("bench_step") if nvtx else None
-        loss = one_step(args.warmup + i)
-        if nvtx:
-            torch.cuda.synchronize()
-            torch.cuda.nvtx.range_end(rid)
-    e1.record()
-    # host time spent ENQUEUEING the timed steps (no sync inside): close to the device time = the step is launch-bound
-    enqueue_ms = max_over_ranks((time.perf_counter() - t_enq) * 1e3) / args.steps
-    barrier()
-    launches = ops.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
-    dev_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    value = tokens_per_step / (dev_ms * 1e-3)
-
-    # ---- end to end through the trainer API: loader (pinned host) → H2D → step → loss D2H ----------------
-    e2e = None
-    if not args.no_e2e:
-        h2d = d2h = 0
-        from libai_b200.utils.events import EventStorage
-
-        with EventStorage(0) as storage:
-            trainer.storage = storage
-            step.log_period = 10 ** 9
-            for i in range(max(2, args.warmup)):
-                trainer.iter = i
-                trainer.run_step()
-            barrier()
-            t0 = time.perf_counter()
-            for i in range(args.steps):
-                trainer.iter = 10 + i
-                # run_step: next(loader) [pinned] → get_batch (H2D) → fwd/bwd/optimizer
-                data_iter = step._data_loader_iter
-                batches = []
-                for _ in range(acc):
-                    inst = next(data_iter)
-                    h2d += sum(v.tensor.numel() * v.tensor.element_size() for v in inst.get_fields().values())
-                    batches.append(DefaultTrainer.get_batch(inst, "cuda"))
-                optimizer.zero_grad()
-                if topo.pipeline_parallel_size > 1:
-                    out = step._pipeline.run(batches)
-                    lval = sum(v for kk, v in (out or {}).items() if "loss" in kk) if out else torch.zeros((), device=dev)
-                else:
-                    lval = None
-                    for j, b in enumerate(batches):
-                        step._arm_grad_overlap(j == len(batches) - 1)
-                        out = model(**b)
-                        l = sum(v for kk, v in out.items() if "loss" in kk) / acc
-                        l.backward()
-                        lval = l.detach() if lval is None else lval + l.detach()
-                optimizer.step()
-                host_loss = float(lval.float().cpu()) if torch.is_tensor(lval) else float(lval)  # D2H read (sync)
-                d2h += 4
-            barrier()
-            wall = time.perf_counter() - t0
-        wall = max_over_ranks(wall)
-        e2e = {
-            "value": tokens_per_step * args.steps / wall,
-            "unit": "tokens/s",
-            "h2d_bytes_per_step": h2d // args.steps,
-            "d2h_bytes_per_step": d2h // args.steps,
-            "last_loss": host_loss,
-        }
+    ref_same_box = None
+    if args.ref_same_box and args.impl == "native":
+        ref_same_box = measure_pytorch_baseline(args, world, rank, local_rank, min(args.steps, 10), 3)
 
     if rank == 0:
-        par = f"dp{topo.data_parallel_size}"
-        if topo.tensor_parallel_size > 1:
-            par += f"_tp{topo.tensor_parallel_size}"
-        if topo.pipeline_parallel_size > 1:
-            par += f"_pp{topo.pipeline_parallel_size}"
-        if args.zero:
-            par += f"_zero{args.zero}"
         base = PUBLISHED_TOKENS_PER_S.get(world)
+        value = main_res["value"]
         line = {
             "metric": "tokens/sec GPT-2 (nl24 h1024 a16 s1024) pre-training, device-timed max-over-ranks",
             "value": value,
@@ -363,7 +494,7 @@ def main():
             "n_gpus": world,
             "steps": args.steps,
             "warmup": args.warmup,
-            "ms_per_step": dev_ms,
+            "ms_per_step": main_res["ms_per_step"],
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": (value / base) if base else None,
@@ -372,19 +503,25 @@ def main():
             "impl": args.impl,
             "config": {
                 "model": f"GPT-2 nl{args.layers} h{args.hidden} a{args.heads} (reference benchmark model, ~355M params)",
-                "global_batch": cfg.train.global_batch_size,
+                "global_batch": main_res["global_batch"],
                 "micro_batch_per_gpu": args.micro_batch,
                 "seq_len": args.seq,
-                "parallelism": par,
+                "parallelism": main_res["parallelism"],
                 "l2_policy": "working set (weights+activations+optimizer state >> 126MB L2) exceeds L2 every step",
-                "cuda_graphs": graphs_on,
+                "cuda_graphs": main_res["cuda_graphs"],
             },
-            "clocks": clocks,
-            "e2e": e2e,
-            "gpu_launches": launches,
-            "host_enqueue_ms_per_step": enqueue_ms,
+            "clocks": main_res["clocks"],
+            "e2e": main_res.get("e2e"),
+            "gpu_launches": main_res["gpu_launches"],
+            "host_enqueue_ms_per_step": main_res["host_enqueue_ms_per_step"],
             "host_cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count(),
-            "final_loss": float(loss) if loss is not None and torch.is_tensor(loss) else None,
+            "final_loss": main_res["final_loss"],
+            # every layout measured in this launch (same model, same global batch): data parallel (the headline `value`),
+            # tensor parallel with the collectives inside the GEMM kernels, and the 3-D layout
+            "layouts": layouts,
+            # stock-PyTorch comparator measured in this same launch on this same box (NOT the OneFlow reference)
+            "ref_same_box": ref_same_box,
+            "vs_ref_same_box": (value / ref_same_box["value"]) if ref_same_box else None,
         }
         print(json.dumps(line))
     if world > 1:

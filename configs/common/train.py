@@ -29,8 +29,9 @@ train = dict(
     # recompute each transformer layer in backward
     activation_checkpoint=dict(enabled=False),
     # NEW: capture forward+backward of every transformer block into CUDA graphs at the first step and replay them
-    # (≈800 kernel launches per step become 48 graph launches; needs dp-only layout, static shapes, dropout 0)
-    cuda_graphs=dict(enabled=False),
+    # (≈800 kernel launches per step become 48 graph launches; data-parallel and fused tensor-parallel layouts, static
+    # shapes; anything else silently keeps eager launches)
+    cuda_graphs=dict(enabled=True),
     # NEW: forward GEMMs of the linear layers with E4M3 operands (per-tensor dynamic scaling, tcgen05 kind::f8f6f4,
     # fp32 accumulation, bf16 outputs); backward GEMMs stay bf16.  Opt-in: see docs/source/tutorials/basics/Kernels.md
     fp8=dict(enabled=False),
@@ -69,9 +70,11 @@ train = dict(
         pipeline_num_layers=None,
         # e.g. [0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3]
         custom_pipeline_stage_id=None,
-        # NEW: Megatron-style sequence parallelism inside the TP region and fused comm+GEMM kernels
-        sequence_parallel=False,
-        fused_tp_comm=False,
+        # NEW: Megatron-style sequence parallelism inside the TP region with the collectives fused into the GEMM kernels
+        # (AG→GEMM / GEMM→RS over NVLink peer memory).  "auto" = on for the models that support token-sharded
+        # activations (GPT-2, BERT, Llama family: `supports_sequence_parallel`), off otherwise; True / False force it.
+        sequence_parallel="auto",
+        fused_tp_comm="auto",
     ),
     # "cuda" | "cpu": where batches are placed by get_batch
     input_placement_device="cuda",

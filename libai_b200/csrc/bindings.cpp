@@ -45,10 +45,11 @@ int lb_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const
 int lb_adamw(float* master, const float* grad, float* m, float* v, void* lp_out, const float* scale, long n, float lr,
              float b1, float b2, float eps, float wd, float bc1, float bc2, int decoupled, cudaStream_t s);
 int lb_sqnorm(const float* x, float* out, long n, cudaStream_t s);
-int lb_gemm_bf16_comm(const void* a, const void* b, void* out, int M, int N, int K, int layout, const void* bias, int act,
-                      void* pre_out, int mode, int world, int rank, unsigned epoch, unsigned target,
-                      const long* peer_buf, const long* peer_flags, void* chunk_flags, const void* residual,
-                      void* rs_out, long staging_parity_off, int n_comm, cudaStream_t stream);
+int lb_gemm_bf16_comm(const void* a, const void* b, void* out, int M, int N, int K, int layout, int epi,
+                      const void* bias, int act, void* pre_out, const void* pre_in, float* colsum, int mode,
+                      int world, int rank, const long* peer_buf, const long* peer_flags, const long* peer_done,
+                      void* state, const void* local_shard, int fill_local, const void* residual, void* rs_out,
+                      long staging_parity_off, int n_comm, cudaStream_t stream);
 int lb_zero_reduce_scatter(const long* grad_ptrs, const long* flag_ptrs, float* red, float* sqnorm, long lo, long n,
                            float scale, int world, int rank, unsigned epoch, cudaStream_t s);
 int lb_zero_adam_allgather(float* master, const float* red, float* m, float* v, const long* param_ptrs,
@@ -527,24 +528,71 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> attn_bwd(const Tensor& dout, const Te
 // ---- fused collectives ---------------------------------------------------------------------------------------
 std::vector<long> to_longs(at::IntArrayRef v) { return std::vector<long>(v.begin(), v.end()); }
 
-// mode 1: AG->GEMM (returns y [M, N]); mode 2: GEMM->RS (returns rs_out [M/world, N])
-Tensor gemm_comm(const Tensor& a, const Tensor& w, int64_t layout, const c10::optional<Tensor>& bias, int64_t act, int64_t mode,
-                 int64_t world, int64_t rank, int64_t epoch, int64_t target, at::IntArrayRef peer_buf,
-                 at::IntArrayRef peer_flags, const c10::optional<Tensor>& chunk_flags,
-                 const c10::optional<Tensor>& residual, int64_t staging_parity_off, int64_t n_comm) {
-  c10::cuda::CUDAGuard guard(a.device());
-  TORCH_CHECK(a.dim() == 2 && w.dim() == 2 && a.is_contiguous() && w.is_contiguous(), "gemm_comm: contiguous 2-D operands");
-  const int64_t M = a.size(0), K = a.size(1), N = layout == 0 ? w.size(0) : w.size(1);
-  TORCH_CHECK((layout == 0 ? w.size(1) : w.size(0)) == K, "gemm_comm: K mismatch");
-  auto pb = to_longs(peer_buf), pf = to_longs(peer_flags);
-  Tensor out = mode == 1 ? at::empty({M, N}, a.options()) : at::empty({M / world, N}, a.options());
-  const void* bias_ptr = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
-  const void* res_ptr = (residual.has_value() && residual->defined()) ? residual->data_ptr() : nullptr;
-  void* cf = (chunk_flags.has_value() && chunk_flags->defined()) ? chunk_flags->data_ptr() : nullptr;
-  check(lb_gemm_bf16_comm(a.data_ptr(), w.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, (int)layout, bias_ptr, (int)act, nullptr,
-                          (int)mode, (int)world, (int)rank, (unsigned)epoch, (unsigned)target, pb.data(), pf.data(), cf,
-                          res_ptr, out.data_ptr(), (long)staging_parity_off, (int)n_comm, cur_stream()),
-        "gemm_comm");
+const void* opt_ptr(const c10::optional<Tensor>& t) { return (t.has_value() && t->defined()) ? t->data_ptr() : nullptr; }
+
+// all-gather -> GEMM: y [M, N] = epilogue(all_gather(shard) @ op(w)); `gathered` is the local symmetric buffer [M, K]
+// whose remote rows the peers' copy CTAs fill during the kernel.  Epilogue: + bias, activation (returning the
+// pre-activation as second tensor when `need_pre`), or `* act'(pre_in)` (dgrad fused with the activation backward) and
+// optional column sums into `colsum` (fp32 [N]).
+std::tuple<Tensor, Tensor> ag_gemm(const Tensor& gathered, const Tensor& shard, const Tensor& w, int64_t layout,
+                                   const c10::optional<Tensor>& bias, int64_t act, bool need_pre,
+                                   const c10::optional<Tensor>& pre_in, c10::optional<Tensor> colsum, bool fill_local,
+                                   int64_t world, int64_t rank, at::IntArrayRef peer_buf, at::IntArrayRef peer_flags,
+                                   at::IntArrayRef peer_done, Tensor state, int64_t n_comm) {
+  c10::cuda::CUDAGuard guard(gathered.device());
+  TORCH_CHECK(gathered.dim() == 2 && shard.dim() == 2 && w.dim() == 2 && gathered.is_contiguous() && shard.is_contiguous() &&
+                  w.is_contiguous(), "ag_gemm: contiguous 2-D operands");
+  TORCH_CHECK(layout == 0 || layout == 1, "ag_gemm: layout 0 (w [N,K]) or 1 (w [K,N])");
+  const int64_t M = gathered.size(0), K = gathered.size(1), N = layout == 0 ? w.size(0) : w.size(1);
+  TORCH_CHECK((layout == 0 ? w.size(1) : w.size(0)) == K && shard.size(1) == K && shard.size(0) * world == M, "ag_gemm: shape mismatch");
+  auto pb = to_longs(peer_buf), pf = to_longs(peer_flags), pd = to_longs(peer_done);
+  Tensor out = at::empty({M, N}, gathered.options());
+  Tensor pre = need_pre ? at::empty({M, N}, gathered.options()) : Tensor();
+  float* cs = (colsum.has_value() && colsum->defined()) ? colsum->data_ptr<float>() : nullptr;
+  check(lb_gemm_bf16_comm(gathered.data_ptr(), w.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, (int)layout, 0,
+                          opt_ptr(bias), (int)act, need_pre ? pre.data_ptr() : nullptr, opt_ptr(pre_in), cs, 1, (int)world,
+                          (int)rank, pb.data(), pf.data(), pd.data(), state.data_ptr(), shard.data_ptr(), fill_local ? 1 : 0,
+                          nullptr, nullptr, 0, (int)n_comm, cur_stream()),
+        "ag_gemm");
+  return {out, need_pre ? pre : out};
+}
+
+// wgrad with the all-gather inside: out [Nl, K] (fp32) (+)= gyᵀ [Nl, T] @ all_gather(shard) [T, K]; the shards lie
+// along the reduction dimension, partitions of the local shard run first while the remote ones arrive.
+void ag_wgrad(const Tensor& gy, const Tensor& gathered, const Tensor& shard, Tensor out, bool accumulate, int64_t world,
+              int64_t rank, at::IntArrayRef peer_buf, at::IntArrayRef peer_flags, at::IntArrayRef peer_done, Tensor state,
+              int64_t n_comm) {
+  c10::cuda::CUDAGuard guard(gy.device());
+  TORCH_CHECK(gy.dim() == 2 && gathered.dim() == 2 && gy.is_contiguous() && gathered.is_contiguous() && shard.is_contiguous(),
+              "ag_wgrad: contiguous 2-D operands");
+  const int64_t T = gy.size(0), Nl = gy.size(1), K = gathered.size(1);
+  TORCH_CHECK(gathered.size(0) == T && shard.size(1) == K && shard.size(0) * world == T, "ag_wgrad: shape mismatch");
+  TORCH_CHECK(out.scalar_type() == at::kFloat && out.dim() == 2 && out.size(0) == Nl && out.size(1) == K && out.is_contiguous(),
+              "ag_wgrad: out must be contiguous fp32 [N_local, K]");
+  if (!accumulate) out.zero_();
+  auto pb = to_longs(peer_buf), pf = to_longs(peer_flags), pd = to_longs(peer_done);
+  check(lb_gemm_bf16_comm(gy.data_ptr(), gathered.data_ptr(), out.data_ptr(), (int)Nl, (int)K, (int)T, 2, 2, nullptr, 0,
+                          nullptr, nullptr, nullptr, 1, (int)world, (int)rank, pb.data(), pf.data(), pd.data(),
+                          state.data_ptr(), shard.data_ptr(), 0, nullptr, nullptr, 0, (int)n_comm, cur_stream()),
+        "ag_wgrad");
+}
+
+// GEMM -> reduce-scatter: returns [M / world, N] = sum over ranks of (x @ op(w)) rows owned by this rank (+bias +residual)
+Tensor gemm_rs(const Tensor& x, const Tensor& w, int64_t layout, const c10::optional<Tensor>& bias,
+               const c10::optional<Tensor>& residual, int64_t world, int64_t rank, at::IntArrayRef peer_buf,
+               at::IntArrayRef peer_flags, at::IntArrayRef peer_done, Tensor state, int64_t staging_parity_off) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.is_contiguous() && w.is_contiguous(), "gemm_rs: contiguous 2-D operands");
+  TORCH_CHECK(layout == 0 || layout == 1, "gemm_rs: layout 0 (w [N,K]) or 1 (w [K,N])");
+  const int64_t M = x.size(0), K = x.size(1), N = layout == 0 ? w.size(0) : w.size(1);
+  TORCH_CHECK((layout == 0 ? w.size(1) : w.size(0)) == K, "gemm_rs: K mismatch");
+  auto pb = to_longs(peer_buf), pf = to_longs(peer_flags), pd = to_longs(peer_done);
+  Tensor out = at::empty({M / world, N}, x.options());
+  check(lb_gemm_bf16_comm(x.data_ptr(), w.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, (int)layout, 0, opt_ptr(bias),
+                          0, nullptr, nullptr, nullptr, 2, (int)world, (int)rank, pb.data(), pf.data(), pd.data(),
+                          state.data_ptr(), nullptr, 0, opt_ptr(residual), out.data_ptr(), (long)staging_parity_off, 0,
+                          cur_stream()),
+        "gemm_rs");
   return out;
 }
 
@@ -589,7 +637,9 @@ void p2p_allgather(const Tensor& shard, at::IntArrayRef out_ptrs, at::IntArrayRe
 }  // namespace
 
 TORCH_LIBRARY(libai_b200, m) {
-  m.def("gemm_comm(Tensor a, Tensor w, int layout, Tensor? bias, int act, int mode, int world, int rank, int epoch, int target, int[] peer_buf, int[] peer_flags, Tensor? chunk_flags, Tensor? residual, int staging_parity_off, int n_comm) -> Tensor", &gemm_comm);
+  m.def("ag_gemm(Tensor gathered, Tensor shard, Tensor w, int layout, Tensor? bias, int act, bool need_pre, Tensor? pre_in, Tensor(a!)? colsum, bool fill_local, int world, int rank, int[] peer_buf, int[] peer_flags, int[] peer_done, Tensor(b!) state, int n_comm) -> (Tensor, Tensor)", &ag_gemm);
+  m.def("ag_wgrad(Tensor gy, Tensor gathered, Tensor shard, Tensor(a!) out, bool accumulate, int world, int rank, int[] peer_buf, int[] peer_flags, int[] peer_done, Tensor(b!) state, int n_comm) -> ()", &ag_wgrad);
+  m.def("gemm_rs(Tensor x, Tensor w, int layout, Tensor? bias, Tensor? residual, int world, int rank, int[] peer_buf, int[] peer_flags, int[] peer_done, Tensor(a!) state, int staging_parity_off) -> Tensor", &gemm_rs);
   m.def("zero_reduce_scatter(int[] grad_ptrs, int[] flag_ptrs, Tensor(a!) red, Tensor(b!) sqnorm, int lo, int n, float scale, int world, int rank, int epoch) -> ()", &zero_reduce_scatter);
   m.def("zero_adam_allgather(Tensor(a!) master, Tensor red, Tensor(b!) m, Tensor(c!) v, int[] param_ptrs, int[] flag_ptrs, Tensor(d!) done_counter, Tensor clip, int lo, int n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, bool decoupled, int world, int rank, int epoch) -> ()", &zero_adam_allgather);
   m.def("device_barrier(int[] flag_ptrs, int world, int rank, int slot, int epoch) -> ()", &device_barrier);

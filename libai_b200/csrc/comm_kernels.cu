@@ -50,10 +50,8 @@ LB_DEVICE void signal_peers(const PeerPtrs& flags, int world, int rank, int slot
 }
 LB_DEVICE void wait_peers(const PeerPtrs& flags, int world, int rank, int slot, uint32_t epoch) {
   const uint32_t* mine = reinterpret_cast<const uint32_t*>(flags.p[rank]) + slot * world;
-  for (int q = 0; q < world; ++q) {
-    while (static_cast<int32_t>(ld_acquire_sys(mine + q) - epoch) < 0) {
-    }
-  }
+  // bounded (common.cuh): a dead peer turns into a device trap with a diagnostic instead of a hung GPU
+  for (int q = 0; q < world; ++q) spin_wait_ge_sys(mine + q, epoch, 0ull, /*what=*/10 + slot, q);
 }
 
 // ------------------------------------------------------------------------------------------------

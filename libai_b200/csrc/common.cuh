@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace lb {
 
@@ -23,6 +24,38 @@ LB_DEVICE bool elect_one() {
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(pred));
   return pred != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-GPU flag waits (NVLink peer memory).  Every wait is BOUNDED: a dead or wedged peer must not hang the GPU
+// forever — after `timeout_ns` the waiter prints who/what it was waiting for and traps, which surfaces
+// as a CUDA error on the host (the trainer's emergency path / the launcher's restart then take over).
+// ---------------------------------------------------------------------------------------------
+LB_DEVICE unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+LB_DEVICE uint32_t ld_acquire_sys_u32(const uint32_t* a) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(a) : "memory");
+  return v;
+}
+constexpr unsigned long long kDefaultSpinTimeoutNs = 120ull * 1000ull * 1000ull * 1000ull;  // 2 min
+// wait until *addr >= target (wrap-safe signed distance); `what`/`who` only label the diagnostic
+static __device__ __noinline__ void spin_timeout_trap(const uint32_t* addr, uint32_t target, int what, int who) {
+  printf("[libai_b200] device spin-wait timed out: kind=%d rank/peer=%d flag=%p value=%u target=%u (block %d)\n", what, who,
+         (const void*)addr, ld_acquire_sys_u32(addr), target, (int)blockIdx.x);
+  __trap();
+}
+LB_DEVICE void spin_wait_ge_sys(const uint32_t* addr, uint32_t target, unsigned long long timeout_ns, int what, int who) {
+  if (static_cast<int32_t>(ld_acquire_sys_u32(addr) - target) >= 0) return;
+  const unsigned long long t0 = globaltimer_ns();
+  const unsigned long long budget = timeout_ns ? timeout_ns : kDefaultSpinTimeoutNs;
+  uint32_t polls = 0;
+  while (static_cast<int32_t>(ld_acquire_sys_u32(addr) - target) < 0) {
+    if ((++polls & 1023u) == 0 && globaltimer_ns() - t0 > budget) spin_timeout_trap(addr, target, what, who);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

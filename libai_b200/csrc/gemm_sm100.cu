@@ -54,26 +54,37 @@ struct GemmParams {
 };
 
 // Fused collective modes (tensor parallel): peer pointers refer to NVLink peer-mapped symmetric memory.
-//   COMM_AG : all-gather -> GEMM.  A = [M, K] "gathered" buffer; rank r produced rows [r*rpr, (r+1)*rpr) of its own
-//             buffer and `n_comm` dedicated CTAs push them into every peer's buffer (P2P stores) while the GEMM CTAs
-//             already work on the local rows; per-row-block arrival counters (bumped by the pushing peer) gate the
-//             TMA loads of the remote rows.
+//   COMM_AG : all-gather -> GEMM.  One operand is the concatenation over ranks of [rows_per_rank, K] shards along its
+//             row dimension: A for NT/NN (row blocks of the output), B for TN (`gathered_is_b`: the shards lie along
+//             the REDUCTION dimension of the wgrad dW = dyᵀ · all_gather(x)).  Tiles / k-blocks that only need the local
+//             shard read it through its own tensor map and start at once; `n_comm` dedicated CTAs push the local shard
+//             into every peer's gathered buffer (TMA bulk copies over NVLink) meanwhile; per-row-block arrival counters
+//             (bumped by the pushing peer) gate the TMA loads of the remote rows.
 //   COMM_RS : GEMM -> reduce-scatter.  Each rank computes the full [M, N] partial product; the epilogue stores
 //             row block tiles straight into the owner's staging slot (P2P stores) and bumps the owner's arrival
 //             counter; after its tiles every CTA helps reducing the local rows (sum over sources + bias + residual).
+// All handshake state lives in DEVICE memory and is advanced by the kernel itself (`state[0]` = number of completed
+// calls on this buffer set): the launch parameters of a call site never change, so transformer blocks containing these
+// kernels are captured into CUDA graphs and replayed.  Write-after-read safety of the symmetric buffers does not rely
+// on any call-order convention: a rank publishes "finished call c" into every peer's `done` row when its kernel
+// retires, and nobody writes call c+1 data into a peer's buffer before having seen that peer's "finished call c".
 enum CommMode : int { COMM_NONE = 0, COMM_AG = 1, COMM_RS = 2 };
 struct CommParams {
   int mode, world, rank;
-  int rows_per_rank;            // M / world, multiple of BLOCK_M
+  int rows_per_rank;            // rows of one shard, multiple of BLOCK_M
   int n_comm;                   // COMM_AG: number of copy CTAs
-  uint32_t epoch;               // call counter (>= 1) for the "shard ready" handshake
-  uint32_t target;              // cumulative arrival count expected by this call (per row block)
+  int gathered_is_b;            // COMM_AG with the TN layout: the gathered operand is B, gated per k-block
+  int fill_local;               // COMM_AG: the copy CTAs also write the local shard into the local gathered buffer
+  uint32_t arrivals;            // arrivals per row block and call (AG: 1; RS: world * n_blocks)
+  uint32_t* state;              // local: [0] completed calls on this buffer set, [1] CTA exit counter
   __nv_bfloat16* peer_buf[8];   // AG: gathered buffers of all ranks; RS: staging buffers of all ranks
   uint32_t* peer_flags[8];      // per-row-block arrival counters of all ranks (AG: M/128 entries; RS: rows_per_rank/128)
-  uint32_t* chunk_flags;        // unused (kept for ABI stability)
+  uint32_t* peer_done[8];       // [world] words on every rank: peer_done[q][r] = calls rank r has finished (written by r)
+  const __nv_bfloat16* local_shard;  // AG: this rank's shard [rows_per_rank, K] (source of the pushes)
   const __nv_bfloat16* residual;  // RS: optional [rows_per_rank, N]
   __nv_bfloat16* rs_out;        // RS: [rows_per_rank, N]
   long staging_parity_off;      // RS: element offset of the staging half used by this call
+  unsigned long long timeout_ns;  // bound of every cross-GPU flag wait (0 = default)
 };
 
 // streaming (non-volatile, L1 no-allocate) 128-bit load: many of these stay in flight per thread over NVLink
@@ -82,11 +93,6 @@ LB_DEVICE uint4 ld_stream_u4(const uint4* p) {
   asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];\n"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p));
-  return v;
-}
-LB_DEVICE uint32_t ld_acquire_sys_u32(const uint32_t* a) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(a) : "memory");
   return v;
 }
 LB_DEVICE uint32_t ld_acquire_gpu_u32(const uint32_t* a) {
@@ -174,7 +180,8 @@ LB_DEVICE void stg_store_chunk(uint8_t* stg, int lane, const float (&v)[32], __n
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool FP8 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p,
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_g /* COMM_AG: the local shard of the gathered operand */, GemmParams p,
             CommParams cp) {
   using Cfg = StageCfg<BLOCK_N>;
   constexpr int NS = Cfg::NUM_STAGES;
@@ -199,17 +206,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int cta = static_cast<int>(blockIdx.x) - n_comm;
   const int cta_stride = static_cast<int>(gridDim.x) - n_comm;
   const int mbpr = cp.mode != COMM_NONE ? cp.rows_per_rank / BLOCK_M : m_blocks;
+  const bool ag_b = cp.mode == COMM_AG && cp.gathered_is_b != 0;   // TN wgrad: shards along the reduction dimension
   // row blocks are visited owner by owner: AG starts with the local rows (already resident), RS ends with them
   auto map_m = [&](int m_seq) -> int {
-    if (cp.mode == COMM_NONE) return m_seq;
+    if (cp.mode == COMM_NONE || ag_b) return m_seq;
     const int shift = (cp.mode == COMM_AG) ? 0 : 1;
     const int owner = (cp.rank + shift + m_seq / mbpr) % cp.world;
     return owner * mbpr + m_seq % mbpr;
   };
+  // work item -> (output tile, K partition).  Default: partitions of one tile are neighbours (their red.adds hit L2
+  // together).  Gathered-B wgrad: partition-major, starting with the partitions that lie in the local shard (the host
+  // makes k_splits a multiple of world and partitions never straddle a shard boundary), so every CTA has local work
+  // while the remote shards are still in flight.
+  const int mn_tiles = m_blocks * n_blocks;
+  auto decode_tile = [&](int tile, int& mn, int& split) {
+    if (ag_b) {
+      mn = tile % mn_tiles;
+      split = (tile / mn_tiles + cp.rank * (p.k_splits / cp.world)) % p.k_splits;
+    } else {
+      mn = tile / p.k_splits;
+      split = tile % p.k_splits;
+    }
+  };
+  // handshake epoch of this call: number of calls already completed on this buffer set (identical on all ranks; the
+  // last CTA to leave advances it, i.e. nobody modifies it while any CTA of this launch may still read it)
+  const uint32_t call_idx = cp.mode != COMM_NONE ? *reinterpret_cast<volatile const uint32_t*>(cp.state) : 0u;
+  const uint32_t arrive_target = (call_idx + 1u) * cp.arrivals;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (cp.mode == COMM_AG) tma_prefetch_desc(&tmap_g);
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -246,11 +273,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       constexpr int NSLOT = (NS * Cfg::STAGE_BYTES) / CHUNK < 2 * NS ? (NS * Cfg::STAGE_BYTES) / CHUNK : 2 * NS;
       static_assert(NSLOT >= 3, "ring too small");
       uint64_t* bars = full_bar;  // full_bar[NS] and empty_bar[NS] are contiguous, all initialised with count 1
-      const size_t blk_bytes = static_cast<size_t>(BLOCK_M) * p.K * 2;
+      const size_t blk_bytes = static_cast<size_t>(BLOCK_M) * (ag_b ? p.N : p.K) * 2;  // 128 rows of the gathered operand
       const int n_chunks = static_cast<int>((blk_bytes + CHUNK - 1) / CHUNK);
-      const int n_remote = (cp.world - 1) * mbpr;
+      // destinations in the order the peers consume our rows (the rank right "below" first); with `fill_local` the
+      // local gathered buffer is one more destination, served last (q / mbpr == world - 1 -> dst == rank)
+      const int n_remote = (cp.world - 1 + (cp.fill_local ? 1 : 0)) * mbpr;
       auto dst_of = [&](int q) { return (cp.rank - 1 - q / mbpr + 2 * cp.world) % cp.world; };
       auto blk_of = [&](int q) { return cp.rank * mbpr + q % mbpr; };
+      // write-after-read: before the first byte of this call goes into peer d's buffer, d must have retired its
+      // previous call on this buffer (it read what we pushed then).  Checked once per destination.
+      uint32_t dst_ok_mask = 1u << cp.rank;
       auto chunk_bytes = [&](int c) {
         const size_t off = static_cast<size_t>(c) * CHUNK;
         return static_cast<uint32_t>(blk_bytes - off < CHUNK ? blk_bytes - off : CHUNK);
@@ -271,8 +303,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t slot = issued % NSLOT;
           // the slot was last read by store #(issued - NSLOT); at least one newer store exists (fill bound above)
           if (issued >= static_cast<uint32_t>(NSLOT)) tma_store_wait_read<1>();
-          const uint8_t* sp = reinterpret_cast<const uint8_t*>(cp.peer_buf[cp.rank]) +
-                              static_cast<size_t>(blk_of(q_ld)) * blk_bytes + static_cast<size_t>(c_ld) * CHUNK;
+          const uint8_t* sp = reinterpret_cast<const uint8_t*>(cp.local_shard) +
+                              static_cast<size_t>(q_ld % mbpr) * blk_bytes + static_cast<size_t>(c_ld) * CHUNK;
           const uint32_t bytes = chunk_bytes(c_ld);
           mbar_arrive_expect_tx(&bars[slot], bytes);
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
@@ -287,7 +319,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         const uint32_t slot = stored % NSLOT;
         mbar_wait(&bars[slot], (stored / NSLOT) & 1);
-        uint8_t* dp = reinterpret_cast<uint8_t*>(cp.peer_buf[dst_of(q_st)]) + static_cast<size_t>(blk_of(q_st)) * blk_bytes +
+        const int dst = dst_of(q_st);
+        if (!((dst_ok_mask >> dst) & 1u)) {
+          spin_wait_ge_sys(cp.peer_done[cp.rank] + dst, call_idx, cp.timeout_ns, /*what=*/3, dst);
+          dst_ok_mask |= 1u << dst;
+        }
+        uint8_t* dp = reinterpret_cast<uint8_t*>(cp.peer_buf[dst]) + static_cast<size_t>(blk_of(q_st)) * blk_bytes +
                       static_cast<size_t>(c_st) * CHUNK;
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dp),
                      "r"(smem_u32(smem + slot * CHUNK)), "r"(chunk_bytes(c_st))
@@ -299,7 +336,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tma_store_wait<0>();
             signal(pend_flag);
           }
-          pend_flag = cp.peer_flags[dst_of(q_st)] + blk_of(q_st);
+          // (the local fill needs no arrival: its consumers are later kernels of this stream)
+          pend_flag = dst == cp.rank ? nullptr : cp.peer_flags[dst] + blk_of(q_st);
           pend_at = stored + 2;
           c_st = 0;
           q_st += n_comm;
@@ -310,35 +348,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           pend_flag = nullptr;
         }
       }
-      if (pend_flag != nullptr) {
-        tma_store_wait<0>();
-        signal(pend_flag);
-      }
+      tma_store_wait<0>();   // nothing may still read the ring (or be in flight to the local buffer) when the CTA exits
+      if (pend_flag != nullptr) signal(pend_flag);
     }
   } else if (warp_idx == 0) {
     // ======================= TMA producer =======================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      int waited_blk = -1;
       for (int tile = cta; tile < num_tiles; tile += cta_stride) {
-        const int split = tile % p.k_splits;
-        const int mn = tile / p.k_splits;
+        int split, mn;
+        decode_tile(tile, mn, split);
         const int m_blk = map_m(mn / n_blocks), n_blk = mn % n_blocks;
-        if (cp.mode == COMM_AG && m_blk / mbpr != cp.rank) {
-          // rows owned by a peer: wait until that peer's copy CTAs have pushed this row block into our buffer
-          while (static_cast<int32_t>(ld_acquire_sys_u32(cp.peer_flags[cp.rank] + m_blk) - cp.target) < 0) {
-          }
+        // gathered A: rows of the local shard come straight from the shard's own tensor map, rows owned by a peer
+        // from the gathered buffer once that peer's copy CTAs have pushed the row block (arrival counter)
+        const bool a_local = cp.mode == COMM_AG && !ag_b && m_blk / mbpr == cp.rank;
+        if (cp.mode == COMM_AG && !ag_b && !a_local) {
+          spin_wait_ge_sys(cp.peer_flags[cp.rank] + m_blk, arrive_target, cp.timeout_ns, /*what=*/1, m_blk / mbpr);
           asm volatile("fence.proxy.async.global;\n" ::: "memory");
         }
+        const CUtensorMap* map_a = a_local ? &tmap_g : &tmap_a;
+        const int m_row = a_local ? (m_blk - cp.rank * mbpr) * BLOCK_M : m_blk * BLOCK_M;
         const int kb0 = split * p.k_per_split;
         const int kb1 = min(kb0 + p.k_per_split, k_blocks_total);
         for (int kb = kb0; kb < kb1; ++kb) {
+          // gathered B (TN): k-block kb = token rows [64 kb, 64 kb + 64) = half of row block kb / 2
+          bool b_local = false;
+          if (ag_b) {
+            const int blk = (kb * BLOCK_K) / BLOCK_M;
+            b_local = blk / mbpr == cp.rank;
+            if (!b_local && blk != waited_blk) {
+              spin_wait_ge_sys(cp.peer_flags[cp.rank] + blk, arrive_target, cp.timeout_ns, /*what=*/1, blk / mbpr);
+              asm volatile("fence.proxy.async.global;\n" ::: "memory");
+              waited_blk = blk;
+            }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(sa, map_a, &full_bar[stage], kb * BLOCK_K, m_row);
           } else {
 #pragma unroll
             for (int a = 0; a < BLOCK_M / 64; ++a)
@@ -347,9 +398,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if constexpr (!B_MN) {
             tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
           } else {
+            const CUtensorMap* map_b = b_local ? &tmap_g : &tmap_b;
+            const int k_row = b_local ? kb * BLOCK_K - cp.rank * cp.rows_per_rank : kb * BLOCK_K;
 #pragma unroll
             for (int a = 0; a < BLOCK_N / 64; ++a)
-              tma_load_2d(sb + a * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_blk * BLOCK_N + a * 64, kb * BLOCK_K);
+              tma_load_2d(sb + a * (BLOCK_K * 128), map_b, &full_bar[stage], n_blk * BLOCK_N + a * 64, k_row);
           }
           if (++stage == NS) {
             stage = 0;
@@ -367,7 +420,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cta; tile < num_tiles; tile += cta_stride) {
-      const int split = tile % p.k_splits;
+      int split, mn_unused;
+      decode_tile(tile, mn_unused, split);
       const int kb0 = split * p.k_per_split;
       const int kb1 = min(kb0 + p.k_per_split, k_blocks_total);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -414,8 +468,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint32_t acc_phase = 0;
     float alpha = 1.0f;
     if constexpr (FP8) alpha = __ldg(p.deq_a) * __ldg(p.deq_b);
+    if (cp.mode == COMM_RS) {
+      // write-after-read on the owners' staging buffers: every owner must have retired its previous call on this
+      // buffer set (its reduce phase read what we stored then) before the first partial tile of this call lands
+      if (lane == 0) {
+        for (int q = 0; q < cp.world; ++q)
+          if (q != cp.rank) spin_wait_ge_sys(cp.peer_done[cp.rank] + q, call_idx, cp.timeout_ns, /*what=*/4, q);
+      }
+      __syncwarp();
+    }
     for (int tile = cta; tile < num_tiles; tile += cta_stride) {
-      const int mn = tile / p.k_splits;
+      int mn, split_unused;
+      decode_tile(tile, mn, split_unused);
       const int m_blk = map_m(mn / n_blocks), n_blk = mn % n_blocks;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
@@ -562,11 +626,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (threadIdx.x == 64) {
           __threadfence_system();
           const int owner = m_blk / mbpr;
-          // arrivals are counted in units of 64 columns so that the expected total (world * N / 64) does not
-          // depend on the tile width chosen by the heuristic
-          asm volatile("red.release.sys.global.add.u32 [%0], %1;\n" ::"l"(cp.peer_flags[owner] + (m_blk % mbpr)),
-                       "r"(static_cast<uint32_t>(BLOCK_N / 64))
-                       : "memory");
+          // one arrival per (source rank, column tile): world * n_blocks per row block and call
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;\n" ::"l"(cp.peer_flags[owner] + (m_blk % mbpr)) : "memory");
         }
       }
       if (++acc == 2) {
@@ -583,10 +644,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const __nv_bfloat16* stag = cp.peer_buf[cp.rank] + cp.staging_parity_off;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int lm = u / col_groups, cg = u % col_groups;
-      if (threadIdx.x == 0) {
-        while (static_cast<int32_t>(ld_acquire_sys_u32(cp.peer_flags[cp.rank] + lm) - cp.target) < 0) {
-        }
-      }
+      if (threadIdx.x == 0) spin_wait_ge_sys(cp.peer_flags[cp.rank] + lm, arrive_target, cp.timeout_ns, /*what=*/2, lm);
       __syncthreads();
       const int c_lo = cg * 256;
       const int c_n = min(256, p.N - c_lo) / 8;  // vectors of 8 per row in this column group
@@ -625,6 +683,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp_idx == 1) {
     tc_fence_after_sync();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+  if (cp.mode != COMM_NONE && threadIdx.x == 0) {
+    // retire: the last CTA to get here advances the call counter and tells every peer that this rank is done reading
+    // (AG: its gathered buffer, RS: its staging buffer) for call `call_idx`
+    __threadfence();
+    const uint32_t prev = atomicAdd(cp.state + 1, 1u);
+    if (prev == gridDim.x - 1) {
+      cp.state[1] = 0;
+      cp.state[0] = call_idx + 1u;
+      __threadfence_system();
+      for (int q = 0; q < cp.world; ++q) {
+        if (q == cp.rank) continue;
+        asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(cp.peer_done[q] + cp.rank), "r"(call_idx + 1u) : "memory");
+      }
+    }
   }
 }
 
@@ -717,8 +790,8 @@ bool operand_tmap(CUtensorMap* m, const void* ptr, bool mn_major, int rows_or_co
 }
 
 template <int BN, bool AMN, bool BMN, int EPI, bool FP8 = false>
-cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const lb::GemmParams& p, const lb::CommParams& cp,
-                       int grid, cudaStream_t stream) {
+cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tg, const lb::GemmParams& p,
+                       const lb::CommParams& cp, int grid, cudaStream_t stream) {
   using Cfg = lb::StageCfg<BN>;
   auto kern = lb::gemm_kernel<BN, AMN, BMN, EPI, FP8>;
   static bool configured = false;
@@ -727,22 +800,22 @@ cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const lb::G
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, lb::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p, cp);
+  kern<<<grid, lb::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tg, p, cp);
   return cudaGetLastError();
 }
 
 template <bool AMN, bool BMN, int EPI, bool FP8 = false>
-cudaError_t launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const lb::GemmParams& p,
+cudaError_t launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tg, const lb::GemmParams& p,
                       const lb::CommParams& cp, int grid, cudaStream_t s) {
   switch (bn) {
     case 256:
-      return launch_cfg<256, AMN, BMN, EPI, FP8>(ta, tb, p, cp, grid, s);
+      return launch_cfg<256, AMN, BMN, EPI, FP8>(ta, tb, tg, p, cp, grid, s);
     case 192:
-      return launch_cfg<192, AMN, BMN, EPI, FP8>(ta, tb, p, cp, grid, s);
+      return launch_cfg<192, AMN, BMN, EPI, FP8>(ta, tb, tg, p, cp, grid, s);
     case 128:
-      return launch_cfg<128, AMN, BMN, EPI, FP8>(ta, tb, p, cp, grid, s);
+      return launch_cfg<128, AMN, BMN, EPI, FP8>(ta, tb, tg, p, cp, grid, s);
     default:
-      return launch_cfg<64, AMN, BMN, EPI, FP8>(ta, tb, p, cp, grid, s);
+      return launch_cfg<64, AMN, BMN, EPI, FP8>(ta, tb, tg, p, cp, grid, s);
   }
 }
 
@@ -762,8 +835,9 @@ static bool wgrad_rmw() {
 
 static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo, int layout,
                      int epi, const void* bias, int act, void* pre_out, const void* pre_in, int force_bn,
-                     int force_splits, const lb::CommParams& cp, cudaStream_t stream, const float* deq_a = nullptr,
+                     int force_splits, const lb::CommParams& cp_in, cudaStream_t stream, const float* deq_a = nullptr,
                      const float* deq_b = nullptr, float* colsum = nullptr) {
+  lb::CommParams cp = cp_in;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (N % 8) || (ldo % 4)) return -1;
   const bool a_mn = (layout == 2);
@@ -798,7 +872,27 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   int splits = 1;
   if (epi == 2) {
     splits = force_splits;
-    if (splits <= 0) {
+    const bool ag_b = cp.mode == lb::COMM_AG && cp.gathered_is_b;
+    if (ag_b) {
+      // gathered-B wgrad: the partitions must not straddle a shard boundary and their number must be a multiple of the
+      // group size (the kernel starts every rank on the partitions of its own shard)
+      const int kb_per_rank = cp.rows_per_rank / lb::BLOCK_K;
+      const long tiles = (long)m_blocks * n_blocks;
+      const int gemm_ctas = sms - cp.n_comm;
+      double best = 1e30;
+      splits = cp.world;
+      for (int j = 1; j <= 16 && j <= kb_per_rank; ++j) {
+        if (kb_per_rank % j) continue;
+        if (j > 1 && kb_per_rank / j < 4) break;
+        const int c = cp.world * j;
+        const long rounds = (tiles * c + gemm_ctas - 1) / gemm_ctas;
+        const double cost = (double)rounds * (kb_per_rank / j + 6.0);
+        if (cost < best - 1e-9) {
+          best = cost;
+          splits = c;
+        }
+      }
+    } else if (splits <= 0) {
       // Persistent CTAs take work items round-robin, so the kernel lasts ceil(items / SMs) rounds of one K partition
       // each: pick the split count that minimises rounds x (k-blocks per partition + a fixed per-item cost for
       // pipeline fill and the fp32 red.add epilogue).  (A plain ceil(SMs / tiles) overshoots into a second round:
@@ -845,9 +939,20 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   p.deq_a = deq_a;
   p.deq_b = deq_b;
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tg;
   if (!operand_tmap(&ta, a, a_mn, M, K, lda, lb::BLOCK_M)) return -2;
   if (!operand_tmap(&tb, b, b_mn, N, K, ldb, bn)) return -2;
+  tg = ta;
+  if (cp.mode == lb::COMM_AG) {
+    // tensor map of the local shard of the gathered operand: [rows_per_rank, K] rows of A (NT/NN), or rows_per_rank
+    // reduction rows of B (TN)
+    const bool ok = cp.gathered_is_b ? operand_tmap(&tg, cp.local_shard, true, N, cp.rows_per_rank, ldb, bn)
+                                     : operand_tmap(&tg, cp.local_shard, false, cp.rows_per_rank, K, lda, lb::BLOCK_M);
+    if (!ok) return -2;
+    cp.arrivals = 1;
+  } else if (cp.mode == lb::COMM_RS) {
+    cp.arrivals = (uint32_t)(cp.world * n_blocks);
+  }
   const long num_tiles = (long)m_blocks * n_blocks * p.k_splits;
   int grid = (int)(num_tiles < sms ? num_tiles : sms);
   if (cp.mode == lb::COMM_AG) {
@@ -858,19 +963,19 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   cudaError_t e;
   if (p.fp8) {
     if (layout != 0 || epi != 0 || cp.mode != lb::COMM_NONE) return -7;
-    e = launch_bn<false, false, lb::EPI_BF16, true>(bn, ta, tb, p, cp, grid, stream);
+    e = launch_bn<false, false, lb::EPI_BF16, true>(bn, ta, tb, tg, p, cp, grid, stream);
   } else if (layout == 0) {
-    if (epi == 0) e = launch_bn<false, false, lb::EPI_BF16>(bn, ta, tb, p, cp, grid, stream);
-    else if (epi == 1) e = launch_bn<false, false, lb::EPI_F32>(bn, ta, tb, p, cp, grid, stream);
-    else e = launch_bn<false, false, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, cp, grid, stream);
+    if (epi == 0) e = launch_bn<false, false, lb::EPI_BF16>(bn, ta, tb, tg, p, cp, grid, stream);
+    else if (epi == 1) e = launch_bn<false, false, lb::EPI_F32>(bn, ta, tb, tg, p, cp, grid, stream);
+    else e = launch_bn<false, false, lb::EPI_ATOMIC_F32>(bn, ta, tb, tg, p, cp, grid, stream);
   } else if (layout == 1) {
-    if (epi == 0) e = launch_bn<false, true, lb::EPI_BF16>(bn, ta, tb, p, cp, grid, stream);
-    else if (epi == 1) e = launch_bn<false, true, lb::EPI_F32>(bn, ta, tb, p, cp, grid, stream);
-    else e = launch_bn<false, true, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, cp, grid, stream);
+    if (epi == 0) e = launch_bn<false, true, lb::EPI_BF16>(bn, ta, tb, tg, p, cp, grid, stream);
+    else if (epi == 1) e = launch_bn<false, true, lb::EPI_F32>(bn, ta, tb, tg, p, cp, grid, stream);
+    else e = launch_bn<false, true, lb::EPI_ATOMIC_F32>(bn, ta, tb, tg, p, cp, grid, stream);
   } else {
-    if (epi == 0) e = launch_bn<true, true, lb::EPI_BF16>(bn, ta, tb, p, cp, grid, stream);
-    else if (epi == 1) e = launch_bn<true, true, lb::EPI_F32>(bn, ta, tb, p, cp, grid, stream);
-    else e = launch_bn<true, true, lb::EPI_ATOMIC_F32>(bn, ta, tb, p, cp, grid, stream);
+    if (epi == 0) e = launch_bn<true, true, lb::EPI_BF16>(bn, ta, tb, tg, p, cp, grid, stream);
+    else if (epi == 1) e = launch_bn<true, true, lb::EPI_F32>(bn, ta, tb, tg, p, cp, grid, stream);
+    else e = launch_bn<true, true, lb::EPI_ATOMIC_F32>(bn, ta, tb, tg, p, cp, grid, stream);
   }
   return (int)e;
 }
@@ -923,35 +1028,60 @@ extern "C" int lb_gemm_bf16_bias_residual(const void* x, const void* w, void* ou
   return gemm_impl(x, w, out, M, N, K, lda, ldb, N, 0, 0, bias, lb::ACT_RESADD, nullptr, residual, 0, 0, cp, stream);
 }
 
-// Tensor-parallel fused collective GEMMs (NT layout, bf16 output).
-//   mode 1 (AG->GEMM): a = local gathered buffer [M, K] (rows of peers are pulled inside the kernel), out [M, N]
-//   mode 2 (GEMM->RS): a = local [M, K_shard]; partial tiles go to the owners' staging buffers; rs_out [M/world, N]
-extern "C" int lb_gemm_bf16_comm(const void* a, const void* b, void* out, int M, int N, int K, int layout,
-                                 const void* bias, int act, void* pre_out, int mode, int world, int rank, unsigned epoch,
-                                 unsigned target, const long* peer_buf, const long* peer_flags, void* chunk_flags,
-                                 const void* residual, void* rs_out, long staging_parity_off, int n_comm,
-                                 cudaStream_t stream) {
-  if (world > 8 || M % (lb::BLOCK_M * world) != 0) return -4;
-  if (mode == 2 && (N % 256) != 0) return -5;
+// Tensor-parallel fused collective GEMMs.
+//   mode 1 (AG->GEMM), layout 0/1: a = local gathered buffer [M, K] (remote rows are pushed into it by the peers' copy
+//           CTAs), local_shard = this rank's [M/world, K] rows, out [M, N] bf16 (+bias, +act with pre-activation copy,
+//           or x act'(pre_in) for a dgrad fused with the activation backward, + column sums for the bias gradient)
+//   mode 1, layout 2 (gathered-B wgrad): a = dy [T, M] (T tokens), b = local gathered buffer [T, N], local_shard =
+//           this rank's [T/world, N] rows of it, out [M, N] fp32: epi 2 accumulates (red.add), epi 1 stores
+//   mode 2 (GEMM->RS), layout 0/1: a = local [M, K_shard]; partial tiles go to the owners' staging buffers;
+//           rs_out [M/world, N] = sum over ranks (+bias +residual)
+static unsigned long long spin_timeout_ns() {
+  static unsigned long long v = ~0ull;
+  if (v == ~0ull) {
+    const char* e = getenv("LIBAI_B200_SPIN_TIMEOUT_MS");
+    v = (e != nullptr && atoll(e) > 0) ? (unsigned long long)atoll(e) * 1000000ull : 0ull;
+  }
+  return v;
+}
+
+extern "C" int lb_gemm_bf16_comm(const void* a, const void* b, void* out, int M, int N, int K, int layout, int epi,
+                                 const void* bias, int act, void* pre_out, const void* pre_in, float* colsum, int mode,
+                                 int world, int rank, const long* peer_buf, const long* peer_flags, const long* peer_done,
+                                 void* state, const void* local_shard, int fill_local, const void* residual, void* rs_out,
+                                 long staging_parity_off, int n_comm, cudaStream_t stream) {
+  if (world > 8 || world < 2 || state == nullptr) return -4;
+  const int gathered_rows = (mode == 1 && layout == 2) ? K : M;   // extent of the dimension that is split over ranks
+  if (gathered_rows % (lb::BLOCK_M * world) != 0) return -4;
+  if (layout < 0 || layout > 2 || (layout == 2 && mode != 1)) return -6;
   lb::CommParams cp;
   memset(&cp, 0, sizeof(cp));
   cp.mode = mode;
   cp.world = world;
   cp.rank = rank;
-  cp.rows_per_rank = M / world;
-  cp.n_comm = n_comm;
-  cp.epoch = epoch;
-  cp.target = target;
+  cp.rows_per_rank = gathered_rows / world;
+  cp.n_comm = mode == 1 ? n_comm : 0;
+  cp.gathered_is_b = (mode == 1 && layout == 2) ? 1 : 0;
+  cp.fill_local = fill_local;
+  cp.state = reinterpret_cast<uint32_t*>(state);
   for (int i = 0; i < world; ++i) {
     cp.peer_buf[i] = reinterpret_cast<__nv_bfloat16*>(peer_buf[i]);
     cp.peer_flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]);
+    cp.peer_done[i] = reinterpret_cast<uint32_t*>(peer_done[i]);
   }
-  cp.chunk_flags = reinterpret_cast<uint32_t*>(chunk_flags);
+  cp.local_shard = reinterpret_cast<const __nv_bfloat16*>(local_shard);
   cp.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   cp.rs_out = reinterpret_cast<__nv_bfloat16*>(rs_out);
   cp.staging_parity_off = staging_parity_off;
+  cp.timeout_ns = spin_timeout_ns();
+  if (mode == 1 && local_shard == nullptr) return -4;
+  if (colsum != nullptr && (reinterpret_cast<uintptr_t>(colsum) & 15)) return -8;
+  int lda, ldb, ldo;
+  if (layout == 0) { lda = K; ldb = K; ldo = N; }
+  else if (layout == 1) { lda = K; ldb = N; ldo = N; }
+  else { lda = M; ldb = N; ldo = N; }
+  if (mode == 2) epi = 0;
   // the RS epilogue writes into the staging buffers; `out` is unused there (pass any valid pointer)
-  if (layout != 0 && layout != 1) return -6;
-  return gemm_impl(a, b, mode == 2 ? rs_out : out, M, N, K, K, layout == 0 ? K : N, N, layout, 0, bias, act, pre_out, nullptr, 0, 1,
-                   cp, stream);
+  return gemm_impl(a, b, mode == 2 ? rs_out : out, M, N, K, lda, ldb, ldo, layout, epi, bias, act, pre_out, pre_in, 0,
+                   mode == 1 && layout == 2 ? 0 : 1, cp, stream, nullptr, nullptr, colsum);
 }

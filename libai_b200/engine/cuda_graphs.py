@@ -11,9 +11,13 @@ optimizer's persistent fp32 ``main_grad`` buffer and return ``None`` to autograd
 descriptors they were launched with, which are by-value kernel parameters) are part of the captured backward graph and
 replay against the same addresses.  Parameters live in the optimizer's flat buffer, i.e. at fixed addresses as well.
 
-Not captured: embedding, LM head + loss, optimizer, and every collective (their flag epochs are kernel arguments that
-change per step).  Restrictions (checked): one tensor argument per block, no pipeline parallelism, no activation
-checkpointing, dropout probability 0 inside the blocks (a captured Philox offset would replay the same mask).
+Tensor-parallel blocks are captured too when the collectives are the fused ones (``train.dist.fused_tp_comm``): the
+AG→GEMM / GEMM→RS kernels keep their call counters, arrival targets and write credits in device memory and advance them
+themselves, so a replay is indistinguishable from a fresh launch.
+
+Not captured: embedding, LM head + loss, optimizer, NCCL collectives.  Restrictions (checked): one tensor argument per
+block, no pipeline parallelism, no activation checkpointing.  Dropout inside captured blocks draws its Philox offset
+from a device counter that the dropout kernels advance (``ops/functional.py``), so replays produce fresh masks.
 """
 from __future__ import annotations
 
@@ -89,11 +93,12 @@ def enable_for_model(model: nn.Module, example_batch: dict) -> bool:
     from libai_b200.utils import distributed as dutil
 
     topo = dutil.get_dist_util()
-    if (topo.pipeline_parallel_size > 1 or topo.tensor_parallel_size > 1
-            or getattr(model, "activation_checkpoint", False)):
-        # (1F1B keeps several micro-batches in flight per block; the fused tensor-parallel collectives take a
-        # per-call epoch as kernel argument; checkpointing re-runs the forward inside backward)
-        logger.warning("cuda graphs: model parallelism / activation checkpointing — not captured")
+    if (topo.pipeline_parallel_size > 1 or getattr(model, "activation_checkpoint", False)
+            or (topo.tensor_parallel_size > 1 and not topo.fused_tp_comm)):
+        # (1F1B keeps several micro-batches in flight per block; checkpointing re-runs the forward inside backward;
+        # tensor parallelism is captured only in its fused form — AG→GEMM / GEMM→RS kernels whose handshake state lives
+        # in device memory (ops/comm_gemm.py) — the NCCL form keeps eager launches)
+        logger.warning("cuda graphs: pipeline parallelism / NCCL-form tensor parallelism / activation checkpointing — not captured")
         return False
     layers = model.stage_layers() if hasattr(model, "stage_layers") else None
     if not isinstance(layers, nn.ModuleList) or len(layers) == 0:

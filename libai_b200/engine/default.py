@@ -107,12 +107,40 @@ def _compile_dependencies():
     dutil.synchronize()
 
 
+def _resolve_auto_tensor_parallel_mode(cfg):
+    """``train.dist.sequence_parallel / fused_tp_comm = "auto"``: on for models that declare
+    ``supports_sequence_parallel`` (GPT-2, BERT, Llama family) — their tensor-parallel blocks then run on token shards
+    with the collectives inside the GEMM kernels (the B200 product path) — off for the others, which keep the
+    reference's replicated-activation form (libai/layers/linear.py:123-149)."""
+    d = try_get_key(cfg, "train.dist")
+    if d is None:
+        return
+    sp, fused = try_get_key(d, "sequence_parallel", default=False), try_get_key(d, "fused_tp_comm", default=False)
+    if not (isinstance(sp, str) or isinstance(fused, str)):
+        return
+    supported = False
+    target = try_get_key(cfg, "model._target_")
+    if target is not None:
+        try:
+            from libai_b200.config.instantiate import _resolve_callable
+
+            cls = _resolve_callable(target) if isinstance(target, str) else target
+            supported = bool(getattr(cls, "supports_sequence_parallel", False))
+        except Exception:   # unknown target: stay with the conservative form
+            supported = False
+    if isinstance(sp, str):
+        d.sequence_parallel = supported
+    if isinstance(fused, str):
+        d.fused_tp_comm = bool(d.sequence_parallel) and supported
+
+
 def default_setup(cfg, args):
     """Common start-up: output dir + logger, distributed topology, batch sizes, config dump."""
     output_dir = try_get_key(cfg, "train.output_dir")
     if dutil.get_rank() == 0 and output_dir:
         os.makedirs(output_dir, exist_ok=True)
     cfg.train.resume = bool(getattr(args, "resume", False))
+    _resolve_auto_tensor_parallel_mode(cfg)
     dutil.setup_dist_util(cfg.train.dist)
     rank = dutil.get_rank()
     logger = setup_logger(output_dir, distributed_rank=rank)

@@ -195,19 +195,13 @@ class StepTrainer(TrainerBase):
             out.append(get_batch(data, input_placement_device, mixup))
         return out
 
-    def run_step(self, get_batch: Callable, input_placement_device: str = "cuda"):
-        assert self.model.training, "[StepTrainer] model was changed to eval mode!"
+    def train_on_batches(self, batches):
+        """One optimizer step over already staged micro-batches (dicts of device tensors): forward/backward of every
+        micro-batch (1F1B schedule under pipeline parallelism), gradient sync, clipping, update.  Returns the
+        micro-batch averaged loss dict (device tensors; ``None`` on non-last pipeline stages).  Public so that callers
+        that stage their own data (``bench.py``) run exactly the trainer's step."""
         topo = dutil.get_dist_util()
-        t0 = time.perf_counter()
-        batches = self._next_batches(get_batch, input_placement_device)
-        data_time = time.perf_counter() - t0
-        use_events = topo.device_type == "cuda"
-        if use_events:
-            if self._ev is None:
-                self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            self._ev[0].record()
-
-        if self.cuda_graphs and not self._graphs_tried and use_events:
+        if self.cuda_graphs and not self._graphs_tried and topo.device_type == "cuda":
             # first step: capture forward+backward of every transformer block into CUDA graphs (engine/cuda_graphs.py)
             from libai_b200.engine.cuda_graphs import enable_for_model
 
@@ -223,7 +217,7 @@ class StepTrainer(TrainerBase):
             loss_dict = self._pipeline.run(batches)
         else:
             loss_dict = None
-            inv = 1.0 / self.grad_acc_steps
+            inv = 1.0 / len(batches)
             for k, batch in enumerate(batches):
                 self._arm_grad_overlap(k == len(batches) - 1)
                 out = self.model(**batch)
@@ -236,6 +230,21 @@ class StepTrainer(TrainerBase):
         if self.loss_scaler is not None:
             self.loss_scaler.check_and_update(self.optimizer)
         self.optimizer.step()
+        return loss_dict
+
+    def run_step(self, get_batch: Callable, input_placement_device: str = "cuda"):
+        assert self.model.training, "[StepTrainer] model was changed to eval mode!"
+        topo = dutil.get_dist_util()
+        t0 = time.perf_counter()
+        batches = self._next_batches(get_batch, input_placement_device)
+        data_time = time.perf_counter() - t0
+        use_events = topo.device_type == "cuda"
+        if use_events:
+            if self._ev is None:
+                self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self._ev[0].record()
+
+        loss_dict = self.train_on_batches(batches)
 
         device_time = None
         if use_events:

@@ -165,6 +165,10 @@ class MultiheadAttention(nn.Module):
                         and (self.output_dropout_prob == 0.0 or not self.training)):
                     # bias + residual in the epilogue of the output projection
                     return OF.linear_bias_residual(context, self.dense.weight, self.dense.bias, residual)
+                if residual is not None and (self.output_dropout_prob == 0.0 or not self.training):
+                    fused = self.dense.fused_bias_residual(context, residual)   # GEMM→RS + bias + residual, one kernel
+                    if fused is not None:
+                        return fused
                 output, bias = self.dense(context)
                 return OF.bias_dropout_add(output, bias, residual, self.output_dropout_prob, self.training)
             qkv = qkv_packed.permute(0, 2, 1, 3)

@@ -62,6 +62,15 @@ class Linear1D(nn.Module):
             # added after the reduce-scatter, i.e. on token shards: its gradient is partial per TP rank
             self.bias.sequence_parallel = dutil.get_dist_util().sequence_parallel
 
+    def fused_bias_residual(self, x, residual):
+        """Row-parallel fast path of the block-output projections under fused tensor parallelism:
+        ``reduce_scatter(x @ Wᵀ) + bias + residual`` in ONE kernel (bias and residual are added by the reduce phase of
+        the GEMM→RS kernel).  Returns ``None`` when the fused kernel does not apply (caller falls back)."""
+        topo = dutil.get_dist_util()
+        if not (topo.fused_tp_comm and self.parallel == "row" and x.is_cuda and x.dtype == self.weight.dtype):
+            return None
+        return self._forward_fused(x, self.bias, None, topo, residual=residual)
+
     def forward(self, x, act=None):
         """``act`` (optional activation name) is fused into the GEMM epilogue when the bias is
         applied here (i.e. not with ``skip_bias_add``)."""
@@ -88,7 +97,7 @@ class Linear1D(nn.Module):
             return y, self.bias
         return y
 
-    def _forward_fused(self, x, bias_now, act, topo):
+    def _forward_fused(self, x, bias_now, act, topo, residual=None):
         """AG->GEMM / GEMM->RS with the collective inside the tcgen05 kernel (None = shape unsupported)."""
         from libai_b200.ops import comm_gemm, use_native
 
@@ -104,7 +113,9 @@ class Linear1D(nn.Module):
         M, N, K = x2.shape[0], self.weight.shape[0], x2.shape[1]
         if not comm_gemm.fused_supported(M, N, K, t) or act is not None:
             return None
-        return comm_gemm.row_parallel_linear(x2.contiguous(), self.weight, bias_now, None, topo.tp_group)
+        if residual is not None:
+            residual = residual.reshape(-1, N).contiguous()
+        return comm_gemm.row_parallel_linear(x2.contiguous(), self.weight, bias_now, residual, topo.tp_group)
 
     def extra_repr(self) -> str:
         return "in_features={}, out_features={}, bias={}, parallel={}".format(

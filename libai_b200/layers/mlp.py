@@ -60,6 +60,19 @@ class MLP(nn.Module):
             out = OF.mlp(x, self.dense_h_to_4h.weight, self.dense_h_to_4h.bias, self.dense_4h_to_h.weight, "gelu")
             out, bias = mappings.reduce_from_tp(out), self.dense_4h_to_h.bias
         else:
+            if (topo.fused_tp_comm and hidden_states.is_cuda and hidden_states.dtype == torch.bfloat16
+                    and hidden_states.dim() == 2 and (self.output_dropout_prob == 0.0 or not self.training)):
+                # both linears + their collectives + bias/GELU/bias/residual as one autograd node (ops/comm_gemm.py)
+                from libai_b200.ops import comm_gemm, use_native
+
+                t = topo.tensor_parallel_size
+                M, K = hidden_states.shape[0] * t, hidden_states.shape[1]
+                f_loc = self.dense_h_to_4h.weight.shape[0]
+                if (use_native(hidden_states) and comm_gemm.fused_supported(M, f_loc, K, t)
+                        and comm_gemm.fused_supported(M, K, f_loc, t)):
+                    res = residual.reshape(-1, K).contiguous() if residual is not None else None
+                    return comm_gemm.tp_mlp(hidden_states.contiguous(), self.dense_h_to_4h.weight, self.dense_h_to_4h.bias,
+                                            self.dense_4h_to_h.weight, self.dense_4h_to_h.bias, res, "gelu", topo.tp_group)
             inter = self.dense_h_to_4h(hidden_states, act="gelu")
             out, bias = self.dense_4h_to_h(inter)
         return OF.bias_dropout_add(out, bias, residual, self.output_dropout_prob, self.training)

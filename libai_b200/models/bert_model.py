@@ -136,6 +136,10 @@ class BertLoss(nn.Module):
 class BertModel(nn.Module, PipelineStageMixin):
     """Bare BERT encoder: returns ``(sequence_output, pooled_output)``."""
 
+    # `train.dist.sequence_parallel = "auto"` resolves to True for this model (token-sharded activations between
+    # the tensor-parallel blocks are handled by its embeddings / heads)
+    supports_sequence_parallel = True
+
     @configurable
     def __init__(self, vocab_size, hidden_size, hidden_layers, num_attention_heads, intermediate_size,
                  hidden_dropout_prob, attention_probs_dropout_prob, max_position_embeddings, num_tokentypes=2,
@@ -245,6 +249,10 @@ class BertPreTrainingHeads(nn.Module):
 
 class BertForPreTraining(nn.Module, PipelineStageMixin):
     """BERT with the masked-LM head and the sentence-order (binary) head."""
+
+    # `train.dist.sequence_parallel = "auto"` resolves to True for this model (token-sharded activations between
+    # the tensor-parallel blocks are handled by its embeddings / heads)
+    supports_sequence_parallel = True
 
     def __init__(self, cfg):
         super().__init__()

@@ -109,6 +109,10 @@ class Transformer(nn.Module):
 class GPTModel(nn.Module, PipelineStageMixin):
     """GPT-2; ``forward`` returns the (vocab-split) logits."""
 
+    # `train.dist.sequence_parallel = "auto"` resolves to True for this model (token-sharded activations between
+    # the tensor-parallel blocks are handled by its embeddings / heads)
+    supports_sequence_parallel = True
+
     @configurable
     def __init__(
         self, hidden_layers, vocab_size, hidden_size, ffn_hidden_size, num_attention_heads,
@@ -198,6 +202,10 @@ class GPTLoss(nn.Module):
 
 class GPTForPreTraining(nn.Module, PipelineStageMixin):
     """GPT-2 with the LM loss on top."""
+
+    # `train.dist.sequence_parallel = "auto"` resolves to True for this model (token-sharded activations between
+    # the tensor-parallel blocks are handled by its embeddings / heads)
+    supports_sequence_parallel = True
 
     def __init__(self, cfg) -> None:
         super().__init__()

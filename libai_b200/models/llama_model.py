@@ -259,6 +259,10 @@ class SFTLoss(nn.Module):
 
 
 class LlamaForCausalLM(nn.Module, PipelineStageMixin, Generator):
+
+    # `train.dist.sequence_parallel = "auto"` resolves to True for this model (token-sharded activations between
+    # the tensor-parallel blocks are handled by its embeddings / heads)
+    supports_sequence_parallel = True
     @configurable
     def __init__(self, hidden_layers, vocab_size, hidden_size, intermediate_size, num_attention_heads,
                  max_position_embeddings=1024, rms_norm_eps=1e-5, initializer_range=0.02,

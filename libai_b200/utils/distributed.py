@@ -159,9 +159,15 @@ class DistributedTopology:
         # Megatron-style sequence parallelism inside the TP region (new vs. the reference):
         # activations between TP blocks are sharded over tokens, col/row linears become
         # all-gather->GEMM / GEMM->reduce-scatter.
-        self.sequence_parallel = bool(try_get_key(cfg, "sequence_parallel", default=False)) and tp > 1
+        # "auto" (the default of configs/common/train.py) is resolved by `engine.default_setup` from the model class
+        # (`supports_sequence_parallel`); an unresolved "auto" counts as off.
+        def _flag(key):
+            v = try_get_key(cfg, key, default=False)
+            return False if isinstance(v, str) else bool(v)
+
+        self.sequence_parallel = _flag("sequence_parallel") and tp > 1
         # run the SP collectives inside the GEMM kernels (AG->GEMM / GEMM->RS over NVLink peer memory)
-        self.fused_tp_comm = bool(try_get_key(cfg, "fused_tp_comm", default=False)) and self.sequence_parallel
+        self.fused_tp_comm = _flag("fused_tp_comm") and self.sequence_parallel
 
         # ---- layer → stage -------------------------------------------------------------
         self._layer_stage_ids = compute_layer_stage_ids(int(cfg.pipeline_num_layers), pp)

@@ -82,15 +82,6 @@ def main():
 
     record("symmetric memory + device barrier", symm)
 
-    def p2pag():
-        x = torch.randn(1024, 512, device="cuda").bfloat16() + rank
-        out = comm_gemm.p2p_all_gather(x, group).clone()
-        ref = torch.empty(1024 * world, 512, device="cuda", dtype=torch.bfloat16)
-        dist.all_gather_into_tensor(ref, x, group=group)
-        return {"ok": torch.equal(out, ref)}
-
-    record("p2p all-gather", p2pag)
-
     M, K, N = 8192, 1024, 4096
     Nl, Kl = N // world, N // world
 
@@ -99,12 +90,19 @@ def main():
         w = (torch.randn(Nl, K, device="cuda") * 0.05).bfloat16()
         b = torch.randn(Nl, device="cuda").bfloat16()
         xs = xfull[rank * (M // world): (rank + 1) * (M // world)].contiguous()
-        y, _ = comm_gemm.ag_gemm(xs, w, b, None, group)
+        y, _, _ = comm_gemm.ag_gemm(xs, w, b, None, group)
         ref = xfull.float() @ w.float().t() + b.float()
         err = rel_err(y, ref)
-        for _ in range(3):  # repeated calls exercise the parity/double buffering + epochs
-            y2, _ = comm_gemm.ag_gemm(xs, w, b, None, group)
+        for _ in range(3):  # repeated calls exercise the parity/double buffering + the device-side call counters
+            y2, _, _ = comm_gemm.ag_gemm(xs, w, b, None, group)
         err2 = rel_err(y2, ref)
+        # fill_local: the gathered buffer itself must equal the all-gather
+        _, _, xg = comm_gemm.ag_gemm(xs, w, b, None, group, fill_local=True)
+        torch.cuda.synchronize()
+        gather_ok = torch.equal(xg, xfull)
+        # fused GELU epilogue with the pre-activation copy
+        yg, pre, _ = comm_gemm.ag_gemm(xs, w, b, "gelu", group, need_pre=True)
+        err_act = max(rel_err(pre, ref), rel_err(yg, torch.nn.functional.gelu(ref)))
         ms = timeit(lambda: comm_gemm.ag_gemm(xs, w, b, None, group))
 
         def nccl():
@@ -114,17 +112,13 @@ def main():
 
         ms_ref = timeit(nccl)
         ms_gemm = timeit(lambda: ext.linear_fwd(xfull, w, b, 0, False))
-        sweep = {}
-        default_ctas = comm_gemm._N_COMM_CTAS
-        for n in (4, 8, 24, 32):          # copy-CTA count sweep (the default is measured above)
-            comm_gemm._N_COMM_CTAS = n
-            sweep[str(n)] = timeit(lambda: comm_gemm.ag_gemm(xs, w, b, None, group))
-        comm_gemm._N_COMM_CTAS = default_ctas
-        y3, _ = comm_gemm.ag_gemm(xs, w, b, None, group)
-        err3 = rel_err(y3, ref)
-        return {"ok": err < 2e-2 and err2 < 2e-2 and err3 < 2e-2, "rel_err": err, "rel_err_repeat": err2, "fused_ms": ms,
-                "nccl_plus_cublas_ms": ms_ref, "gemm_only_ms": ms_gemm, "copy_ctas": default_ctas,
-                "fused_ms_by_copy_ctas": sweep}
+        flops = 2.0 * M * Nl * K
+        link_bytes = (world - 1) * (M // world) * K * 2       # this rank's shard to every peer
+        roof_ms = max(flops / 1.6e15, link_bytes / 770e9) * 1e3
+        return {"ok": err < 2e-2 and err2 < 2e-2 and gather_ok and err_act < 2e-2, "rel_err": err, "rel_err_repeat": err2,
+                "gathered_buffer_exact": gather_ok, "rel_err_gelu_pre": err_act, "fused_ms": ms,
+                "nccl_plus_cublas_ms": ms_ref, "gemm_only_ms": ms_gemm, "copy_ctas": comm_gemm._n_comm_ctas(world),
+                "roofline_ms": roof_ms, "roofline_fraction": roof_ms / ms}
 
     record(f"AG->GEMM M{M} N{Nl} K{K}", aggemm)
 
@@ -151,39 +145,136 @@ def main():
 
         ms_ref = timeit(nccl)
         ms_gemm = timeit(lambda: ext.linear_fwd(x, w, None, 0, False))
+        flops = 2.0 * M * K * Kl
+        link_bytes = (world - 1) * (M // world) * K * 2
+        roof_ms = max(flops / 1.6e15, link_bytes / 770e9) * 1e3
         return {"ok": err < 3e-2 and err2 < 3e-2, "rel_err": err, "rel_err_repeat": err2, "fused_ms": ms,
-                "cublas_plus_nccl_ms": ms_ref, "gemm_only_ms": ms_gemm}
+                "cublas_plus_nccl_ms": ms_ref, "gemm_only_ms": ms_gemm, "roofline_ms": roof_ms,
+                "roofline_fraction": roof_ms / ms}
 
     record(f"GEMM->RS M{M} N{K} K{Kl}", gemmrs)
 
+    def gemmrs_odd_n():
+        """N not a multiple of the tile width (Llama-7B tp4: ffn/t = 2752)."""
+        Mo, No, Ko = 2048, 2752, 512
+        x = torch.randn(Mo, Ko, device="cuda").bfloat16()
+        w = (torch.randn(No, Ko, device="cuda") * 0.05).bfloat16()
+        y = comm_gemm.gemm_rs(x, w, None, None, group)
+        part = (x.float() @ w.float().t())
+        dist.all_reduce(part, group=group)
+        ref = part[rank * (Mo // world): (rank + 1) * (Mo // world)]
+        err = rel_err(y, ref)
+        xs = x[rank * (Mo // world): (rank + 1) * (Mo // world)].contiguous()
+        xfull = torch.empty(Mo, Ko, device="cuda", dtype=torch.bfloat16)
+        dist.all_gather_into_tensor(xfull, xs, group=group)
+        y2, _, _ = comm_gemm.ag_gemm(xs, w, None, None, group)
+        err2 = rel_err(y2, xfull.float() @ w.float().t())
+        return {"ok": err < 3e-2 and err2 < 2e-2, "rs_rel_err": err, "ag_rel_err": err2}
+
+    record("AG->GEMM / GEMM->RS with N = 2752", gemmrs_odd_n)
+
+    def agwgrad():
+        """dW = dyᵀ · all_gather(x_shard) with the all-gather inside the split-K wgrad kernel."""
+        T, h, Nloc = 8192, 1024, 3072 // world
+        xfull = torch.randn(T, h, device="cuda").bfloat16()
+        dist.broadcast(xfull, 0)
+        gy = (torch.randn(T, Nloc, device="cuda") * 0.1).bfloat16()
+        xs = xfull[rank * (T // world): (rank + 1) * (T // world)].contiguous()
+        out = torch.zeros(Nloc, h, device="cuda", dtype=torch.float32)
+        comm_gemm.ag_wgrad(gy, xs, out, True, group)
+        comm_gemm.ag_wgrad(gy, xs, out, True, group)      # accumulates
+        ref = 2.0 * (gy.float().t() @ xfull.float())
+        err = rel_err(out, ref)
+        ms = timeit(lambda: comm_gemm.ag_wgrad(gy, xs, out, True, group))
+
+        def nccl():
+            g = torch.empty(T, h, device="cuda", dtype=torch.bfloat16)
+            dist.all_gather_into_tensor(g, xs, group=group)
+            return ext.gemm(gy, g, 2, None, out, True, torch.float32)
+
+        ms_ref = timeit(nccl)
+        ms_gemm = timeit(lambda: ext.gemm(gy, xfull, 2, None, out, True, torch.float32))
+        return {"ok": err < 2e-2, "rel_err": err, "fused_ms": ms, "nccl_allgather_plus_native_wgrad_ms": ms_ref,
+                "wgrad_only_ms": ms_gemm}
+
+    record("AG->wgrad (gathered B, split-K) T8192", agwgrad)
+
+    def graph_replay():
+        """The fused kernels inside a CUDA graph: call counters / arrival targets live in device memory, so the SAME
+        captured launches are replayed with fresh data and must keep producing the right result."""
+        T, h = 4096, 1024
+        fl = 4096 // world
+        w1 = (torch.randn(fl, h, device="cuda") * 0.03).bfloat16()
+        w2 = (torch.randn(h, fl, device="cuda") * 0.03).bfloat16()
+        xs = torch.randn(T // world, h, device="cuda").bfloat16()
+        static_x = xs.clone()
+
+        def body():
+            hmid, _, _ = comm_gemm.ag_gemm(static_x, w1, None, "gelu", group)
+            return comm_gemm.gemm_rs(hmid, w2, None, None, group)
+
+        for _ in range(3):
+            body()
+        torch.cuda.synchronize()
+        dist.barrier()
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                static_y = body()
+        torch.cuda.current_stream().wait_stream(side)
+        errs = []
+        for it in range(6):
+            xnew = torch.randn(T // world, h, device="cuda").bfloat16() * (1 + it)
+            static_x.copy_(xnew)
+            g.replay()
+            if it % 2 == 1:
+                body()        # eager calls interleaved with replays keep working (shared device-side counters)
+            xfull = torch.empty(T, h, device="cuda", dtype=torch.bfloat16)
+            dist.all_gather_into_tensor(xfull, xnew, group=group)
+            part = torch.nn.functional.gelu(xfull.float() @ w1.float().t()).bfloat16().float() @ w2.float().t()
+            dist.all_reduce(part, group=group)
+            errs.append(rel_err(static_y, part[rank * (T // world): (rank + 1) * (T // world)]))
+        ms = timeit(lambda: g.replay())
+        return {"ok": max(errs) < 3e-2, "errs": errs, "replay_ms": ms}
+
+    record("fused AG->GEMM + GEMM->RS replayed from a CUDA graph", graph_replay)
+
     def autograd_parity():
-        """Column + row fused linears (fwd + bwd) against the NCCL mappings path."""
+        """Column + row fused linears and the fused TP MLP (fwd + bwd) against the NCCL mappings path."""
         T, h, f = 2048, 1024, 4096
         x = torch.randn(T // world, h, device="cuda").bfloat16()
         w1 = (torch.randn(f // world, h, device="cuda") * 0.03).bfloat16()
-        b1 = torch.zeros(f // world, device="cuda").bfloat16()
+        b1 = (torch.randn(f // world, device="cuda") * 0.1).bfloat16()
         w2 = (torch.randn(h, f // world, device="cuda") * 0.03).bfloat16()
+        b2 = (torch.randn(h, device="cuda") * 0.1).bfloat16()
+        res = torch.randn(T // world, h, device="cuda").bfloat16()
         outs = []
-        for fused in (True, False):
+        for mode in ("mlp", "colrow", "nccl"):
             xx = x.clone().requires_grad_(True)
             a1, a2 = w1.clone().requires_grad_(True), w2.clone().requires_grad_(True)
-            bb = b1.clone().requires_grad_(True)
-            if fused:
+            bb, bb2 = b1.clone().requires_grad_(True), b2.clone().requires_grad_(True)
+            rr = res.clone().requires_grad_(True)
+            if mode == "mlp":
+                y = comm_gemm.tp_mlp(xx, a1, bb, a2, bb2, rr, "gelu", group)
+            elif mode == "colrow":
                 hmid = comm_gemm.column_parallel_linear(xx, a1, bb, "gelu", group)
-                y = comm_gemm.row_parallel_linear(hmid, a2, None, None, group)
+                y = comm_gemm.row_parallel_linear(hmid, a2, bb2, rr, group)
             else:
                 os.environ["LIBAI_B200_IMPL"] = "ref"
                 g = mappings.gather_from_sp(xx)
                 hmid = torch.nn.functional.gelu(torch.nn.functional.linear(g, a1, bb))
-                y = mappings.reduce_scatter_to_sp(torch.nn.functional.linear(hmid, a2))
+                y = mappings.reduce_scatter_to_sp(torch.nn.functional.linear(hmid, a2)) + bb2 + rr
                 os.environ["LIBAI_B200_IMPL"] = "native"
-            gy = torch.ones_like(y) * 0.01
+            gy = torch.randn(y.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7 + rank)).bfloat16() * 0.01
             y.backward(gy)
-            outs.append((y.detach(), xx.grad, a1.grad, a2.grad, bb.grad))
-        errs = [rel_err(a, b) for a, b in zip(outs[0], outs[1])]
-        return {"ok": max(errs) < 4e-2, "errs": errs}
+            outs.append((y.detach(), xx.grad, a1.grad, a2.grad, bb.grad, bb2.grad, rr.grad))
+        errs_mlp = [rel_err(a, b) for a, b in zip(outs[0], outs[2])]
+        errs_cr = [rel_err(a, b) for a, b in zip(outs[1], outs[2])]
+        return {"ok": max(errs_mlp) < 4e-2 and max(errs_cr) < 4e-2, "errs_tp_mlp": errs_mlp, "errs_col_row": errs_cr}
 
-    record("fused column/row linear autograd vs NCCL", autograd_parity)
+    record("fused column/row linear + TP-MLP autograd vs NCCL", autograd_parity)
 
     def zero():
         """ZeRO-1 with fused RS+Adam+AG kernels vs the NCCL sequence (dp = world)."""

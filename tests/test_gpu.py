@@ -210,3 +210,28 @@ def test_fused_nvlink_collectives(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     results = json.load(open(out))
     assert all(x.get("ok") for x in results), [x for x in results if not x.get("ok")]
+
+
+def _trajectory(tmp_path, name, nproc, *flags):
+    out = str(tmp_path / f"{name}.json")
+    cmd = [sys.executable]
+    if nproc > 1:
+        cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+                "--master-port", "29541"]
+    r = _run(cmd + ["tests/gpu_tp_parity.py", "--out", out, *flags], timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return json.load(open(out))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_tensor_parallel_trains_like_one_gpu(tmp_path):
+    """GPT-2 with TP2 + sequence parallelism + AG→GEMM / GEMM→RS kernels (blocks replayed from CUDA
+    graphs) follows the single-GPU native loss trajectory within bf16 tolerance — and so does the NCCL form."""
+    one = _trajectory(tmp_path, "one", 1)
+    fused = _trajectory(tmp_path, "tp2_fused", 2, "--tp", "2", "--fused", "1")
+    nccl = _trajectory(tmp_path, "tp2_nccl", 2, "--tp", "2", "--fused", "0")
+    assert fused["graphs"], "fused tensor-parallel blocks must be CUDA-graph captured"
+    assert one["losses"][-1] < one["losses"][0] - 1.0, one["losses"]        # it actually learns
+    for a, b, c in zip(one["losses"], fused["losses"], nccl["losses"]):
+        assert abs(a - b) < 0.05 * max(1.0, abs(a)), (one["losses"], fused["losses"])
+        assert abs(a - c) < 0.05 * max(1.0, abs(a)), (one["losses"], nccl["losses"])
