@@ -270,7 +270,7 @@ def measure_native(args, lay, world, rank, local_rank, steps, warmup, with_e2e, 
     cfg = build_cfg(args, lay)
     default_setup(cfg, argparse.Namespace(resume=False, config_file=""))
     logging.getLogger("libai_b200").setLevel(logging.WARNING)
-    torch.manual_seed(cfg.train.seed + rank)
+    torch.manual_seed(dutil.model_parallel_seed(cfg.train.seed))
     trainer = BenchTrainer(cfg)  # public API: builds model, optimizer, scheduler, loader, hooks
     step = trainer._trainer      # the StepTrainer behind trainer.run_step()
     topo = dutil.get_dist_util()

@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include <cstdlib>
+#include <cstring>
 
 namespace lb {
 
@@ -47,7 +48,29 @@ struct AttnFwdParams {
   float scale_log2;   // scale * log2(e)
   float scale;
   const int* kv_lens; // optional [B]: number of valid keys per sample (right-padded batches)
+  // additive score bias (v2 kernel): dense bf16 [.., S, S] with (batch, head, query) strides in elements (0 = broadcast;
+  // T5 relative-position bias, Swin/BERT style masks) or ALiBi slopes per head (bias = slope * (key - query))
+  const __nv_bfloat16* bias;
+  long bias_strides[3];
+  const float* alibi_slopes;
+  // attention dropout on P (v2 kernel): keep <=> philox byte >= drop_thresh; O is scaled by inv_keep
+  uint32_t drop_thresh;
+  float inv_keep;
+  RngArgs rng;
+  long long* rng_out;   // [2]: the (seed, offset) pair used, for the backward
 };
+
+enum AttnBias : int { BIAS_NONE = 0, BIAS_DENSE = 1, BIAS_ALIBI = 2 };
+
+// 16 random bytes for keys [16 g, 16 g + 16) of query row q_idx of (batch, head) slice bh
+LB_DEVICE uint4 attn_dropout_bytes(uint32_t q_idx, uint32_t g, uint32_t bh, unsigned long long seed, unsigned long long offset) {
+  return philox4x32_7(q_idx, g, bh ^ (static_cast<uint32_t>(offset >> 32) << 20), static_cast<uint32_t>(offset),
+                      static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+}
+LB_DEVICE uint32_t rnd_byte(const uint4& r, int i) {   // i in [0, 16)
+  const uint32_t w = (i < 4) ? r.x : (i < 8 ? r.y : (i < 12 ? r.z : r.w));
+  return (w >> ((i & 3) * 8)) & 0xFFu;
+}
 
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -327,7 +350,7 @@ struct AttnCfg2 {
   static constexpr int MIN_CTAS = (D == 64) ? 2 : 1;
 };
 
-template <int D>
+template <int D, int BIAS, bool DROP>
 __global__ void __launch_bounds__(ATT_FWD2_THREADS, AttnCfg2<D>::MIN_CTAS)
 attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, AttnFwdParams p) {
@@ -451,6 +474,41 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint32_t p_addr = tmem_base + lane_off + Cfg::P_COL + half * 32;
     const uint32_t o_addr = tmem_base + lane_off + Cfg::O_COL + half * (D / 2);
     float m_run = -INFINITY, l_run = 0.f;       // l_run: partial row sum over this half's columns
+    constexpr float LOG2E = 1.4426950408889634f;
+    unsigned long long rng_seed = 0, rng_offset = 0;
+    if constexpr (DROP) {
+      rng_resolve(p.rng, rng_seed, rng_offset);
+      if (p.rng_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
+        p.rng_out[0] = static_cast<long long>(rng_seed);
+        p.rng_out[1] = static_cast<long long>(rng_offset);
+      }
+    }
+    const uint32_t bh = static_cast<uint32_t>(batch * p.A + head);
+    const __nv_bfloat16* bias_row = nullptr;
+    float slope2 = 0.f;
+    if constexpr (BIAS == BIAS_DENSE)
+      bias_row = p.bias + batch * p.bias_strides[0] + head * p.bias_strides[1] +
+                 static_cast<long>(min(q_idx, p.S - 1)) * p.bias_strides[2];
+    if constexpr (BIAS == BIAS_ALIBI) slope2 = p.alibi_slopes[head] * LOG2E;
+    // score in the log2 domain: s * scale_log2 (+ bias * log2 e)
+    auto bias2 = [&](const uint4 (&bq)[4], int i, int kidx) -> float {
+      if constexpr (BIAS == BIAS_DENSE) {
+        const uint32_t w = (&bq[i >> 3].x)[(i & 7) >> 1];
+        const float2 f = unpack_bf16(w);
+        return ((i & 1) ? f.y : f.x) * LOG2E;
+      } else if constexpr (BIAS == BIAS_ALIBI) {
+        return slope2 * static_cast<float>(kidx - q_idx);
+      } else {
+        return 0.f;
+      }
+    };
+    auto load_bias = [&](uint4 (&bq)[4], int kbase) {
+      if constexpr (BIAS == BIAS_DENSE) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          bq[v] = (kbase + v * 8 < p.S) ? *reinterpret_cast<const uint4*>(bias_row + kbase + v * 8) : make_uint4(0, 0, 0, 0);
+      }
+    };
 
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full, j & 1);
@@ -464,11 +522,17 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t t[32];
+          uint4 bq[4];
           tmem_ld_32x32b_x32(s_addr + c * 32, t);
+          load_bias(bq, k0 + c * 32);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float x0 = __uint_as_float(t[i]), x1 = __uint_as_float(t[i + 1]);
+            if constexpr (BIAS != BIAS_NONE) {   // with a bias the max is taken in the log2 domain
+              x0 = fmaf(x0, p.scale_log2, bias2(bq, i, k0 + c * 32 + i));
+              x1 = fmaf(x1, p.scale_log2, bias2(bq, i + 1, k0 + c * 32 + i + 1));
+            }
             if constexpr (MASK) {
               const int kidx = k0 + c * 32 + i;
               if (kidx >= kv_len || (p.causal && kidx > q_idx)) x0 = -INFINITY;
@@ -484,7 +548,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       asm volatile("bar.sync 1, 256;\n" ::: "memory");
       mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);
       // ---- lazy rescale: only move the reference max when it grows by more than 2^8
-      const float m_cand = fmaxf(m_run, mx * p.scale_log2);
+      const float m_cand = fmaxf(m_run, BIAS != BIAS_NONE ? mx : mx * p.scale_log2);
       const bool bump = (m_cand - m_run > 8.0f) || (m_run == -INFINITY && m_cand != -INFINITY);
       float alpha = 1.0f;
       if (bump) {
@@ -501,20 +565,37 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t t[32];
+          uint4 bq[4];
           tmem_ld_32x32b_x32(s_addr + c * 32, t);
+          load_bias(bq, k0 + c * 32);
+          uint4 rnd[2];
+          if constexpr (DROP) {   // 32 keys = two 16-byte Philox results, generated while the TMEM load is in flight
+            rnd[0] = attn_dropout_bytes(static_cast<uint32_t>(q_idx), static_cast<uint32_t>((k0 + c * 32) >> 4), bh, rng_seed, rng_offset);
+            rnd[1] = attn_dropout_bytes(static_cast<uint32_t>(q_idx), static_cast<uint32_t>((k0 + c * 32) >> 4) + 1u, bh, rng_seed, rng_offset);
+          }
           tmem_ld_wait();
           uint32_t packed[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            float e0 = fast_exp2(__uint_as_float(t[i]) * p.scale_log2 - m_use);
-            float e1 = fast_exp2(__uint_as_float(t[i + 1]) * p.scale_log2 - m_use);
+            float e0, e1;
+            if constexpr (BIAS != BIAS_NONE) {
+              e0 = fast_exp2(fmaf(__uint_as_float(t[i]), p.scale_log2, bias2(bq, i, k0 + c * 32 + i)) - m_use);
+              e1 = fast_exp2(fmaf(__uint_as_float(t[i + 1]), p.scale_log2, bias2(bq, i + 1, k0 + c * 32 + i + 1)) - m_use);
+            } else {
+              e0 = fast_exp2(__uint_as_float(t[i]) * p.scale_log2 - m_use);
+              e1 = fast_exp2(__uint_as_float(t[i + 1]) * p.scale_log2 - m_use);
+            }
             if constexpr (MASK) {
               const int kidx = k0 + c * 32 + i;
               if (kidx >= kv_len || (p.causal && kidx > q_idx)) e0 = 0.f;
               if (kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) e1 = 0.f;
             }
-            rs0 += e0;
+            rs0 += e0;   // the softmax normaliser is the sum of the UNdropped probabilities
             rs1 += e1;
+            if constexpr (DROP) {
+              if (rnd_byte(rnd[i >> 4], i & 15) < p.drop_thresh) e0 = 0.f;
+              if (rnd_byte(rnd[i >> 4], (i & 15) + 1) < p.drop_thresh) e1 = 0.f;
+            }
             packed[i / 2] = pack_bf16(e0, e1);
           }
           tmem_st_32x32b_x16(p_addr + c * 16, packed);
@@ -548,7 +629,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     l_run += xch[(half ^ 1) * 128 + r];
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after_sync();
-    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    const float inv = l_run > 0.f ? (DROP ? p.inv_keep : 1.0f) / l_run : 0.f;
     __nv_bfloat16* orow = p.o + ((static_cast<size_t>(batch) * p.S + q_idx) * p.A + head) * D + half * (D / 2);
 #pragma unroll
     for (int c = 0; c < D / 64; ++c) {
@@ -590,11 +671,11 @@ bool make_qkv_tmap(CUtensorMap* m, const void* ptr, int B, int A, int S, int D, 
   return lb_host::make_tmap_bf16(m, ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int D>
-cudaError_t launch_fwd_v2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                          const lb::AttnFwdParams& p, cudaStream_t s) {
+template <int D, int BIAS, bool DROP>
+cudaError_t launch_fwd_v2_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                            const lb::AttnFwdParams& p, cudaStream_t s) {
   using Cfg = lb::AttnCfg2<D>;
-  auto kern = lb::attn_fwd_v2_kernel<D>;
+  auto kern = lb::attn_fwd_v2_kernel<D, BIAS, DROP>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -604,6 +685,16 @@ cudaError_t launch_fwd_v2(const CUtensorMap& tq, const CUtensorMap& tk, const CU
   dim3 grid((p.S + lb::ATT_BM - 1) / lb::ATT_BM, p.A, p.B);
   kern<<<grid, lb::ATT_FWD2_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, p);
   return cudaGetLastError();
+}
+
+template <int D>
+cudaError_t launch_fwd_v2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                          const lb::AttnFwdParams& p, cudaStream_t s) {
+  const int bias = p.bias != nullptr ? lb::BIAS_DENSE : (p.alibi_slopes != nullptr ? lb::BIAS_ALIBI : lb::BIAS_NONE);
+  const bool drop = p.drop_thresh > 0;
+  if (bias == lb::BIAS_NONE) return drop ? launch_fwd_v2_t<D, lb::BIAS_NONE, true>(tq, tk, tv, p, s) : launch_fwd_v2_t<D, lb::BIAS_NONE, false>(tq, tk, tv, p, s);
+  if (bias == lb::BIAS_DENSE) return drop ? launch_fwd_v2_t<D, lb::BIAS_DENSE, true>(tq, tk, tv, p, s) : launch_fwd_v2_t<D, lb::BIAS_DENSE, false>(tq, tk, tv, p, s);
+  return drop ? launch_fwd_v2_t<D, lb::BIAS_ALIBI, true>(tq, tk, tv, p, s) : launch_fwd_v2_t<D, lb::BIAS_ALIBI, false>(tq, tk, tv, p, s);
 }
 
 int attn_fwd_version() {
@@ -618,7 +709,8 @@ int attn_fwd_version() {
 template <int D>
 cudaError_t launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const lb::AttnFwdParams& p,
                        cudaStream_t s) {
-  if (attn_fwd_version() == 2) return launch_fwd_v2<D>(tq, tk, tv, p, s);
+  if (attn_fwd_version() == 2 || p.bias != nullptr || p.alibi_slopes != nullptr || p.drop_thresh > 0)
+    return launch_fwd_v2<D>(tq, tk, tv, p, s);   // (bias / dropout exist in the v2 kernel only)
   using Cfg = lb::AttnCfg<D>;
   auto kern = lb::attn_fwd_kernel<D>;
   static bool configured = false;
@@ -633,9 +725,13 @@ cudaError_t launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 }
 }  // namespace
 
+// p_drop in [0, 1): attention dropout probability (quantised to 1/256 like the byte-threshold test of the kernel);
+// bias (optional, bf16): dense additive score bias with (batch, head, query-row) strides in elements, key stride 1;
+// alibi_slopes (optional, fp32 [A]).
 extern "C" int lb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int A, int S, int D,
                            const long* q_strides, const long* k_strides, const long* v_strides, int causal, float scale,
-                           const int* kv_lens, cudaStream_t s) {
+                           const int* kv_lens, const void* bias, const long* bias_strides, const float* alibi_slopes,
+                           float p_drop, const lb::RngArgs* rng, long long* rng_out, cudaStream_t s) {
   if (D != 64 && D != 128) return -1;
   for (int i = 0; i < 3; ++i)
     if ((q_strides[i] % 8) || (k_strides[i] % 8) || (v_strides[i] % 8)) return -3;
@@ -653,6 +749,18 @@ extern "C" int lb_attn_fwd(const void* q, const void* k, const void* v, void* o,
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.kv_lens = kv_lens;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  for (int i = 0; i < 3; ++i) p.bias_strides[i] = (bias != nullptr && bias_strides != nullptr) ? bias_strides[i] : 0;
+  if (bias != nullptr && ((p.bias_strides[0] | p.bias_strides[1] | p.bias_strides[2]) % 8 || (reinterpret_cast<uintptr_t>(bias) & 15)))
+    return -3;
+  p.alibi_slopes = bias != nullptr ? nullptr : alibi_slopes;
+  uint32_t thr = (uint32_t)(p_drop * 256.0f + 0.5f);
+  if (thr > 255u) thr = 255u;
+  p.drop_thresh = (p_drop > 0.f && rng != nullptr) ? (thr == 0 ? 1u : thr) : 0u;
+  p.inv_keep = 256.0f / (256.0f - (float)p.drop_thresh);
+  memset(&p.rng, 0, sizeof(p.rng));
+  if (rng != nullptr) p.rng = *rng;
+  p.rng_out = rng_out;
   cudaError_t e = (D == 64) ? launch_fwd<64>(tq, tk, tv, p, s) : launch_fwd<128>(tq, tk, tv, p, s);
   return (int)e;
 }
@@ -695,9 +803,17 @@ struct AttnBwdParams {
   int causal;
   float scale, scale_log2;
   const int* kv_lens;   // optional [B]
+  // same additive bias / dropout description as the forward; `rng_state` = the (seed, offset) pair the forward used
+  const __nv_bfloat16* bias;
+  long bias_strides[3];
+  const float* alibi_slopes;
+  float* dbias;         // optional fp32, same strides as `bias`: += P ∘ (dP − δ) (gradient of a learned bias)
+  uint32_t drop_thresh;
+  float inv_keep;
+  const long long* rng_state;
 };
 
-template <int D>
+template <int D, int BIAS, bool DROP>
 __global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -853,10 +969,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int r = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const size_t bh = static_cast<size_t>(batch) * p.A + head;
+    constexpr float LOG2E = 1.4426950408889634f;
+    unsigned long long rng_seed = 0, rng_offset = 0;
+    if constexpr (DROP) {
+      rng_seed = static_cast<unsigned long long>(p.rng_state[0]);
+      rng_offset = static_cast<unsigned long long>(p.rng_state[1]);
+    }
+    float slope2 = 0.f;
+    if constexpr (BIAS == BIAS_ALIBI) slope2 = p.alibi_slopes[head] * LOG2E;
+    const float inv_scale = 1.0f / p.scale;
     for (int it = 0; it < iters; ++it) {
       const int q_blk = i_begin + it;
       const int q_idx = q_blk * 128 + r;
       const bool q_ok = q_idx < p.S;
+      const long bias_off = batch * p.bias_strides[0] + head * p.bias_strides[1] +
+                            static_cast<long>(min(q_idx, p.S - 1)) * p.bias_strides[2];
       const float lse2 = q_ok ? p.lse[bh * p.S + q_idx] * 1.4426950408889634f : 0.f;
       const float delta = q_ok ? p.delta[bh * p.S + q_idx] : 0.f;
       const bool need_mask = (p.causal && q_blk == kv_blk) || (k0 + 128 > kv_len) || (q_blk * 128 + 128 > p.S);
@@ -873,21 +1000,72 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           uint32_t ts[32], td[32];
           tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::S_COL + c * 32, ts);
           tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DP_COL + c * 32, td);
+          uint4 bq[4];
+          if constexpr (BIAS == BIAS_DENSE) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const int kb = k0 + c * 32 + v * 8;
+              bq[v] = kb < p.S ? *reinterpret_cast<const uint4*>(p.bias + bias_off + kb) : make_uint4(0, 0, 0, 0);
+            }
+          }
+          uint4 rnd[2];
+          if constexpr (DROP) {
+            rnd[0] = attn_dropout_bytes(static_cast<uint32_t>(q_idx), static_cast<uint32_t>((k0 + c * 32) >> 4), static_cast<uint32_t>(bh), rng_seed, rng_offset);
+            rnd[1] = attn_dropout_bytes(static_cast<uint32_t>(q_idx), static_cast<uint32_t>((k0 + c * 32) >> 4) + 1u, static_cast<uint32_t>(bh), rng_seed, rng_offset);
+          }
           tmem_ld_wait();
           uint32_t pp[16], dd[16];
+          float dsv[32];   // only materialised for the dbias path
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            float p0 = fast_exp2(__uint_as_float(ts[i]) * p.scale_log2 - lse2);
-            float p1 = fast_exp2(__uint_as_float(ts[i + 1]) * p.scale_log2 - lse2);
+            float p0, p1;
+            if constexpr (BIAS == BIAS_DENSE) {
+              const float2 bf = unpack_bf16((&bq[i >> 3].x)[(i & 7) >> 1]);
+              p0 = fast_exp2(fmaf(__uint_as_float(ts[i]), p.scale_log2, bf.x * LOG2E) - lse2);
+              p1 = fast_exp2(fmaf(__uint_as_float(ts[i + 1]), p.scale_log2, bf.y * LOG2E) - lse2);
+            } else if constexpr (BIAS == BIAS_ALIBI) {
+              const int kidx = k0 + c * 32 + i;
+              p0 = fast_exp2(fmaf(__uint_as_float(ts[i]), p.scale_log2, slope2 * static_cast<float>(kidx - q_idx)) - lse2);
+              p1 = fast_exp2(fmaf(__uint_as_float(ts[i + 1]), p.scale_log2, slope2 * static_cast<float>(kidx + 1 - q_idx)) - lse2);
+            } else {
+              p0 = fast_exp2(__uint_as_float(ts[i]) * p.scale_log2 - lse2);
+              p1 = fast_exp2(__uint_as_float(ts[i + 1]) * p.scale_log2 - lse2);
+            }
             if constexpr (MASK) {
               const int kidx = k0 + c * 32 + i;
               if (!q_ok || kidx >= kv_len || (p.causal && kidx > q_idx)) p0 = 0.f;
               if (!q_ok || kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) p1 = 0.f;
             }
-            const float d0 = p0 * fmaf(__uint_as_float(td[i]), p.scale, -delta_s);
-            const float d1 = p1 * fmaf(__uint_as_float(td[i + 1]), p.scale, -delta_s);
-            pp[i / 2] = pack_bf16(p0, p1);
+            float g0 = __uint_as_float(td[i]), g1 = __uint_as_float(td[i + 1]);   // dP w.r.t. the dropped, rescaled P
+            float pd0 = p0, pd1 = p1;                                               // what multiplied V in the forward
+            if constexpr (DROP) {
+              const bool keep0 = rnd_byte(rnd[i >> 4], i & 15) >= p.drop_thresh;
+              const bool keep1 = rnd_byte(rnd[i >> 4], (i & 15) + 1) >= p.drop_thresh;
+              g0 = keep0 ? g0 * p.inv_keep : 0.f;
+              g1 = keep1 ? g1 * p.inv_keep : 0.f;
+              pd0 = keep0 ? p0 * p.inv_keep : 0.f;
+              pd1 = keep1 ? p1 * p.inv_keep : 0.f;
+            }
+            const float d0 = p0 * fmaf(g0, p.scale, -delta_s);
+            const float d1 = p1 * fmaf(g1, p.scale, -delta_s);
+            pp[i / 2] = pack_bf16(pd0, pd1);
             dd[i / 2] = pack_bf16(d0, d1);
+            if constexpr (BIAS == BIAS_DENSE) {
+              dsv[i] = d0 * inv_scale;
+              dsv[i + 1] = d1 * inv_scale;
+            }
+          }
+          if constexpr (BIAS == BIAS_DENSE) {
+            if (p.dbias != nullptr && q_ok) {   // d bias = P ∘ (dP − δ): fp32 reductions (broadcast dims sum over CTAs)
+              float* drow = p.dbias + bias_off + k0 + c * 32;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                if (k0 + c * 32 + i < p.S)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(drow + i), "f"(dsv[i]), "f"(dsv[i + 1]),
+                               "f"(dsv[i + 2]), "f"(dsv[i + 3])
+                               : "memory");
+              }
+            }
           }
           const int half_off = (c / 2) * (128 * 128);
 #pragma unroll
@@ -1074,11 +1252,11 @@ attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict_
 }  // namespace lb
 
 namespace {
-template <int D>
-cudaError_t launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-                       const CUtensorMap& tdq, const lb::AttnBwdParams& p, cudaStream_t s) {
+template <int D, int BIAS, bool DROP>
+cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                         const CUtensorMap& tdq, const lb::AttnBwdParams& p, cudaStream_t s) {
   using Cfg = lb::AttnBwdCfg<D>;
-  auto kern = lb::attn_bwd_kernel<D>;
+  auto kern = lb::attn_bwd_kernel<D, BIAS, DROP>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -1089,12 +1267,23 @@ cudaError_t launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   kern<<<grid, lb::ATT_BWD_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, tdo, tdq, p);
   return cudaGetLastError();
 }
+template <int D>
+cudaError_t launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                       const CUtensorMap& tdq, const lb::AttnBwdParams& p, cudaStream_t s) {
+  const int bias = p.bias != nullptr ? lb::BIAS_DENSE : (p.alibi_slopes != nullptr ? lb::BIAS_ALIBI : lb::BIAS_NONE);
+  const bool drop = p.drop_thresh > 0;
+  if (bias == lb::BIAS_NONE) return drop ? launch_bwd_t<D, lb::BIAS_NONE, true>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd_t<D, lb::BIAS_NONE, false>(tq, tk, tv, tdo, tdq, p, s);
+  if (bias == lb::BIAS_DENSE) return drop ? launch_bwd_t<D, lb::BIAS_DENSE, true>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd_t<D, lb::BIAS_DENSE, false>(tq, tk, tv, tdo, tdq, p, s);
+  return drop ? launch_bwd_t<D, lb::BIAS_ALIBI, true>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd_t<D, lb::BIAS_ALIBI, false>(tq, tk, tv, tdo, tdq, p, s);
+}
 }  // namespace
 
 extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o,
                            const float* lse, void* dq, void* dk, void* dv, float* delta, float* dq_accum, int B, int A,
                            int S, int D, const long* q_strides, const long* k_strides, const long* v_strides,
-                           const long* do_strides, int causal, float scale, const int* kv_lens, cudaStream_t s) {
+                           const long* do_strides, int causal, float scale, const int* kv_lens, const void* bias,
+                           const long* bias_strides, const float* alibi_slopes, float* dbias, float p_drop,
+                           const long long* rng_state, cudaStream_t s) {
   if (D != 64 && D != 128) return -1;
   for (int i = 0; i < 3; ++i)
     if ((q_strides[i] % 8) || (k_strides[i] % 8) || (v_strides[i] % 8) || (do_strides[i] % 8)) return -3;
@@ -1144,6 +1333,15 @@ extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.kv_lens = kv_lens;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  for (int i = 0; i < 3; ++i) p.bias_strides[i] = (bias != nullptr && bias_strides != nullptr) ? bias_strides[i] : 0;
+  p.alibi_slopes = bias != nullptr ? nullptr : alibi_slopes;
+  p.dbias = bias != nullptr ? dbias : nullptr;
+  uint32_t thr = (uint32_t)(p_drop * 256.0f + 0.5f);
+  if (thr > 255u) thr = 255u;
+  p.drop_thresh = (p_drop > 0.f && rng_state != nullptr) ? (thr == 0 ? 1u : thr) : 0u;
+  p.inv_keep = 256.0f / (256.0f - (float)p.drop_thresh);
+  p.rng_state = rng_state;
   cudaError_t e = (D == 64) ? launch_bwd<64>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd<128>(tq, tk, tv, tdo, tdq, p, s);
   if (e != cudaSuccess) return (int)e;
   const long nvec = rows * D / 8;

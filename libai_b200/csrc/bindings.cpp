@@ -2,6 +2,9 @@
 // Registered with TORCH_LIBRARY so the in-tree `_C.so` is loaded by torch.ops.load_library (no
 // python ABI dependency).
 #include <ATen/cuda/CUDAContext.h>
+#include <ATen/cuda/CUDAGeneratorImpl.h>
+#include <cstring>
+#include <mutex>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/library.h>
 #include <torch/torch.h>
@@ -59,13 +62,26 @@ int lb_zero_adam_allgather(float* master, const float* red, float* m, float* v, 
 int lb_device_barrier(const long* flag_ptrs, int world, int rank, int slot, unsigned epoch, cudaStream_t s);
 int lb_p2p_allgather(const void* shard, const long* out_ptrs, const long* flag_ptrs, unsigned* done_counter,
                      long nbytes, int world, int rank, unsigned epoch, cudaStream_t s);
+// mirror of lb::RngArgs (common.cuh)
+struct LbRngArgs {
+  unsigned long long seed_val, offset_val;
+  const long long* seed_ptr;
+  const long long* offset_ptr;
+  unsigned int offset_intragraph;
+  int captured;
+  unsigned long long salt;
+};
 int lb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int A, int S, int D,
                 const long* q_strides, const long* k_strides, const long* v_strides, int causal, float scale,
-                const int* kv_lens, cudaStream_t s);
+                const int* kv_lens, const void* bias, const long* bias_strides, const float* alibi_slopes, float p_drop,
+                const LbRngArgs* rng, long long* rng_out, cudaStream_t s);
 int lb_attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o, const float* lse,
                 void* dq, void* dk, void* dv, float* delta, float* dq_accum, int B, int A, int S, int D,
                 const long* q_strides, const long* k_strides, const long* v_strides, const long* do_strides, int causal,
-                float scale, const int* kv_lens, cudaStream_t s);
+                float scale, const int* kv_lens, const void* bias, const long* bias_strides, const float* alibi_slopes,
+                float* dbias, float p_drop, const long long* rng_state, cudaStream_t s);
+int lb_bias_dropout_residual(const void* x, const void* bias, const void* res, void* y, long rows, int N, float p,
+                             const LbRngArgs* rng, const long long* rng_in, long long* rng_out, cudaStream_t s);
 }
 
 namespace {
@@ -471,11 +487,83 @@ Tensor sqnorm(const Tensor& x) {
   return out;
 }
 
+// ---- dropout RNG ---------------------------------------------------------------------------------------------
+// (seed, offset) of the default CUDA generator, advanced by `increment`; graph-capture aware (pointers + intra-graph
+// offset while capturing — PyTorch refreshes the pointed-to values before every replay).  `salt` != 0 decorrelates
+// tensor-parallel ranks in sharded regions.
+LbRngArgs next_rng(int64_t salt, uint64_t increment = 4) {
+  auto gen = at::get_generator_or_default<at::CUDAGeneratorImpl>(c10::nullopt, at::cuda::detail::getDefaultCUDAGenerator());
+  at::PhiloxCudaState st;
+  {
+    std::lock_guard<std::mutex> lock(gen->mutex_);
+    st = gen->philox_cuda_state(increment);
+  }
+  LbRngArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.captured = st.captured_ ? 1 : 0;
+  if (st.captured_) {
+    a.seed_ptr = reinterpret_cast<const long long*>(st.seed_.ptr);
+    a.offset_ptr = reinterpret_cast<const long long*>(st.offset_.ptr);
+    a.offset_intragraph = st.offset_intragraph_;
+  } else {
+    a.seed_val = st.seed_.val;
+    a.offset_val = st.offset_.val;
+  }
+  a.salt = static_cast<unsigned long long>(salt);
+  return a;
+}
+
+// y = residual + dropout(x + bias, p); returns (y, rng_state int64[2]) — the backward is the same op on the output
+// gradient with `rng_state` passed back in (bias = residual = None)
+std::tuple<Tensor, Tensor> bias_dropout_residual(const Tensor& x, const c10::optional<Tensor>& bias,
+                                                 const c10::optional<Tensor>& res, double p, int64_t salt,
+                                                 const c10::optional<Tensor>& rng_state) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.is_contiguous() && x.dim() == 2, "bias_dropout_residual: bf16 contiguous 2-D");
+  TORCH_CHECK(p >= 0.0 && p < 1.0, "dropout probability must be in [0, 1)");
+  Tensor y = at::empty_like(x);
+  const void* bptr = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
+  const void* rptr = (res.has_value() && res->defined()) ? res->data_ptr() : nullptr;
+  if (rng_state.has_value() && rng_state->defined()) {
+    check(lb_bias_dropout_residual(x.data_ptr(), bptr, rptr, y.data_ptr(), x.size(0), (int)x.size(1), (float)p, nullptr,
+                                   reinterpret_cast<const long long*>(rng_state->data_ptr<int64_t>()), nullptr, cur_stream()),
+          "bias_dropout_residual");
+    return std::make_tuple(y, *rng_state);
+  }
+  Tensor st = at::empty({2}, x.options().dtype(at::kLong));
+  LbRngArgs a = next_rng(salt);
+  check(lb_bias_dropout_residual(x.data_ptr(), bptr, rptr, y.data_ptr(), x.size(0), (int)x.size(1), (float)p, &a, nullptr,
+                                 reinterpret_cast<long long*>(st.data_ptr<int64_t>()), cur_stream()),
+        "bias_dropout_residual");
+  return std::make_tuple(y, st);
+}
+
 // ---- attention ----------------------------------------------------------------------------------------------
 // q, k, v: [B, A, S, D] views with arbitrary batch/head/seq strides (D contiguous). Output o is allocated as
 // [B, S, A, D] and returned as the [B, A, S, D] view, lse fp32 [B, A, S].
-std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, bool causal, double scale,
-                                    const c10::optional<Tensor>& kv_lens) {
+struct BiasDesc {
+  const void* ptr = nullptr;
+  long strides[3] = {0, 0, 0};
+};
+// bias [Bb, Ab, S, S] (Bb in {1, B}, Ab in {1, A}), bf16, key dimension contiguous; broadcast dims get stride 0
+BiasDesc bias_desc(const c10::optional<Tensor>& bias, int B, int A, int S) {
+  BiasDesc d;
+  if (!(bias.has_value() && bias->defined())) return d;
+  const Tensor& b = *bias;
+  TORCH_CHECK(b.dim() == 4 && b.scalar_type() == at::kBFloat16 && b.stride(3) == 1 && b.size(2) == S && b.size(3) == S,
+              "attention bias: bf16 [B|1, A|1, S, S] with contiguous keys");
+  TORCH_CHECK((b.size(0) == 1 || b.size(0) == B) && (b.size(1) == 1 || b.size(1) == A), "attention bias: bad broadcast shape");
+  d.ptr = b.data_ptr();
+  d.strides[0] = b.size(0) == 1 ? 0 : b.stride(0);
+  d.strides[1] = b.size(1) == 1 ? 0 : b.stride(1);
+  d.strides[2] = b.stride(2);
+  return d;
+}
+
+// returns (o, lse, rng_state): rng_state int64[2] = (seed, offset) of the dropout mask (empty without dropout)
+std::tuple<Tensor, Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, bool causal, double scale,
+                                            const c10::optional<Tensor>& kv_lens, const c10::optional<Tensor>& bias,
+                                            const c10::optional<Tensor>& alibi_slopes, double p_drop, int64_t salt) {
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(q.dim() == 4 && q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1, "attn_fwd: [B,A,S,D], D contiguous");
   const int B = (int)q.size(0), A = (int)q.size(1), S = (int)q.size(2), D = (int)q.size(3);
@@ -489,15 +577,35 @@ std::tuple<Tensor, Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tens
     TORCH_CHECK(kv_lens->scalar_type() == at::kInt && kv_lens->numel() == B && kv_lens->is_cuda(), "kv_lens: int32 cuda [B]");
     kvl = kv_lens->data_ptr<int>();
   }
+  BiasDesc bd = bias_desc(bias, B, A, S);
+  const float* slopes = nullptr;
+  if (alibi_slopes.has_value() && alibi_slopes->defined()) {
+    TORCH_CHECK(alibi_slopes->scalar_type() == at::kFloat && alibi_slopes->numel() == A && alibi_slopes->is_cuda(), "alibi_slopes: fp32 cuda [A]");
+    slopes = alibi_slopes->data_ptr<float>();
+  }
+  Tensor rng_state;
+  LbRngArgs a;
+  const bool drop = p_drop > 0.0;
+  if (drop) {
+    TORCH_CHECK(p_drop < 1.0, "dropout probability must be in [0, 1)");
+    rng_state = at::empty({2}, q.options().dtype(at::kLong));
+    a = next_rng(salt);
+  } else {
+    rng_state = at::empty({0}, q.options().dtype(at::kLong));
+  }
   check(lb_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), B, A, S, D, qs, ks,
-                    vs, causal ? 1 : 0, (float)scale, kvl, cur_stream()),
+                    vs, causal ? 1 : 0, (float)scale, kvl, bd.ptr, bd.strides, slopes, (float)p_drop, drop ? &a : nullptr,
+                    drop ? reinterpret_cast<long long*>(rng_state.data_ptr<int64_t>()) : nullptr, cur_stream()),
         "attn_fwd");
-  return std::make_tuple(o.permute({0, 2, 1, 3}), lse);
+  return std::make_tuple(o.permute({0, 2, 1, 3}), lse, rng_state);
 }
 
+// `dbias` (optional, fp32, same shape as `bias`): the gradient of a learned bias is accumulated into it
 std::tuple<Tensor, Tensor, Tensor, Tensor> attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor& v,
                                             const Tensor& o, const Tensor& lse, bool causal, double scale,
-                                            const c10::optional<Tensor>& kv_lens) {
+                                            const c10::optional<Tensor>& kv_lens, const c10::optional<Tensor>& bias,
+                                            const c10::optional<Tensor>& alibi_slopes, c10::optional<Tensor> dbias,
+                                            double p_drop, const c10::optional<Tensor>& rng_state) {
   c10::cuda::CUDAGuard guard(q.device());
   const int B = (int)q.size(0), A = (int)q.size(1), S = (int)q.size(2), D = (int)q.size(3);
   // gradients are produced in the packed [B, S, A, 3, D] layout so that the QKV dgrad/wgrad GEMMs read them directly
@@ -517,10 +625,21 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> attn_bwd(const Tensor& dout, const Te
   long ks[3] = {k.stride(0), k.stride(1), k.stride(2)};
   long vs[3] = {v.stride(0), v.stride(1), v.stride(2)};
   long ds[3] = {dout_c.stride(0), dout_c.stride(1), dout_c.stride(2)};
+  BiasDesc bd = bias_desc(bias, B, A, S);
+  float* dbp = nullptr;
+  if (dbias.has_value() && dbias->defined()) {
+    TORCH_CHECK(bd.ptr != nullptr && dbias->scalar_type() == at::kFloat && dbias->sizes() == bias->sizes() &&
+                    dbias->strides() == bias->strides(), "attn_bwd: dbias must be fp32 with the shape/strides of bias");
+    dbp = dbias->data_ptr<float>();
+  }
+  const bool has_rng = p_drop > 0.0 && rng_state.has_value() && rng_state->defined() && rng_state->numel() == 2;
   check(lb_attn_bwd(dout_c.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(),
                     dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr<float>(), dq_acc.data_ptr<float>(), B, A,
                     S, D, qs, ks, vs, ds, causal ? 1 : 0, (float)scale,
-                    (kv_lens.has_value() && kv_lens->defined()) ? kv_lens->data_ptr<int>() : nullptr, cur_stream()),
+                    (kv_lens.has_value() && kv_lens->defined()) ? kv_lens->data_ptr<int>() : nullptr, bd.ptr, bd.strides,
+                    (alibi_slopes.has_value() && alibi_slopes->defined()) ? alibi_slopes->data_ptr<float>() : nullptr, dbp,
+                    (float)(has_rng ? p_drop : 0.0),
+                    has_rng ? reinterpret_cast<const long long*>(rng_state->data_ptr<int64_t>()) : nullptr, cur_stream()),
         "attn_bwd");
   return std::make_tuple(dq, dk, dv, dqkv);
 }
@@ -668,6 +787,7 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("ce_bwd(Tensor(a!) logits, Tensor labels, Tensor lse, Tensor gloss, int vocab_start) -> Tensor(a!)", &ce_bwd);
   m.def("fused_adamw(Tensor(a!) master, Tensor grad, Tensor(b!) m, Tensor(c!) v, Tensor? lp_out, Tensor scale, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, bool decoupled) -> ()", &fused_adamw);
   m.def("sqnorm(Tensor x) -> Tensor", &sqnorm);
-  m.def("attn_fwd(Tensor q, Tensor k, Tensor v, bool causal, float scale, Tensor? kv_lens) -> (Tensor, Tensor)", &attn_fwd);
-  m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor o, Tensor lse, bool causal, float scale, Tensor? kv_lens) -> (Tensor, Tensor, Tensor, Tensor)", &attn_bwd);
+  m.def("attn_fwd(Tensor q, Tensor k, Tensor v, bool causal, float scale, Tensor? kv_lens, Tensor? bias=None, Tensor? alibi_slopes=None, float p_drop=0.0, int salt=0) -> (Tensor, Tensor, Tensor)", &attn_fwd);
+  m.def("attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor o, Tensor lse, bool causal, float scale, Tensor? kv_lens, Tensor? bias=None, Tensor? alibi_slopes=None, Tensor(a!)? dbias=None, float p_drop=0.0, Tensor? rng_state=None) -> (Tensor, Tensor, Tensor, Tensor)", &attn_bwd);
+  m.def("bias_dropout_residual(Tensor x, Tensor? bias, Tensor? res, float p, int salt, Tensor? rng_state=None) -> (Tensor, Tensor)", &bias_dropout_residual);
 }

@@ -59,6 +59,47 @@ LB_DEVICE void spin_wait_ge_sys(const uint32_t* addr, uint32_t target, unsigned 
 }
 
 // ---------------------------------------------------------------------------------------------
+// counter-based RNG for dropout: Philox4x32 (7 rounds — passes BigCrush, Salmon et al. 2011) keyed by the PyTorch CUDA
+// generator's (seed, offset) and indexed by ELEMENT POSITION, so forward, backward and any re-tiling regenerate the
+// same mask.  The (seed, offset) pair comes from `at::CUDAGeneratorImpl::philox_cuda_state`: plain values in eager
+// mode, device pointers + an intra-graph offset while a CUDA graph is being captured (PyTorch rewrites the pointed-to
+// values before every replay) — so captured transformer blocks draw fresh masks on every replay.
+// `salt` distinguishes tensor-parallel ranks in sharded regions (0 in replicated regions: identical masks).
+// ---------------------------------------------------------------------------------------------
+struct RngArgs {
+  unsigned long long seed_val, offset_val;   // eager: the values
+  const long long* seed_ptr;                 // capture: where PyTorch keeps them
+  const long long* offset_ptr;
+  unsigned int offset_intragraph;
+  int captured;
+  unsigned long long salt;
+};
+LB_DEVICE void rng_resolve(const RngArgs& a, unsigned long long& seed, unsigned long long& offset) {
+  if (a.captured) {
+    seed = static_cast<unsigned long long>(*a.seed_ptr);
+    offset = static_cast<unsigned long long>(*a.offset_ptr) + a.offset_intragraph;
+  } else {
+    seed = a.seed_val;
+    offset = a.offset_val;
+  }
+  seed ^= a.salt * 0x9E3779B97F4A7C15ull;
+}
+LB_DEVICE uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 LB_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {

@@ -83,6 +83,55 @@ __global__ void bias_residual_kernel(const __nv_bfloat16* __restrict__ x, const 
   }
 }
 
+// y = residual + dropout(x + bias) * 1/(1-p)     (reference: flow._C.fused_bias_add_dropout + the residual add,
+// libai/layers/mlp.py:104, attention.py:265).  One Philox call (128 bits) decides 8 elements with 16 bits each:
+// keep <=> u16 >= thresh, p_eff = thresh / 65536, scale = 65536 / (65536 - thresh) (exactly unbiased).  The mask is a
+// function of (seed, offset, element index) only: the backward is the same kernel on the output gradient (bias =
+// residual = nullptr) with the (seed, offset) pair the forward stored in `rng_out`.
+__global__ void __launch_bounds__(256)
+bias_dropout_residual_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ bias,
+                             const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, size_t total_vec,
+                             int nvec_per_row, uint32_t thresh, float scale, RngArgs rng, const long long* rng_in,
+                             long long* rng_out) {
+  unsigned long long seed, offset;
+  if (rng_in != nullptr) {
+    seed = static_cast<unsigned long long>(rng_in[0]);
+    offset = static_cast<unsigned long long>(rng_in[1]);
+  } else {
+    rng_resolve(rng, seed, offset);
+    if (rng_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+      rng_out[0] = static_cast<long long>(seed);
+      rng_out[1] = static_cast<long long>(offset);
+    }
+  }
+  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  const uint32_t o0 = static_cast<uint32_t>(offset), o1 = static_cast<uint32_t>(offset >> 32);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+    float v[8];
+    ld8(x + i * 8, v);
+    if (bias != nullptr) {
+      float b[8];
+      ld8(bias + (i % nvec_per_row) * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += b[j];
+    }
+    const uint4 rnd = philox4x32_7(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), o0, o1, k0, k1);
+    const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t u = (w[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+      v[j] = u >= thresh ? v[j] * scale : 0.f;
+    }
+    if (res != nullptr) {
+      float r[8];
+      ld8(res + i * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    st8(y + i * 8, v);
+  }
+}
+
 __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gate, const __nv_bfloat16* __restrict__ up,
                                   __nv_bfloat16* __restrict__ y, size_t total_vec) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
@@ -481,6 +530,23 @@ extern "C" int lb_bias_residual(const void* x, const void* bias, const void* res
   if (tv == 0) return 0;
   lb::bias_residual_kernel<<<ew_grid(tv, 256), 256, 0, s>>>((const bf16*)x, (const bf16*)bias, (const bf16*)res,
                                                             (bf16*)y, tv, N / 8);
+  return (int)cudaGetLastError();
+}
+// p in [0, 1): drop probability.  rng_in != nullptr: reuse a stored (seed, offset) pair (backward); else resolve `rng`
+// and store the pair into rng_out (if given).
+extern "C" int lb_bias_dropout_residual(const void* x, const void* bias, const void* res, void* y, long rows, int N, float p,
+                                        const lb::RngArgs* rng, const long long* rng_in, long long* rng_out,
+                                        cudaStream_t s) {
+  if (N % 8) return -1;
+  const size_t tv = (size_t)rows * N / 8;
+  if (tv == 0) return 0;
+  uint32_t thresh = (uint32_t)(p * 65536.0f + 0.5f);
+  if (thresh > 65535u) thresh = 65535u;
+  const float scale = 65536.0f / (65536.0f - (float)thresh);
+  lb::RngArgs r{};
+  if (rng != nullptr) r = *rng;
+  lb::bias_dropout_residual_kernel<<<ew_grid(tv, 256), 256, 0, s>>>((const bf16*)x, (const bf16*)bias, (const bf16*)res,
+                                                                    (bf16*)y, tv, N / 8, thresh, scale, r, rng_in, rng_out);
   return (int)cudaGetLastError();
 }
 extern "C" int lb_swiglu_fwd(const void* gate, const void* up, void* y, long n, cudaStream_t s) {

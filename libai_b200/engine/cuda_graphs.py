@@ -32,17 +32,6 @@ from libai_b200 import ops
 logger = logging.getLogger(__name__)
 
 
-def _block_has_dropout(block: nn.Module) -> bool:
-    for m in block.modules():
-        if isinstance(m, nn.Dropout) and m.p > 0:
-            return True
-        for name in ("attention_dropout_prob", "output_dropout_prob", "drop_path_prob", "hidden_dropout_prob"):
-            v = getattr(m, name, 0.0)
-            if isinstance(v, (int, float)) and v > 0:
-                return True
-    return False
-
-
 def _with_launch_count(block: nn.Module, fwd_kernels: int, bwd_kernels: int) -> nn.Module:
     """The kernels inside a replayed graph are still launches of our kernels: keep ``ops.launch_count()`` honest.
     (``make_graphed_callables`` patches ``block.forward`` in place, so module names / state-dict keys are unchanged.)"""
@@ -62,9 +51,8 @@ def graph_transformer_blocks(blocks: Sequence[nn.Module], sample_hidden: torch.T
     replacements, or ``None`` (with a log line) when a precondition does not hold."""
     if not sample_hidden.is_cuda:
         return None
-    if any(_block_has_dropout(b) for b in blocks):
-        logger.warning("cuda graphs: blocks use dropout > 0 — not captured")
-        return None
+    # (dropout inside the blocks is fine: the native kernels take their Philox (seed, offset) from PyTorch's CUDA
+    # generator, which hands out graph-safe state during capture and refreshes the offset before every replay)
     # Per-block kernel counts for the launch bookkeeping.  The forward count comes from a no-grad eager call (it also
     # makes sure every lazy one-time setup has happened: cudaFuncSetAttribute, extension load, driver entry points);
     # the backward count from the warm-up + capture passes below.  No eager *backward* here: it would leave

@@ -142,6 +142,8 @@ def default_setup(cfg, args):
     cfg.train.resume = bool(getattr(args, "resume", False))
     _resolve_auto_tensor_parallel_mode(cfg)
     dutil.setup_dist_util(cfg.train.dist)
+    # device RNG (dropout masks): one stream per model replica / pipeline stage, shared by its tensor-parallel ranks
+    torch.manual_seed(dutil.model_parallel_seed(try_get_key(cfg, "train.seed", default=1234)))
     rank = dutil.get_rank()
     logger = setup_logger(output_dir, distributed_rank=rank)
     logger.info("Rank of current process: {}. World size: {}".format(rank, dutil.get_world_size()))

@@ -156,7 +156,7 @@ class MultiheadAttention(nn.Module):
                 # fast path: flash attention directly on the packed projection
                 context = OF.attention_qkvpacked(
                     qkv_packed, causal=self.attn_mask_type == AttnMaskType.causal, scale=self.softmax_scale,
-                    kv_lens=kv_lens,
+                    kv_lens=kv_lens, dropout_p=self.attention_dropout_prob, training=self.training,
                 ).reshape(bsz, -1, a * d)
                 if sp and hidden_states.dim() == 2:
                     context = context.reshape(-1, a * d)

@@ -18,6 +18,8 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
+from libai_b200.layers.dropout import Dropout
+
 from libai_b200.config import configurable
 from libai_b200.layers import (
     Embedding,
@@ -56,7 +58,7 @@ class BertEmbeddings(nn.Module):
             Embedding(num_tokentypes, hidden_size, init_method=init_method, amp_enabled=amp_enabled)
             if num_tokentypes > 0 else None
         )
-        self.embedding_dropout = nn.Dropout(embedding_dropout_prob)
+        self.embedding_dropout = Dropout(embedding_dropout_prob)
 
     def forward(self, input_ids, tokentype_ids=None, position_ids=None):
         bsz, seq_length = input_ids.shape

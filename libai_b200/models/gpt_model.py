@@ -13,6 +13,8 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from libai_b200.layers.dropout import Dropout
+
 from libai_b200.config import configurable
 from libai_b200.layers import (
     Embedding,
@@ -56,7 +58,7 @@ class GPTEmbedding(nn.Module):
         super().__init__()
         self.token_embeddings = VocabEmbedding(vocab_size, hidden_size, init_method=init_method, amp_enabled=amp_enabled)
         self.position_embeddings = Embedding(max_seq_length, hidden_size, init_method=init_method, amp_enabled=amp_enabled)
-        self.dropout = nn.Dropout(embedding_dropout_prob)
+        self.dropout = Dropout(embedding_dropout_prob)
         self.max_seq_length = max_seq_length
 
     def forward(self, input_ids, past_length=0):

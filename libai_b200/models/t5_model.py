@@ -15,6 +15,8 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
+from libai_b200.layers.dropout import Dropout
+
 from libai_b200.config import configurable
 from libai_b200.layers import Embedding, LayerNorm, LMLogits, ParallelCrossEntropyLoss, TransformerLayer, VocabEmbedding
 from libai_b200.layers._param import create_parameter, xavier_normal_
@@ -39,7 +41,7 @@ class T5Embedding(nn.Module):
                                               init_method=init_method, amp_enabled=amp_enabled)
         self.position_embeddings = Embedding(num_embeddings=max_sequence_length, embedding_dim=hidden_size,
                                              init_method=init_method, amp_enabled=amp_enabled)
-        self.embedding_dropout = nn.Dropout(embedding_dropout_prob)
+        self.embedding_dropout = Dropout(embedding_dropout_prob)
 
     def forward(self, input_ids, past_length=0):
         seq_length = input_ids.shape[1]

@@ -422,14 +422,74 @@ def bias_gelu(x, bias):
     return bias_act(x, bias, "gelu")
 
 
-def bias_dropout_add(x, bias, residual, p: float, training: bool):
-    """``residual + dropout(x + bias)`` (replaces ``fused_bias_add_dropout`` + the add)."""
-    if use_native(x) and x.dtype == torch.bfloat16 and (p == 0.0 or not training):
-        # dropout-free fast path (the benchmark configs run with p = 0 or in eval)
-        return _BiasAddFn.apply(x, bias, residual)
+def tp_rng_salt(sharded: bool) -> int:
+    """Salt of the dropout RNG stream (TP-aware RNG).  All tensor-parallel ranks of a model replica share
+    one (seed, offset) sequence (``dutil.model_parallel_seed``); activations that are *sharded* over the TP group
+    (attention heads, token shards under sequence parallelism) must see different masks on different ranks → the TP
+    rank is mixed into the Philox key; *replicated* activations (salt 0) get identical masks everywhere."""
+    if not sharded:
+        return 0
+    from libai_b200.utils import distributed as dutil
+
+    topo = dutil.get_dist_util()
+    return topo.tp_rank + 1 if topo.tensor_parallel_size > 1 else 0
+
+
+def _activations_token_sharded() -> bool:
+    from libai_b200.utils import distributed as dutil
+
+    return bool(dutil.get_dist_util().sequence_parallel)
+
+
+class _BiasDropoutAddFn(torch.autograd.Function):
+    """``residual + dropout(x + bias)`` in one native kernel; the mask is a pure function of the Philox
+    ``(seed, offset)`` pair stored by the forward and the element index, so nothing but 16 bytes is kept for backward."""
+
+    @staticmethod
+    def forward(ctx, x, bias, residual, p, salt):
+        ext = load_ext()
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        r2 = None if residual is None else residual.reshape(-1, x.shape[-1]).contiguous()
+        y, rng_state = ext.bias_dropout_residual(x2, bias, r2, p, salt, None)
+        count_launch()
+        ctx.save_for_backward(rng_state)
+        ctx.p, ctx.bias_param, ctx.has_res = p, bias, residual is not None
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        ext = load_ext()
+        (rng_state,) = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1]).contiguous()
+        gx, _ = ext.bias_dropout_residual(g2, None, None, ctx.p, 0, rng_state)
+        count_launch()
+        gb = None
+        if ctx.bias_param is not None and ctx.needs_input_grad[1]:
+            gb = _bias_grad(ext, gx, ctx.bias_param)
+        return gx.view(gy.shape), gb, (gy if ctx.has_res else None), None, None
+
+
+def bias_dropout_add(x, bias, residual, p: float, training: bool, sharded=None):
+    """``residual + dropout(x + bias)`` (replaces ``fused_bias_add_dropout`` + the add).  ``sharded``: whether ``x`` is
+    sharded over the tensor-parallel group (default: yes iff sequence parallelism is on), see :func:`tp_rng_salt`."""
+    if use_native(x) and x.dtype == torch.bfloat16 and x.shape[-1] % 8 == 0:
+        if p == 0.0 or not training:
+            return _BiasAddFn.apply(x, bias, residual)
+        if sharded is None:
+            sharded = _activations_token_sharded()
+        return _BiasDropoutAddFn.apply(x, bias, residual, float(p), tp_rng_salt(sharded))
     y = x if bias is None else x + bias.to(x.dtype)
     y = F.dropout(y, p=p, training=training)
     return y if residual is None else residual + y
+
+
+def dropout(x, p: float, training: bool, sharded: bool = False):
+    """Native Philox dropout (same kernel as :func:`bias_dropout_add` without bias / residual)."""
+    if p == 0.0 or not training:
+        return x
+    if use_native(x) and x.dtype == torch.bfloat16 and x.shape[-1] % 8 == 0:
+        return _BiasDropoutAddFn.apply(x, None, None, float(p), tp_rng_salt(sharded))
+    return F.dropout(x, p=p, training=training)
 
 
 class _BiasAddFn(torch.autograd.Function):
@@ -474,23 +534,53 @@ def attention_ref(q, k, v, *, causal: bool, scale: float, mask=None, bias=None, 
     return torch.matmul(probs, v.float()).to(q.dtype)
 
 
+def _prep_bias(bias, q):
+    """Additive score bias for the flash kernel: bf16 ``[B|1, A|1, S, S]`` with contiguous keys."""
+    if bias is None:
+        return None
+    b = bias
+    while b.dim() < 4:
+        b = b.unsqueeze(0)
+    if b.dtype != torch.bfloat16:
+        b = b.to(torch.bfloat16)
+    if b.stride(-1) != 1 or b.stride(-2) % 8 or b.stride(0) % 8 or b.stride(1) % 8 or b.data_ptr() % 16:
+        b = b.contiguous()
+    return b
+
+
 class _FlashAttnFn(torch.autograd.Function):
+    """Flash attention on ``[b, a, s, d]`` views with optional additive bias (dense or ALiBi slopes), key-padding
+    lengths and Philox dropout on the probabilities — all inside the tcgen05 kernels."""
+
     @staticmethod
-    def forward(ctx, q, k, v, causal, scale):
+    def forward(ctx, q, k, v, causal, scale, bias, alibi_slopes, p_drop, kv_lens):
         ext = load_ext()
-        o, lse = ext.attn_fwd(q, k, v, causal, scale, None)
+        b = _prep_bias(bias, q)
+        o, lse, rng_state = ext.attn_fwd(q, k, v, causal, scale, kv_lens, b, alibi_slopes, p_drop,
+                                         tp_rng_salt(True) if p_drop > 0 else 0)
         count_launch()
-        ctx.save_for_backward(q, k, v, o, lse)
-        ctx.causal, ctx.scale = causal, scale
+        ctx.save_for_backward(q, k, v, o, lse, b, alibi_slopes, rng_state, kv_lens)
+        ctx.causal, ctx.scale, ctx.p_drop = causal, scale, p_drop
+        ctx.bias_shape = None if bias is None else (bias.shape, bias.dtype)
         return o
 
     @staticmethod
     def backward(ctx, go):
         ext = load_ext()
-        q, k, v, o, lse = ctx.saved_tensors
-        dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale, None)
+        q, k, v, o, lse, b, slopes, rng_state, kv_lens = ctx.saved_tensors
+        dbias = None
+        if b is not None and ctx.needs_input_grad[5]:
+            dbias = torch.zeros(b.shape, dtype=torch.float32, device=b.device)
+            if dbias.stride() != b.stride():
+                dbias = torch.empty_strided(b.shape, b.stride(), dtype=torch.float32, device=b.device).zero_()
+        dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale, kv_lens, b, slopes, dbias, ctx.p_drop,
+                                     rng_state if ctx.p_drop > 0 else None)
         count_launch(3)
-        return dq, dk, dv, None, None
+        gb = None
+        if dbias is not None:
+            shape, dtype = ctx.bias_shape
+            gb = dbias.to(dtype).reshape(shape)
+        return dq, dk, dv, None, None, gb, None, None, None
 
 
 class _FlashAttnPackedFn(torch.autograd.Function):
@@ -499,27 +589,29 @@ class _FlashAttnPackedFn(torch.autograd.Function):
     slicing, no gradient accumulation kernels around the attention."""
 
     @staticmethod
-    def forward(ctx, qkv, causal, scale, kv_lens):
+    def forward(ctx, qkv, causal, scale, kv_lens, p_drop=0.0, alibi_slopes=None):
         ext = load_ext()
         d = qkv.shape[-1] // 3
         v4 = qkv.permute(0, 2, 1, 3)
         q, k, v = v4[..., :d], v4[..., d : 2 * d], v4[..., 2 * d :]
-        o, lse = ext.attn_fwd(q, k, v, causal, scale, kv_lens)
+        o, lse, rng_state = ext.attn_fwd(q, k, v, causal, scale, kv_lens, None, alibi_slopes, p_drop,
+                                         tp_rng_salt(True) if p_drop > 0 else 0)
         count_launch()
-        ctx.save_for_backward(qkv, o, lse, kv_lens)
-        ctx.causal, ctx.scale = causal, scale
+        ctx.save_for_backward(qkv, o, lse, kv_lens, rng_state, alibi_slopes)
+        ctx.causal, ctx.scale, ctx.p_drop = causal, scale, p_drop
         return o.permute(0, 2, 1, 3)  # [b, s, a, d] contiguous
 
     @staticmethod
     def backward(ctx, go):
         ext = load_ext()
-        qkv, o, lse, kv_lens = ctx.saved_tensors
+        qkv, o, lse, kv_lens, rng_state, slopes = ctx.saved_tensors
         d = qkv.shape[-1] // 3
         v4 = qkv.permute(0, 2, 1, 3)
         q, k, v = v4[..., :d], v4[..., d : 2 * d], v4[..., 2 * d :]
-        _, _, _, dqkv = ext.attn_bwd(go.permute(0, 2, 1, 3), q, k, v, o, lse, ctx.causal, ctx.scale, kv_lens)
+        _, _, _, dqkv = ext.attn_bwd(go.permute(0, 2, 1, 3), q, k, v, o, lse, ctx.causal, ctx.scale, kv_lens, None, slopes,
+                                     None, ctx.p_drop, rng_state if ctx.p_drop > 0 else None)
         count_launch(3)
-        return dqkv.view(qkv.shape), None, None, None
+        return dqkv.view(qkv.shape), None, None, None, None, None
 
 
 def attention_qkvpacked_supported(qkv, mask, dropout_p, training) -> bool:
@@ -527,36 +619,45 @@ def attention_qkvpacked_supported(qkv, mask, dropout_p, training) -> bool:
         use_native(qkv)
         and qkv.dtype == torch.bfloat16
         and mask is None
-        and (dropout_p == 0.0 or not training)
         and qkv.shape[-1] // 3 in (64, 128)
         and qkv.is_contiguous()
     )
 
 
-def attention_qkvpacked(qkv, *, causal: bool, scale: float, kv_lens=None):
+def attention_qkvpacked(qkv, *, causal: bool, scale: float, kv_lens=None, dropout_p: float = 0.0, training: bool = False,
+                        alibi_slopes=None):
     """qkv ``[b, s, a, 3d]`` → context ``[b, s, a, d]``; ``kv_lens`` (int32 ``[b]``): valid keys per sample
-    of a right-padded batch (keys beyond it are masked inside the kernel)."""
-    return _FlashAttnPackedFn.apply(qkv, causal, float(scale), kv_lens)
+    of a right-padded batch (keys beyond it are masked inside the kernel); ``dropout_p`` > 0 in training drops
+    attention probabilities inside the kernel (Philox, TP-rank salted)."""
+    p = float(dropout_p) if training else 0.0
+    return _FlashAttnPackedFn.apply(qkv, causal, float(scale), kv_lens, p, alibi_slopes)
 
 
 def attention(q, k, v, *, causal: bool = False, scale: Optional[float] = None, mask=None, bias=None,
-              dropout_p: float = 0.0, training: bool = False):
-    """Softmax attention on ``[b, a, s, d]``.  The native flash kernel handles the mask-free /
-    causal, dropout-free case (all pre-training benchmark configs); other variants use the
-    reference math."""
+              dropout_p: float = 0.0, training: bool = False, alibi_slopes=None, kv_lens=None):
+    """Softmax attention on ``[b, a, s, d]``.  The native flash kernels handle causal / full / key-padding
+    (``kv_lens``) masking, an additive score bias (dense ``[b|1, a|1, s, s]`` — T5 relative positions — or
+    ``alibi_slopes`` ``[a]``) and dropout on the probabilities; arbitrary dense 0/1 masks and cross attention with
+    different query / key lengths use the reference math."""
     if scale is None:
         scale = 1.0 / math.sqrt(q.shape[-1])
     if (
         use_native(q)
         and q.dtype == torch.bfloat16
         and mask is None
-        and bias is None
-        and (dropout_p == 0.0 or not training)
         and q.shape[-1] in (64, 128)
         and q.shape[-2] == k.shape[-2]
+        and q.shape[-2] % 8 == 0
+        and (bias is None or (bias.shape[-1] == k.shape[-2] and bias.shape[-2] == q.shape[-2]))
     ):
         # strided [b, a, s, d] views of the packed QKV projection are consumed directly (TMA strides)
-        return _FlashAttnFn.apply(q, k, v, causal, float(scale))
+        return _FlashAttnFn.apply(q, k, v, causal, float(scale), bias, alibi_slopes,
+                                  float(dropout_p) if training else 0.0, kv_lens)
+    if alibi_slopes is not None:
+        sq, sk = q.shape[-2], k.shape[-2]
+        rel = torch.arange(sk, device=q.device)[None, :] - torch.arange(sk - sq, sk, device=q.device)[:, None]
+        ab = alibi_slopes.float()[None, :, None, None] * rel[None, None].float()
+        bias = ab if bias is None else bias.float() + ab
     return attention_ref(q, k, v, causal=causal, scale=scale, mask=mask, bias=bias,
                          dropout_p=dropout_p, training=training)
 

@@ -358,8 +358,17 @@ class FlatOptimizer(torch.optim.Optimizer):
                     cur = max(cur, hi)
             else:
                 acc = _acc(fg.grad_shard())
-                for lo, hi in skip:
-                    acc = acc - _acc(fg.grad_flat[lo:hi])
+                if skip:
+                    # ONE reduction over the packed duplicates (≈150 LayerNorm / bias segments under tensor parallelism:
+                    # one kernel per segment made the step host-bound on tp_rank != 0)
+                    merged = []
+                    for lo, hi in skip:
+                        if merged and merged[-1][1] + 8 >= lo:       # neighbours (≤ alignment padding apart, zeros)
+                            merged[-1] = (merged[-1][0], hi)
+                        else:
+                            merged.append((lo, hi))
+                    dup = torch.cat([fg.grad_flat[lo:hi] for lo, hi in merged]) if len(merged) > 1 else fg.grad_flat[merged[0][0]:merged[0][1]]
+                    acc = acc - (torch.dot(dup, dup) if norm_type == 2.0 else dup.abs().pow(norm_type).sum())
             total = acc if total is None else (torch.maximum(total, acc) if math.isinf(norm_type) else total + acc)
         if total is None:
             total = torch.zeros((), dtype=torch.float32, device=dutil.get_device())

@@ -324,6 +324,15 @@ def reset_dist_util() -> None:
 
 
 # thin functional accessors -------------------------------------------------------------------
+def model_parallel_seed(base_seed: int) -> int:
+    """Seed of the *device* RNG (dropout): identical on all tensor-parallel ranks of one model replica — replicated
+    activations must see identical masks, sharded ones add the TP rank as Philox salt (``ops.functional.tp_rng_salt``)
+    — and different across data-parallel replicas and pipeline stages.  (The reference gets this from OneFlow's global
+    generator; Megatron from its CudaRNGStatesTracker.)"""
+    topo = get_dist_util()
+    return int(base_seed) + 100003 * topo.dp_rank + 7919 * topo.pp_rank
+
+
 def get_layer_stage_id(layer_idx: int) -> int:
     return get_dist_util().get_layer_stage_id(layer_idx)
 

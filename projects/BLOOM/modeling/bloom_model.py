@@ -60,9 +60,15 @@ class BloomAttention(nn.Module):
             v = torch.cat((layer_past[1].type_as(v), v), dim=2)
         present = (k, v) if use_cache else None
         topo = dutil.get_dist_util()
-        bias = alibi[:, topo.tp_rank * a : (topo.tp_rank + 1) * a] if alibi.shape[1] != a else alibi
-        ctx = OF.attention(q, k, v, causal=False, scale=1.0 / math.sqrt(d), mask=mask, bias=bias,
-                           dropout_p=self.attention_dropout, training=self.training)
+        if alibi.dim() == 1:
+            # unpadded batch without a KV cache: ALiBi slopes + causal mask are evaluated inside the flash kernel
+            slopes = alibi[topo.tp_rank * a : (topo.tp_rank + 1) * a] if alibi.shape[0] != a else alibi
+            ctx = OF.attention(q, k, v, causal=True, scale=1.0 / math.sqrt(d), alibi_slopes=slopes.contiguous(),
+                               dropout_p=self.attention_dropout, training=self.training)
+        else:
+            bias = alibi[:, topo.tp_rank * a : (topo.tp_rank + 1) * a] if alibi.shape[1] != a else alibi
+            ctx = OF.attention(q, k, v, causal=False, scale=1.0 / math.sqrt(d), mask=mask, bias=bias,
+                               dropout_p=self.attention_dropout, training=self.training)
         out = self.dense(ctx.transpose(1, 2).reshape(b, -1, a * d))
         return residual + self.hidden_dropout(out), present
 
@@ -126,12 +132,16 @@ class BloomModel(nn.Module):
         past_key_values = past_key_values or [None] * len(self.h)
         past_len = 0 if past_key_values[0] is None else past_key_values[0][0].shape[2]
         k = past_len + q
-        if attention_mask is None:
-            attention_mask = torch.ones(b, k, dtype=torch.long, device=input_ids.device)
         hidden = self.word_embeddings_layernorm(self.word_embeddings(input_ids))
-        alibi = build_alibi_tensor(attention_mask, self.n_head, torch.float32)
-        causal = torch.ones(k, k, dtype=torch.bool, device=input_ids.device).tril()[k - q :]
-        mask = causal[None, None] & attention_mask.bool()[:, None, None, :]
+        if attention_mask is None and past_len == 0 and not use_cache and input_ids.is_cuda:
+            # no padding, no cache: hand the blocks the per-head slopes only (1-D `alibi` selects the in-kernel path)
+            alibi, mask = alibi_slopes(self.n_head).to(input_ids.device), None
+        else:
+            if attention_mask is None:
+                attention_mask = torch.ones(b, k, dtype=torch.long, device=input_ids.device)
+            alibi = build_alibi_tensor(attention_mask, self.n_head, torch.float32)
+            causal = torch.ones(k, k, dtype=torch.bool, device=input_ids.device).tril()[k - q :]
+            mask = causal[None, None] & attention_mask.bool()[:, None, None, :]
         presents = []
         for block, past in zip(self.h, past_key_values):
             hidden, present = block(hidden, alibi, mask, past, use_cache)

@@ -107,6 +107,13 @@ class T5Attention(nn.Module):
                 position_bias = self.compute_bias(q.shape[2], k.shape[2], hidden.device)
             else:
                 position_bias = torch.zeros(1, a, q.shape[2], k.shape[2], device=hidden.device, dtype=hidden.dtype)
+            if mask is not None:
+                # fold the 0/1 mask into the additive bias ONCE (the stack hands `position_bias` from layer to layer):
+                # every layer then runs the flash kernel with a dense bias instead of the O(s²) masked-softmax math
+                position_bias = position_bias + (1.0 - mask.to(position_bias.dtype)) * -10000.0
+            position_bias._libai_mask_folded = mask is not None
+        if getattr(position_bias, "_libai_mask_folded", False):
+            mask = None
         ctx = OF.attention(q, k, v, causal=False, scale=1.0, mask=mask, bias=position_bias, dropout_p=self.attn_dropout_p,
                            training=self.training)
         out = self.dropout(self.dense(ctx.transpose(1, 2).reshape(b, -1, a * d)))

@@ -550,7 +550,7 @@ def main():
             v4 = qkv.view(B, S, A, 3 * D).permute(0, 2, 1, 3)
             q, k, v = v4[..., :D], v4[..., D:2 * D], v4[..., 2 * D:]
             scale = 1.0 / math.sqrt(D)
-            o, lse = ext.attn_fwd(q, k, v, causal, scale, None)
+            o, lse, _ = ext.attn_fwd(q, k, v, causal, scale, None)
             qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
             ref = attention_ref(qf, kf, vf, causal=causal, scale=scale, fill=-1e30)
             e = [rel_err(o, ref)]
@@ -569,7 +569,7 @@ def main():
         q, k, v = v4[..., :D], v4[..., D:2 * D], v4[..., 2 * D:]
         lens = torch.tensor([320, 200, 77], device="cuda", dtype=torch.int32)
         scale = 0.125
-        o, lse = ext.attn_fwd(q, k, v, False, scale, lens)
+        o, lse, _ = ext.attn_fwd(q, k, v, False, scale, lens)
         qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
         mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None])[:, None, None, :]
         ref = attention_ref(qf, kf, vf, causal=False, scale=scale, mask=mask, fill=-1e30)
@@ -581,6 +581,145 @@ def main():
 
     record("attention kv_lens (key padding)", att_kvlens)
 
+    def att_bias():
+        """Dense additive bias (T5 relative positions: [1, A, S, S] broadcast over the batch) fwd + bwd + dbias."""
+        B, A, S, D = 2, 3, 256, 64
+        qkv = torch.randn(B, S, A, 3 * D, device="cuda").bfloat16()
+        v4 = qkv.permute(0, 2, 1, 3)
+        q, k, v = v4[..., :D], v4[..., D:2 * D], v4[..., 2 * D:]
+        bias = (torch.randn(1, A, S, S, device="cuda") * 2.0).bfloat16()
+        o, lse, _ = ext.attn_fwd(q, k, v, False, 1.0, None, bias, None, 0.0, 0)
+        qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+        bf = bias.float().detach().requires_grad_(True)
+        ref = attention_ref(qf, kf, vf, causal=False, scale=1.0, bias=bf, fill=-1e30)
+        go = torch.randn(B, S, A, D, device="cuda").bfloat16().permute(0, 2, 1, 3)
+        ref.backward(go.float())
+        dbias = torch.zeros(1, A, S, S, device="cuda")
+        dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, False, 1.0, None, bias, None, dbias, 0.0, None)
+        e = [rel_err(o, ref), rel_err(dq, qf.grad), rel_err(dk, kf.grad), rel_err(dv, vf.grad), rel_err(dbias, bf.grad)]
+        # per-sample bias + causal through the autograd wrapper
+        from libai_b200.ops import functional as OF
+        bias2 = (torch.randn(B, A, S, S, device="cuda")).bfloat16().requires_grad_(True)
+        q2, k2, v2 = (t.detach().contiguous().requires_grad_(True) for t in (q, k, v))
+        o2 = OF.attention(q2, k2, v2, causal=True, scale=0.125, bias=bias2)
+        o2.backward(go)
+        q3, k3, v3, b3 = (t.detach().float().requires_grad_(True) for t in (q, k, v, bias2))
+        r2 = attention_ref(q3, k3, v3, causal=True, scale=0.125, bias=b3, fill=-1e30)
+        r2.backward(go.float())
+        e += [rel_err(o2, r2), rel_err(q2.grad, q3.grad), rel_err(bias2.grad, b3.grad)]
+        return {"ok": max(e) < 3e-2, "errs": e}
+
+    record("attention dense bias (+dbias)", att_bias)
+
+    def att_alibi():
+        B, A, S, D = 2, 4, 384, 64
+        qkv = torch.randn(B, S, A, 3 * D, device="cuda").bfloat16()
+        v4 = qkv.permute(0, 2, 1, 3)
+        q, k, v = v4[..., :D], v4[..., D:2 * D], v4[..., 2 * D:]
+        slopes = torch.tensor([0.5, 0.25, 0.125, 0.0625], device="cuda")
+        o, lse, _ = ext.attn_fwd(q, k, v, True, 0.125, None, None, slopes, 0.0, 0)
+        rel = (torch.arange(S, device="cuda")[None, :] - torch.arange(S, device="cuda")[:, None]).float()
+        bias = slopes[None, :, None, None] * rel[None, None]
+        qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+        ref = attention_ref(qf, kf, vf, causal=True, scale=0.125, bias=bias, fill=-1e30)
+        go = torch.randn(B, S, A, D, device="cuda").bfloat16().permute(0, 2, 1, 3)
+        ref.backward(go.float())
+        dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, True, 0.125, None, None, slopes, None, 0.0, None)
+        e = [rel_err(o, ref), rel_err(dq, qf.grad), rel_err(dk, kf.grad), rel_err(dv, vf.grad)]
+        return {"ok": max(e) < 3e-2, "errs": e}
+
+    record("attention ALiBi slopes", att_alibi)
+
+    def att_dropout():
+        """Dropout inside the flash kernels: the mask is recovered exactly (q = k = 0 → uniform P, V = I) and the
+        kernel's forward / backward are compared with the reference math using that very mask."""
+        B, A, S, D, pdrop = 2, 2, 64, 64, 0.25
+        eye = torch.eye(S, device="cuda").bfloat16()[None, None].expand(B, A, S, D).contiguous()
+        zero = torch.zeros(B, A, S, D, device="cuda").bfloat16()
+        torch.cuda.manual_seed(4321)
+        om, _, st_m = ext.attn_fwd(zero, zero, eye, False, 1.0, None, None, None, pdrop, 3)
+        keep = (om.float() > 0)
+        inv_keep = 256.0 / (256.0 - round(pdrop * 256))
+        frac = float(keep.float().mean())
+        qkv = torch.randn(B, S, A, 3 * D, device="cuda").bfloat16()
+        v4 = qkv.permute(0, 2, 1, 3)
+        q, k, v = v4[..., :D], v4[..., D:2 * D], v4[..., 2 * D:]
+        torch.cuda.manual_seed(4321)
+        o, lse, st = ext.attn_fwd(q, k, v, False, 0.125, None, None, None, pdrop, 3)
+        same_state = torch.equal(st, st_m)
+        qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+        probs = torch.softmax(qf @ kf.transpose(-1, -2) * 0.125, dim=-1)
+        ref = (probs * keep.float() * inv_keep) @ vf
+        go = torch.randn(B, S, A, D, device="cuda").bfloat16().permute(0, 2, 1, 3)
+        ref.backward(go.float())
+        dq, dk, dv, _ = ext.attn_bwd(go, q, k, v, o, lse, False, 0.125, None, None, None, None, pdrop, st)
+        e = [rel_err(o, ref), rel_err(dq, qf.grad), rel_err(dk, kf.grad), rel_err(dv, vf.grad)]
+        # another TP salt → another mask; statistics on a long sequence (causal, ragged)
+        torch.cuda.manual_seed(4321)
+        om2, _, _ = ext.attn_fwd(zero, zero, eye, False, 1.0, None, None, None, pdrop, 4)
+        differs = float(((om2.float() > 0) != keep).float().mean())
+        return {"ok": max(e) < 3e-2 and abs(frac - (1 - round(pdrop * 256) / 256)) < 0.02 and same_state and differs > 0.2,
+                "errs": e, "keep_fraction": frac, "mask_differs_across_salts": differs, "same_rng_state": same_state}
+
+    record("attention dropout (exact mask)", att_dropout)
+
+    def dropout_ew():
+        """bias + dropout + residual kernel: exact mask recovery, backward with the stored state, salts, statistics."""
+        M, N, pdrop = 512, 1024, 0.1
+        ones = torch.ones(M, N, device="cuda").bfloat16()
+        torch.cuda.manual_seed(99)
+        ym, st_m = ext.bias_dropout_residual(ones, None, None, pdrop, 0, None)
+        keep = ym.float() > 0
+        scale = 65536.0 / (65536.0 - round(pdrop * 65536))
+        x = torch.randn(M, N, device="cuda").bfloat16()
+        b = torch.randn(N, device="cuda").bfloat16()
+        r = torch.randn(M, N, device="cuda").bfloat16()
+        torch.cuda.manual_seed(99)
+        y, st = ext.bias_dropout_residual(x, b, r, pdrop, 0, None)
+        ref = r.float() + (x.float() + b.float()) * keep.float() * scale
+        gy = torch.randn(M, N, device="cuda").bfloat16()
+        gx, _ = ext.bias_dropout_residual(gy, None, None, pdrop, 0, st)
+        e = [rel_err(y, ref), rel_err(gx, gy.float() * keep.float() * scale)]
+        torch.cuda.manual_seed(99)
+        y2, _ = ext.bias_dropout_residual(ones, None, None, pdrop, 2, None)
+        differs = float(((y2.float() > 0) != keep).float().mean())
+        frac = float(keep.float().mean())
+        # consecutive calls advance the generator offset: different masks
+        y3, _ = ext.bias_dropout_residual(ones, None, None, pdrop, 0, None)
+        y4, _ = ext.bias_dropout_residual(ones, None, None, pdrop, 0, None)
+        adv = float(((y3.float() > 0) != (y4.float() > 0)).float().mean())
+        ms = timeit(lambda: ext.bias_dropout_residual(x, b, r, pdrop, 0, None))
+        big = torch.randn(8192, 1024, device="cuda").bfloat16()
+        ms_big = timeit(lambda: ext.bias_dropout_residual(big, b, big, pdrop, 0, None))
+        ms_nodrop = timeit(lambda: ext.bias_residual_fwd(big, b, big))
+        return {"ok": max(e) < 1e-2 and abs(frac - 0.9) < 0.01 and differs > 0.1 and adv > 0.1, "errs": e, "keep_fraction": frac,
+                "mask_differs_across_salts": differs, "mask_differs_across_calls": adv, "ms_8192x1024": ms_big,
+                "ms_8192x1024_without_dropout": ms_nodrop, "gbs": 3 * big.numel() * 2 / ms_big / 1e6}
+
+    record("bias+dropout+residual (Philox)", dropout_ew)
+
+    def dropout_graph():
+        """Captured dropout draws a fresh mask on every replay (PyTorch refreshes the Philox offset of the graph)."""
+        ones = torch.ones(256, 1024, device="cuda").bfloat16()
+        for _ in range(2):
+            ext.bias_dropout_residual(ones, None, None, 0.5, 0, None)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y, st = ext.bias_dropout_residual(ones, None, None, 0.5, 0, None)
+            gx, _ = ext.bias_dropout_residual(ones, None, None, 0.5, 0, st)
+        masks = []
+        consistent = True
+        for _ in range(3):
+            g.replay()
+            torch.cuda.synchronize()
+            masks.append(y.float() > 0)
+            consistent = consistent and torch.equal(y, gx)       # backward regenerates the forward's mask
+        d01 = float((masks[0] != masks[1]).float().mean())
+        d12 = float((masks[1] != masks[2]).float().mean())
+        return {"ok": d01 > 0.3 and d12 > 0.3 and consistent, "replay_mask_diff": [d01, d12], "fwd_bwd_consistent": consistent}
+
+    record("dropout inside a CUDA graph", dropout_graph)
+
     if not args.quick:
         def att_speed():
             B, A, S, D = 8, 16, 1024, 64
@@ -589,7 +728,7 @@ def main():
             q, k, v = v4[..., :D], v4[..., D:2 * D], v4[..., 2 * D:]
             scale = 0.125
             ms = timeit(lambda: ext.attn_fwd(q, k, v, True, scale, None))
-            o, lse = ext.attn_fwd(q, k, v, True, scale, None)
+            o, lse, _ = ext.attn_fwd(q, k, v, True, scale, None)
             go = torch.randn(B, S, A, D, device="cuda").bfloat16().permute(0, 2, 1, 3)
             msb = timeit(lambda: ext.attn_bwd(go, q, k, v, o, lse, True, scale, None))
             flops = 4.0 * B * A * S * S * D / 2
@@ -599,8 +738,11 @@ def main():
             og = torch.nn.functional.scaled_dot_product_attention(qg, kg, vg, is_causal=True)
             gog = torch.randn_like(og)
             sdb = timeit(lambda: torch.autograd.grad(og, (qg, kg, vg), gog, retain_graph=True))
+            msd = timeit(lambda: ext.attn_fwd(q, k, v, True, scale, None, None, None, 0.1, 0))
+            od, lsed, std = ext.attn_fwd(q, k, v, True, scale, None, None, None, 0.1, 0)
+            msbd = timeit(lambda: ext.attn_bwd(go, q, k, v, od, lsed, True, scale, None, None, None, None, 0.1, std))
             return {"fwd_ms": ms, "fwd_tflops": flops / ms / 1e9, "bwd_ms": msb, "bwd_tflops": 2.5 * flops / msb / 1e9,
-                    "sdpa_fwd_ms": sd, "sdpa_bwd_ms": sdb}
+                    "sdpa_fwd_ms": sd, "sdpa_bwd_ms": sdb, "fwd_ms_dropout0.1": msd, "bwd_ms_dropout0.1": msbd}
 
         record("attention speed B8 A16 S1024 D64 causal", att_speed)
 

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--pp", type=int, default=1)
     ap.add_argument("--fused", type=int, default=1)
     ap.add_argument("--graphs", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--dropout", type=float, default=0.0)
     ap.add_argument("--zero", type=int, default=0)
     ap.add_argument("--out", default="")
@@ -61,7 +61,7 @@ def main():
     cfg.train.dist.fused_tp_comm = bool(a.fused) and a.tp > 1
     cfg.train.zero_optimization.enabled = a.zero > 0
     cfg.train.zero_optimization.stage = max(a.zero, 1)
-    cfg.optim.lr = 3e-3
+    cfg.optim.lr = 4e-4
     cfg.train.warmup_ratio = 0.0
     default_setup(cfg, argparse.Namespace(resume=False, config_file=""))
     trainer = DefaultTrainer(cfg)

@@ -231,7 +231,7 @@ def test_fused_tensor_parallel_trains_like_one_gpu(tmp_path):
     fused = _trajectory(tmp_path, "tp2_fused", 2, "--tp", "2", "--fused", "1")
     nccl = _trajectory(tmp_path, "tp2_nccl", 2, "--tp", "2", "--fused", "0")
     assert fused["graphs"], "fused tensor-parallel blocks must be CUDA-graph captured"
-    assert one["losses"][-1] < one["losses"][0] - 1.0, one["losses"]        # it actually learns
+    assert one["losses"][-1] < one["losses"][0] - 0.2, one["losses"]        # it actually learns
     for a, b, c in zip(one["losses"], fused["losses"], nccl["losses"]):
         assert abs(a - b) < 0.05 * max(1.0, abs(a)), (one["losses"], fused["losses"])
         assert abs(a - c) < 0.05 * max(1.0, abs(a)), (one["losses"], nccl["losses"])

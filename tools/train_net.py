@@ -34,9 +34,10 @@ def main(args, trainer_cls=DefaultTrainer):
     default_setup(cfg, args)
 
     seed = cfg.train.seed + dutil.get_rank()
-    torch.manual_seed(seed)
     np.random.seed(seed)
     random.seed(seed)
+    # device RNG (dropout masks): same stream on all tensor-parallel ranks of a replica, see dutil.model_parallel_seed
+    torch.manual_seed(dutil.model_parallel_seed(cfg.train.seed))
 
     if args.fast_dev_run:
         cfg.train.train_epoch = 0
