@@ -32,6 +32,20 @@ sys.path.insert(0, REPO)
 # published LiBai numbers for the GPT-2 data-parallel rows (samples/s × 1024 tokens), BASELINE.md #6-#8
 PUBLISHED_TOKENS_PER_S = {1: 17940.0, 4: 64973.0, 8: 128655.0}
 
+# benchmark models: the headline (gpt2 = the reference's benchmark GPT-2) and the other BASELINE.json configs
+MODELS = {
+    "gpt2": dict(cfg="configs/gpt2_synthetic.py", layers=24, hidden=1024, heads=16, seq=1024, micro=8, unit="tokens/s",
+                 name="GPT-2 nl{layers} h{hidden} a{heads} (reference benchmark model, ~355M params)"),
+    "gpt2_large": dict(cfg="configs/gpt2_synthetic.py", layers=36, hidden=1280, heads=20, seq=1024, micro=8, unit="tokens/s",
+                       name="GPT-2 large nl{layers} h{hidden} a{heads} (~774M params)"),
+    "bert_large": dict(cfg="configs/bert_large_synthetic.py", layers=24, hidden=1024, heads=16, seq=512, micro=16,
+                       unit="tokens/s", name="BERT-large nl{layers} h{hidden} a{heads} s512 (reference benchmark BERT)"),
+    "llama7b": dict(cfg="projects/Llama/configs/llama7b_synthetic.py", layers=32, hidden=4096, heads=32, seq=2048, micro=1,
+                    unit="tokens/s", name="Llama-2 7B nl{layers} h{hidden} a{heads} ffn11008 s2048"),
+    "vit_l": dict(cfg="configs/vit_large_synthetic.py", layers=24, hidden=1024, heads=16, seq=197, micro=128, unit="images/s",
+                  name="ViT-Large/16 224x224 nl{layers} h{hidden} a{heads}"),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -39,11 +53,17 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "ref", "reference"])
-    ap.add_argument("--micro-batch", type=int, default=8, help="samples per GPU per step")
-    ap.add_argument("--layers", type=int, default=24)
-    ap.add_argument("--hidden", type=int, default=1024)
-    ap.add_argument("--heads", type=int, default=16)
-    ap.add_argument("--seq", type=int, default=1024)
+    ap.add_argument("--model", default="gpt2", choices=sorted(MODELS),
+                    help="gpt2 (default, the headline: reference benchmark GPT-2 nl24 h1024) | gpt2_large | bert_large | "
+                         "llama7b | vit_l — the other BASELINE.json configs; metric stays tokens/s (images/s for vit_l)")
+    ap.add_argument("--micro-batch", type=int, default=0, help="samples per GPU per step (0 = the model's default)")
+    ap.add_argument("--layers", type=int, default=0)
+    ap.add_argument("--hidden", type=int, default=0)
+    ap.add_argument("--heads", type=int, default=0)
+    ap.add_argument("--seq", type=int, default=0)
+    ap.add_argument("--dropout", type=float, default=-1.0,
+                    help="override every dropout probability of the model (the reference's gpt2_pretrain recipe trains "
+                         "with 0.1; the synthetic benchmark config and the published benchmark use 0)")
     ap.add_argument("--tp", type=int, default=1, help="tensor-parallel size of the PRIMARY layout (sequence parallel + "
                     "collectives fused into the GEMM kernels); per-DP-rank micro-batch is scaled so that the global batch "
                     "stays --micro-batch x --gpus")
@@ -67,7 +87,14 @@ def parse_args():
     ap.add_argument("--fp8", type=int, default=0,
                     help="1: forward GEMMs with E4M3 operands (experiment; the headline number is the bf16 default — "
                          "the JSON line then says dtype fp8-fwd/bf16-bwd)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    spec = MODELS[a.model]
+    for k in ("layers", "hidden", "heads", "seq"):
+        if not getattr(a, k):
+            setattr(a, k, spec[k])
+    if not a.micro_batch:
+        a.micro_batch = spec["micro"]
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -196,14 +223,34 @@ def layout_name(lay):
 def build_cfg(args, lay):
     from libai_b200.config import LazyConfig
 
-    cfg = LazyConfig.load(os.path.join(REPO, "configs", "gpt2_synthetic.py"))
+    spec = MODELS[args.model]
+    cfg = LazyConfig.load(os.path.join(REPO, spec["cfg"]))
     m = cfg.model.cfg
-    m.hidden_layers, m.hidden_size, m.num_attention_heads = args.layers, args.hidden, args.heads
-    m.ffn_hidden_size = 4 * args.hidden
-    m.max_seq_length = args.seq
-    for ds in cfg.dataloader.train.dataset:
-        ds.seq_length = args.seq
-        ds.vocab_size = m.vocab_size
+    if args.model in ("gpt2", "gpt2_large"):
+        m.hidden_layers, m.hidden_size, m.num_attention_heads = args.layers, args.hidden, args.heads
+        m.ffn_hidden_size = 4 * args.hidden
+        m.max_seq_length = args.seq
+        for ds in cfg.dataloader.train.dataset:
+            ds.seq_length = args.seq
+            ds.vocab_size = m.vocab_size
+    elif args.model == "bert_large":
+        m.hidden_layers, m.hidden_size, m.num_attention_heads = args.layers, args.hidden, args.heads
+        m.intermediate_size = 4 * args.hidden
+        if args.dropout < 0:   # like the GPT-2 benchmark config: dropout-free unless asked for
+            m.hidden_dropout_prob = m.attention_probs_dropout_prob = 0.0
+    elif args.model == "llama7b":
+        m.hidden_layers, m.hidden_size, m.num_attention_heads = args.layers, args.hidden, args.heads
+        if args.hidden != 4096:
+            m.intermediate_size = (int(args.hidden * 8 / 3) + 127) // 128 * 128
+        m.max_position_embeddings = args.seq
+        for ds in cfg.dataloader.train.dataset:
+            ds.seq_length = args.seq
+    elif args.model == "vit_l":
+        m.depth, m.embed_dim, m.num_heads = args.layers, args.hidden, args.heads
+    if args.dropout >= 0:
+        for k in list(m.keys()):
+            if "dropout" in k or k in ("drop_rate", "attn_drop_rate"):
+                m[k] = args.dropout
     cfg.dataloader.train.num_workers = 2
     cfg.train.train_micro_batch_size = lay["micro"]
     cfg.train.num_accumulation_steps = lay["acc"]
@@ -219,6 +266,7 @@ def build_cfg(args, lay):
     cfg.train.dist.pipeline_parallel_size = lay["pp"]
     cfg.train.dist.pipeline_num_layers = args.layers
     cfg.train.dist.data_parallel_size = lay["dp"]
+    cfg.train.input_placement_device = "cuda"
     # tensor parallelism = token-sharded activations + AG->GEMM / GEMM->RS kernels ("auto" resolves to this for GPT-2;
     # spelled out so that the bench line can state it)
     cfg.train.dist.sequence_parallel = lay["tp"] > 1
@@ -274,7 +322,8 @@ def measure_native(args, lay, world, rank, local_rank, steps, warmup, with_e2e, 
     trainer = BenchTrainer(cfg)  # public API: builds model, optimizer, scheduler, loader, hooks
     step = trainer._trainer      # the StepTrainer behind trainer.run_step()
     topo = dutil.get_dist_util()
-    tokens_per_step = cfg.train.global_batch_size * args.seq
+    # work units per step: tokens (images for the vision model)
+    tokens_per_step = cfg.train.global_batch_size * (1 if args.model == "vit_l" else args.seq)
     assert cfg.train.global_batch_size == args.micro_batch * world, (cfg.train.global_batch_size, args.micro_batch, world)
     if args.fp8:
         ops.set_fp8(True)
@@ -464,7 +513,7 @@ def main():
 
     layouts = {main_res["parallelism"]: {k: main_res[k] for k in ("value", "ms_per_step", "cuda_graphs", "gpu_launches",
                                                                   "host_enqueue_ms_per_step", "global_batch")}}
-    if args.extras and args.impl == "native" and not args.layout and args.tp == 1 and args.pp == 1:
+    if args.extras and args.impl == "native" and args.model == "gpt2" and not args.layout and args.tp == 1 and args.pp == 1:
         # the model-parallel layouts that fit this GPU count, same global batch, same launch (BASELINE.json configs:
         # "TP=2 DP=4", "TP=2 PP=2 DP=2 + ZeRO-1")
         names = {2: ["tp2"], 4: ["tp2", "3d"], 8: ["tp2", "3d"]}.get(world, [])
@@ -481,16 +530,19 @@ def main():
                     raise      # a rank-local failure would leave the others in a collective: fail loudly instead
 
     ref_same_box = None
-    if args.ref_same_box and args.impl == "native":
+    if args.ref_same_box and args.impl == "native" and args.model == "gpt2":
         ref_same_box = measure_pytorch_baseline(args, world, rank, local_rank, min(args.steps, 10), 3)
 
     if rank == 0:
-        base = PUBLISHED_TOKENS_PER_S.get(world)
+        base = PUBLISHED_TOKENS_PER_S.get(world) if args.model == "gpt2" else None
         value = main_res["value"]
+        spec = MODELS[args.model]
+        unit = spec["unit"]
         line = {
-            "metric": "tokens/sec GPT-2 (nl24 h1024 a16 s1024) pre-training, device-timed max-over-ranks",
+            "metric": ("tokens/sec GPT-2 (nl24 h1024 a16 s1024) pre-training, device-timed max-over-ranks" if args.model == "gpt2"
+                       else f"{unit.replace('/s', '/sec')} {args.model} pre-training, device-timed max-over-ranks"),
             "value": value,
-            "unit": "tokens/s",
+            "unit": unit,
             "n_gpus": world,
             "steps": args.steps,
             "warmup": args.warmup,
@@ -499,10 +551,10 @@ def main():
             "scaling": "weak",
             "vs_baseline": (value / base) if base else None,
             "dtype": "bf16" if not args.fp8 else "fp8(e4m3)-fwd/bf16-bwd",
-            "data": "synthetic tokens, random-init weights",
+            "data": ("synthetic images" if args.model == "vit_l" else "synthetic tokens") + ", random-init weights",
             "impl": args.impl,
             "config": {
-                "model": f"GPT-2 nl{args.layers} h{args.hidden} a{args.heads} (reference benchmark model, ~355M params)",
+                "model": spec["name"].format(layers=args.layers, hidden=args.hidden, heads=args.heads),
                 "global_batch": main_res["global_batch"],
                 "micro_batch_per_gpu": args.micro_batch,
                 "seq_len": args.seq,
