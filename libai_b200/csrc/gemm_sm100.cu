@@ -75,6 +75,7 @@ struct CommParams {
   int n_comm;                   // COMM_AG: number of copy CTAs
   int gathered_is_b;            // COMM_AG with the TN layout: the gathered operand is B, gated per k-block
   int fill_local;               // COMM_AG: the copy CTAs also write the local shard into the local gathered buffer
+  int copy_rings;               // COMM_AG: independent copy engines (threads with their own smem ring) per copy CTA
   uint32_t arrivals;            // arrivals per row block and call (AG: 1; RS: world * n_blocks)
   uint32_t* state;              // local: [0] completed calls on this buffer set, [1] CTA exit counter
   __nv_bfloat16* peer_buf[8];   // AG: gathered buffers of all ranks; RS: staging buffers of all ranks
@@ -268,11 +269,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // first); after a row block has fully landed the peer's arrival counter is bumped with a system-scope release.
     // WAR safety: the gathered buffers are double-buffered by call parity; a peer only finishes call n-1 after our
     // pushes of call n-1, which we issue after our call n-2 kernel ended, so nobody still reads parity (n-2).
-    if (threadIdx.x == 0) {
-      constexpr uint32_t CHUNK = 32768;
-      constexpr int NSLOT = (NS * Cfg::STAGE_BYTES) / CHUNK < 2 * NS ? (NS * Cfg::STAGE_BYTES) / CHUNK : 2 * NS;
-      static_assert(NSLOT >= 3, "ring too small");
-      uint64_t* bars = full_bar;  // full_bar[NS] and empty_bar[NS] are contiguous, all initialised with count 1
+    // `copy_rings` independent engines per copy CTA (lane 0 of the first warps), each with its own slice of the
+    // (otherwise idle) pipeline smem as a 6-slot ring and its own mbarriers: one engine alone is latency bound
+    // (~1.6 us per 32 KB chunk, ~20 GB/s — profiles/r2_04_comm_bench_2gpu.json).
+    const int n_rings = cp.copy_rings > 0 ? cp.copy_rings : 1;
+    if (lane == 0 && warp_idx < n_rings) {
+      // 12 slots; at most LOADS_AHEAD loads (local, L2-resident source: fast) and up to NSLOT - LOADS_AHEAD stores (the
+      // slow side: remote writes) are in flight
+      constexpr int NSLOT = 12, LOADS_AHEAD = 3, STORES_PENDING = NSLOT - LOADS_AHEAD;
+      const int ring = warp_idx;
+      const uint32_t ring_bytes = static_cast<uint32_t>(NS * Cfg::STAGE_BYTES) / n_rings;
+      const uint32_t CHUNK = (ring_bytes / NSLOT) & ~1023u;
+      uint8_t* ring_smem = smem + ring * ring_bytes;
+      uint64_t* bars = reinterpret_cast<uint64_t*>(staging) + ring * 16;   // (the epilogue staging area is idle here)
+#pragma unroll
+      for (int b = 0; b < NSLOT; ++b) mbar_init(&bars[b], 1);
+      fence_barrier_init();
+      fence_proxy_async();
       const size_t blk_bytes = static_cast<size_t>(BLOCK_M) * (ag_b ? p.N : p.K) * 2;  // 128 rows of the gathered operand
       const int n_chunks = static_cast<int>((blk_bytes + CHUNK - 1) / CHUNK);
       // destinations in the order the peers consume our rows (the rank right "below" first); with `fill_local` the
@@ -288,33 +301,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         return static_cast<uint32_t>(blk_bytes - off < CHUNK ? blk_bytes - off : CHUNK);
       };
       auto signal = [&](uint32_t* flag) {
+        // the bulk stores of the row block have completed (wait_group): order them (async proxy) before the
+        // generic-proxy release that publishes the arrival
         asm volatile("fence.proxy.async.global;\n" ::: "memory");
-        __threadfence_system();
         asm volatile("red.release.sys.global.add.u32 [%0], 1;\n" ::"l"(flag) : "memory");
       };
-      // One flat stream of chunks over all row blocks of this CTA: the load cursor runs up to NSLOT-1 chunks ahead
+      // One flat stream of chunks over all row blocks of this engine: the load cursor runs up to NSLOT-1 chunks ahead
       // of the store cursor, and a finished row block is signalled two stores later (so the completion wait never
       // drains the pipe).
-      int q_ld = blockIdx.x, c_ld = 0, q_st = blockIdx.x, c_st = 0;
+      const int engine = static_cast<int>(blockIdx.x) * n_rings + ring, n_engines = n_comm * n_rings;
+      int q_ld = engine, c_ld = 0, q_st = engine, c_st = 0;
       uint32_t issued = 0, stored = 0, pend_at = 0;
       uint32_t* pend_flag = nullptr;
       while (q_st < n_remote) {
-        while (q_ld < n_remote && issued - stored < static_cast<uint32_t>(NSLOT - 1)) {
+        while (q_ld < n_remote && issued - stored < static_cast<uint32_t>(LOADS_AHEAD)) {
           const uint32_t slot = issued % NSLOT;
-          // the slot was last read by store #(issued - NSLOT); at least one newer store exists (fill bound above)
-          if (issued >= static_cast<uint32_t>(NSLOT)) tma_store_wait_read<1>();
+          // the slot was last read by store #(issued - NSLOT); at least STORES_PENDING newer stores exist (fill bound)
+          if (issued >= static_cast<uint32_t>(NSLOT)) tma_store_wait_read<STORES_PENDING>();
           const uint8_t* sp = reinterpret_cast<const uint8_t*>(cp.local_shard) +
                               static_cast<size_t>(q_ld % mbpr) * blk_bytes + static_cast<size_t>(c_ld) * CHUNK;
           const uint32_t bytes = chunk_bytes(c_ld);
           mbar_arrive_expect_tx(&bars[slot], bytes);
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                           smem_u32(smem + slot * CHUNK)),
+                           smem_u32(ring_smem + slot * CHUNK)),
                        "l"(sp), "r"(bytes), "r"(smem_u32(&bars[slot]))
                        : "memory");
           ++issued;
           if (++c_ld == n_chunks) {
             c_ld = 0;
-            q_ld += n_comm;
+            q_ld += n_engines;
           }
         }
         const uint32_t slot = stored % NSLOT;
@@ -327,7 +342,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         uint8_t* dp = reinterpret_cast<uint8_t*>(cp.peer_buf[dst]) + static_cast<size_t>(blk_of(q_st)) * blk_bytes +
                       static_cast<size_t>(c_st) * CHUNK;
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dp),
-                     "r"(smem_u32(smem + slot * CHUNK)), "r"(chunk_bytes(c_st))
+                     "r"(smem_u32(ring_smem + slot * CHUNK)), "r"(chunk_bytes(c_st))
                      : "memory");
         tma_store_commit();
         ++stored;
@@ -338,12 +353,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           // (the local fill needs no arrival: its consumers are later kernels of this stream)
           pend_flag = dst == cp.rank ? nullptr : cp.peer_flags[dst] + blk_of(q_st);
-          pend_at = stored + 2;
+          pend_at = stored + 6;
           c_st = 0;
-          q_st += n_comm;
+          q_st += n_engines;
         }
         if (pend_flag != nullptr && stored >= pend_at) {
-          tma_store_wait<2>();  // all but the two newest stores are complete -> the pending row block has landed
+          tma_store_wait<6>();  // all but the six newest stores are complete -> the pending row block has landed
           signal(pend_flag);
           pend_flag = nullptr;
         }
@@ -567,11 +582,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           __nv_bfloat16* slab = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(slab_row0) * p.ldo + col0;
           size_t ld = static_cast<size_t>(p.ldo);
           if (cp.mode == COMM_RS) {
-            // partial tile -> slot [src = rank] of the owner's staging buffer (P2P stores over NVLink when the owner
-            // is a peer); row index local to the owner.  64-byte row segments = full-sector NVLink write packets.
-            const int owner = m_blk / mbpr;
-            const size_t lrow0 = static_cast<size_t>(cp.rank) * cp.rows_per_rank + (slab_row0 - owner * cp.rows_per_rank);
-            slab = cp.peer_buf[owner] + cp.staging_parity_off + lrow0 * p.N + col0;
+            // partial tile -> this rank's OWN partial-product buffer [M, N] (peer-mapped): the epilogue runs at local
+            // HBM speed; the owners pull the rows they own during their reduce phase with wide coalesced loads and the
+            // whole GPU's memory-level parallelism (P2P stores of 64-byte row segments from the epilogue throttled the
+            // GEMM itself: profiles/r2_04_comm_bench_2gpu.json)
+            slab = cp.peer_buf[cp.rank] + cp.staging_parity_off + static_cast<size_t>(slab_row0) * p.N + col0;
             ld = static_cast<size_t>(p.N);
           }
           stg_store_chunk(stg, lane, v, slab, ld, rows_valid, cols_valid,
@@ -624,7 +639,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // all 256 epilogue threads have issued their P2P stores -> one release-increment on the owner's counter
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         if (threadIdx.x == 64) {
-          __threadfence_system();
+          // (release at system scope is cumulative over the stores of all 256 epilogue threads ordered before it by
+          // the bar.sync above: no separate fence.sc.sys — that one drained this warp's store queue once per tile)
           const int owner = m_blk / mbpr;
           // one arrival per (source rank, column tile): world * n_blocks per row block and call
           asm volatile("red.release.sys.global.add.u32 [%0], 1;\n" ::"l"(cp.peer_flags[owner] + (m_blk % mbpr)) : "memory");
@@ -639,40 +655,66 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   if (cp.mode == COMM_RS) {
     // ---------------- reduce phase: out[r, :] = sum_src staging[src][r, :] (+ bias) (+ residual) ----------------
+    // Bandwidth bound (world + 2 streams of rows_per_rank x N bf16), one CTA per SM: every thread keeps UNR row
+    // vectors x (sources + residual) 16-byte loads in flight — with one vector at a time this phase was latency bound
+    // and cost more than the GEMM it follows (profiles/r2_04_comm_bench_2gpu.json).
+    constexpr int UNR = 4;
     const int col_groups = (p.N + 255) / 256;
     const int units = mbpr * col_groups;
-    const __nv_bfloat16* stag = cp.peer_buf[cp.rank] + cp.staging_parity_off;
+    auto acc_add = [](float (&a)[8], const uint4& q) {
+      const float2 x = unpack_bf16(q.x), y = unpack_bf16(q.y), z = unpack_bf16(q.z), w = unpack_bf16(q.w);
+      a[0] += x.x; a[1] += x.y; a[2] += y.x; a[3] += y.y; a[4] += z.x; a[5] += z.y; a[6] += w.x; a[7] += w.y;
+    };
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int lm = u / col_groups, cg = u % col_groups;
       if (threadIdx.x == 0) spin_wait_ge_sys(cp.peer_flags[cp.rank] + lm, arrive_target, cp.timeout_ns, /*what=*/2, lm);
       __syncthreads();
       const int c_lo = cg * 256;
       const int c_n = min(256, p.N - c_lo) / 8;  // vectors of 8 per row in this column group
-      for (int v = threadIdx.x; v < BLOCK_M * c_n; v += NUM_THREADS) {
-        const int rr = lm * BLOCK_M + v / c_n;
-        const int cc = c_lo + (v % c_n) * 8;
-        float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int src = 0; src < cp.world; ++src) {
-          const uint4 q = *reinterpret_cast<const uint4*>(stag + (static_cast<size_t>(src) * cp.rows_per_rank + rr) * p.N + cc);
-          const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
-          acc8[0] += a.x; acc8[1] += a.y; acc8[2] += b.x; acc8[3] += b.y;
-          acc8[4] += c.x; acc8[5] += c.y; acc8[6] += d.x; acc8[7] += d.y;
+      const int total_v = BLOCK_M * c_n;
+      for (int v0 = threadIdx.x; v0 < total_v; v0 += NUM_THREADS * UNR) {
+        float acc8[UNR][8];
+        size_t off[UNR];
+        int cc[UNR];
+        bool ok[UNR];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+          const int v = v0 + j * NUM_THREADS;
+          ok[j] = v < total_v;
+          const int vv = ok[j] ? v : 0;
+          cc[j] = c_lo + (vv % c_n) * 8;
+          off[j] = static_cast<size_t>(lm * BLOCK_M + vv / c_n) * p.N + cc[j];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc8[j][e] = 0.f;
+        }
+        uint4 q[UNR], rq[UNR], bq[UNR];
+        if (cp.residual != nullptr) {
+#pragma unroll
+          for (int j = 0; j < UNR; ++j) rq[j] = ld_stream_u4(reinterpret_cast<const uint4*>(cp.residual + off[j]));
         }
         if (p.bias != nullptr) {
-          const uint4 q = *reinterpret_cast<const uint4*>(p.bias + cc);
-          const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
-          acc8[0] += a.x; acc8[1] += a.y; acc8[2] += b.x; acc8[3] += b.y;
-          acc8[4] += c.x; acc8[5] += c.y; acc8[6] += d.x; acc8[7] += d.y;
+#pragma unroll
+          for (int j = 0; j < UNR; ++j) bq[j] = *reinterpret_cast<const uint4*>(p.bias + cc[j]);
         }
-        if (cp.residual != nullptr) {
-          const uint4 q = *reinterpret_cast<const uint4*>(cp.residual + static_cast<size_t>(rr) * p.N + cc);
-          const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
-          acc8[0] += a.x; acc8[1] += a.y; acc8[2] += b.x; acc8[3] += b.y;
-          acc8[4] += c.x; acc8[5] += c.y; acc8[6] += d.x; acc8[7] += d.y;
+        for (int s0 = 0; s0 < cp.world; ++s0) {
+          // every rank's partial product of MY rows (peers over NVLink, starting with the next rank so that the ranks
+          // do not all pull from the same peer at the same time)
+          const int src = (cp.rank + 1 + s0) % cp.world;
+          const __nv_bfloat16* sp = cp.peer_buf[src] + cp.staging_parity_off + static_cast<size_t>(cp.rank) * cp.rows_per_rank * p.N;
+#pragma unroll
+          for (int j = 0; j < UNR; ++j) q[j] = ld_stream_u4(reinterpret_cast<const uint4*>(sp + off[j]));
+#pragma unroll
+          for (int j = 0; j < UNR; ++j) acc_add(acc8[j], q[j]);
         }
-        *reinterpret_cast<uint4*>(cp.rs_out + static_cast<size_t>(rr) * p.N + cc) =
-            make_uint4(pack_bf16(acc8[0], acc8[1]), pack_bf16(acc8[2], acc8[3]), pack_bf16(acc8[4], acc8[5]),
-                       pack_bf16(acc8[6], acc8[7]));
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+          if (p.bias != nullptr) acc_add(acc8[j], bq[j]);
+          if (cp.residual != nullptr) acc_add(acc8[j], rq[j]);
+          if (ok[j])
+            *reinterpret_cast<uint4*>(cp.rs_out + off[j]) =
+                make_uint4(pack_bf16(acc8[j][0], acc8[j][1]), pack_bf16(acc8[j][2], acc8[j][3]),
+                           pack_bf16(acc8[j][4], acc8[j][5]), pack_bf16(acc8[j][6], acc8[j][7]));
+        }
       }
       __syncthreads();
     }
@@ -1074,6 +1116,25 @@ extern "C" int lb_gemm_bf16_comm(const void* a, const void* b, void* out, int M,
   cp.rs_out = reinterpret_cast<__nv_bfloat16*>(rs_out);
   cp.staging_parity_off = staging_parity_off;
   cp.timeout_ns = spin_timeout_ns();
+  {
+    static int rings = -1;
+    if (rings < 0) {
+      const char* e = getenv("LIBAI_B200_COPY_RINGS");
+      rings = (e != nullptr && atoi(e) >= 1 && atoi(e) <= 8) ? atoi(e) : 1;   // measured: more engines do not help
+    }
+    cp.copy_rings = rings;
+  }
+  // timing experiments only (results are WRONG with these set): keep the handshake but take the NVLink payload out
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("LIBAI_B200_DEBUG_COMM_NO_PAYLOAD");
+      dbg = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    if (dbg == 1) {
+      for (int i = 0; i < world; ++i) cp.peer_buf[i] = cp.peer_buf[rank];   // AG pushes / RS partial tiles stay local
+    }
+  }
   if (mode == 1 && local_shard == nullptr) return -4;
   if (colsum != nullptr && (reinterpret_cast<uintptr_t>(colsum) & 15)) return -8;
   int lda, ldb, ldo;

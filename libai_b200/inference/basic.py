@@ -114,7 +114,9 @@ class BasePipeline(metaclass=ABCMeta):
         return outputs
 
     def to_device(self, tensor):
-        return tensor.to(next(self.model.parameters()).device)
+        # (parameters of other pipeline stages are `meta` placeholders: take the first materialised one)
+        dev = next((p.device for p in self.model.parameters() if p.device.type != "meta"), None)
+        return tensor.to(dev if dev is not None else dist.get_dist_util().device)
 
     def to_local(self, model_outputs_dict):
         """Outputs are replicated across the model-parallel group already; bring them to host memory."""

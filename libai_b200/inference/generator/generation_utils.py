@@ -18,6 +18,8 @@ import warnings
 from typing import Callable, Dict, Iterable, List, Optional, Tuple, Union
 
 import torch
+
+from libai_b200.utils import distributed as dutil
 import torch.distributed as dist
 
 from .generation_beam_search import BeamScorer, BeamSearchScorer
@@ -75,7 +77,11 @@ class Generator:
         return value if value is not None else self._gcfg(key)
 
     def _device(self):
-        return next(self.parameters()).device
+        # parameters owned by other pipeline stages are `meta` placeholders
+        for p in self.parameters():
+            if p.device.type != "meta":
+                return p.device
+        return dutil.get_dist_util().device
 
     # ------------------------------------------------------------------ input preparation
     def _prepare_model_inputs(self, inputs=None, bos_token_id=None, model_kwargs=None):
@@ -157,7 +163,11 @@ class Generator:
             model_kwargs["past"] = outputs["past_key_values"]
         else:
             past = getattr(self, "past_key_values", None)
-            model_kwargs["past"] = past if past and past[-1] is not None else None
+            # under pipeline parallelism a rank only holds the caches of its own layers (possibly none at all): the
+            # model's `past_length` says whether a cache exists somewhere
+            cached = bool(past) and (any(p is not None for p in past) or (
+                dutil.get_dist_util().pipeline_parallel_size > 1 and getattr(self, "past_length", 0) > 0))
+            model_kwargs["past"] = past if cached else None
         key = "decoder_attn_mask" if is_encoder_decoder else "attention_mask"
         if model_kwargs.get(key) is not None:
             mask = model_kwargs[key]

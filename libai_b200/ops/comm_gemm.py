@@ -29,7 +29,7 @@ _BM = 128
 
 def _n_comm_ctas(world: int) -> int:
     """Copy CTAs of the AG kernels: each streams ~200 KB in flight through its TMA ring; more destinations → more CTAs."""
-    return 16 if world <= 4 else 32
+    return 24 if world <= 4 else 32      # measured: profiles/r2_04_comm_bench_2gpu.json (8: 132 us, 16: 71, 24: 69, 32: 65, 48: 73)
 
 
 class _TPState:
@@ -111,8 +111,14 @@ def ag_gemm(x_shard: torch.Tensor, w: torch.Tensor, bias, act, group, layout: in
     s = st.ag_state(M, K)
     par = _next(s)
     gathered = s["buf"].view(torch.bfloat16, (2, M, K))[par]
+    if fill_local:
+        # the local rows of the gathered buffer are only needed by LATER kernels of this stream (the wgrad that reuses
+        # all_gather(dy)): a plain device copy at HBM speed (~6 us per 16 MB) instead of a second job for the copy
+        # CTAs, whose throughput is what the kernel waits for (profiles/r2_04_comm_bench_2gpu.json)
+        gathered[st.rank * rows : (st.rank + 1) * rows].copy_(x_shard)
+        count_launch()
     y, pre = ext.ag_gemm(
-        gathered, x_shard, w, layout, bias, _ACT_IDS[act], need_pre, pre_in, colsum, fill_local, st.world, st.rank,
+        gathered, x_shard, w, layout, bias, _ACT_IDS[act], need_pre, pre_in, colsum, False, st.world, st.rank,
         s["buf"].peer_ptrs(par * M * K * 2), st.ws.flags.peer_ptrs(s["flag_offs"][par]),
         st.ws.flags.peer_ptrs(s["done_offs"][par]), s["state"][par], _n_comm_ctas(st.world),
     )

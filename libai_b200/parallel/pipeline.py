@@ -176,12 +176,24 @@ class _ScheduleScope:
         return False
 
 
-def _broadcast_from_last_stage(out, topo):
+def broadcast_from_stage(out, stage: int, topo=None):
+    """Hand stage ``stage``'s value (tensor / tuple / list / dict of tensors, ``None`` and python scalars allowed) to
+    every stage of this rank's pipeline group.  Used by inference code that walks the layers stage by stage
+    (``projects/MT5`` generation with a KV cache) — correctness first, one broadcast per stage boundary."""
+    topo = topo or dutil.get_dist_util()
+    if topo.pipeline_parallel_size == 1:
+        return out
+    return _broadcast_from_last_stage(out, topo, stage)
+
+
+def _broadcast_from_last_stage(out, topo, stage: Optional[int] = None):
     """Hand the last stage's result (tensor / tuple / dict of tensors, nested python scalars allowed) to every stage
     of the pipeline group so that callers see the same value on all ranks."""
-    src = topo.pp_ranks[-1]
+    stage = topo.pipeline_parallel_size - 1 if stage is None else stage
+    src = topo.pp_ranks[stage]
     group = topo.pp_group
     dev = topo.device
+    is_src = topo.pp_rank == stage
 
     def describe(o):
         if torch.is_tensor(o):
@@ -192,20 +204,20 @@ def _broadcast_from_last_stage(out, topo):
             return ("l" if isinstance(o, list) else "u", [describe(v) for v in o])
         return ("o", o)
 
-    meta = [describe(out) if topo.is_last_stage else None]
+    meta = [describe(out) if is_src else None]
     dist.broadcast_object_list(meta, src=src, group=group, device=dev if dev.type == "cuda" else None)
 
     def rebuild(m, o):
         kind = m[0]
         if kind == "t":
-            t = o.detach().contiguous() if topo.is_last_stage else torch.empty(m[1], dtype=m[2], device=dev)
+            t = o.detach().contiguous() if is_src else torch.empty(m[1], dtype=m[2], device=dev)
             if t.numel():
                 dist.broadcast(t, src=src, group=group)
             return t
         if kind == "d":
-            return {k: rebuild(mv, o[k] if topo.is_last_stage else None) for k, mv in m[1]}
+            return {k: rebuild(mv, o[k] if is_src else None) for k, mv in m[1]}
         if kind in ("l", "u"):
-            vals = [rebuild(mv, o[i] if topo.is_last_stage else None) for i, mv in enumerate(m[1])]
+            vals = [rebuild(mv, o[i] if is_src else None) for i, mv in enumerate(m[1])]
             return vals if kind == "l" else tuple(vals)
         return m[1]
 

@@ -254,8 +254,101 @@ class MT5Model(nn.Module, Generator):
             hidden, bias = layer(hidden, mask, position_bias=bias)
         return self.encoder.final_layernorm(hidden)
 
+    # ---- inference under pipeline parallelism -----------------------------------------------------------------
+    # (reference tests/inference/test_text_generation.py:41-90: generation with PP4 / TP2xPP2.)  The layers of the two
+    # stacks live on different stages; the running state (hidden, relative-position biases) is handed over by a
+    # broadcast inside the pipeline group at every stage boundary, every layer keeps its KV cache on its own stage and
+    # the last stage's logits go back to everyone so that all ranks take the same decoding decisions.
+    def _pp_walk(self, layers, state, step, first_stage=0):
+        """``state``: list of tensors / None; ``step(layer, state) -> state`` runs on the owning stage only."""
+        from libai_b200.parallel.pipeline import broadcast_from_stage
+
+        topo = dutil.get_dist_util()
+        cur = first_stage
+        for layer in layers:
+            st = topo.get_layer_stage_id(layer.layer_idx)
+            if st != cur:
+                state = list(broadcast_from_stage(state, cur, topo))
+                cur = st
+            if topo.pp_rank == st:
+                state = step(layer, state)
+        return state, cur
+
+    def _forward_pipelined(self, encoder_input_ids, decoder_input_ids, encoder_attn_mask, decoder_attn_mask,
+                           encoder_decoder_attn_mask, use_cache, only_encoder):
+        from libai_b200.parallel.pipeline import broadcast_from_stage
+
+        topo = dutil.get_dist_util()
+        last = topo.pipeline_parallel_size - 1
+        if use_cache and self.encoder_states is not None:
+            encoder_states = self.encoder_states
+        else:
+            self.set_cache(None, None)
+            self.past_length = 0
+            mask = _extend(encoder_attn_mask)
+            hidden = self.embedding(encoder_input_ids) if topo.is_first_stage else None
+
+            def enc_step(layer, st):
+                h, b = layer(st[0], mask, position_bias=st[1])
+                return [h, b]
+
+            state, cur = self._pp_walk(self.encoder.layers, [hidden, None], enc_step)
+            ln_stage = topo.get_layer_stage_id(self.encoder.final_layernorm.layer_idx)
+            if ln_stage != cur:
+                state = list(broadcast_from_stage(state, cur, topo))
+            enc = self.encoder.final_layernorm(state[0]) if topo.pp_rank == ln_stage else None
+            encoder_states = broadcast_from_stage(enc, ln_stage, topo)      # every decoder stage cross-attends to it
+        if only_encoder:
+            return encoder_states
+        past_len = self.past_length if use_cache else 0
+        q_len = decoder_input_ids.shape[1]
+        causal = torch.ones(past_len + q_len, past_len + q_len, dtype=torch.bool, device=decoder_input_ids.device).tril()
+        dec_mask = causal[past_len:][None, None]
+        if decoder_attn_mask is not None:
+            extra = _extend(decoder_attn_mask)
+            if extra.shape[-1] == past_len + q_len:
+                dec_mask = dec_mask & extra[..., -q_len:, :] if extra.shape[-2] > 1 else dec_mask & extra
+        cross_mask = _extend(encoder_decoder_attn_mask if encoder_decoder_attn_mask is not None else encoder_attn_mask)
+        if cross_mask is not None and cross_mask.shape[-2] > 1:
+            cross_mask = cross_mask[..., -q_len:, :]
+        hidden = self.embedding(decoder_input_ids) if topo.is_first_stage else None
+        presents = {}
+        index = {id(layer): i for i, layer in enumerate(self.decoder.layers)}
+
+        def dec_step(layer, st):
+            i = index[id(layer)]
+            h, b, cb, present = layer(st[0], dec_mask, encoder_states, cross_mask, past_key_value=self.past_key_values[i],
+                                      position_bias=st[1], encoder_decoder_position_bias=st[2], use_cache=use_cache)
+            presents[i] = present
+            return [h, b, cb]
+
+        state, cur = self._pp_walk(self.decoder.layers, [hidden, None, None], dec_step)
+        if cur != last:
+            state = list(broadcast_from_stage(state, cur, topo))
+        if use_cache:
+            self.encoder_states = encoder_states
+            self.past_key_values = [presents.get(i) for i in range(len(self.decoder.layers))]   # own layers only
+            self.past_length = past_len + q_len
+        logits = None
+        if self.model_type != "mt5" and getattr(self, "_pp_tied_weight", None) is None:
+            # tied LM head: the word embedding lives on the first stage; the last stage needs a copy (weights are frozen
+            # during inference, so it is fetched once)
+            w = self.embedding.word_embeddings.weight.detach() if topo.is_first_stage else None
+            self._pp_tied_weight = broadcast_from_stage(w, 0, topo)
+        if topo.is_last_stage:
+            hidden = self.decoder.final_layernorm(state[0])
+            if self.tie_word_embeddings:
+                hidden = hidden * (self.hidden_size ** -0.5)
+            logits = self.lm_head(hidden) if self.model_type == "mt5" else self.lm_head(hidden, self._pp_tied_weight)
+            if topo.tensor_parallel_size > 1:
+                logits = mappings.gather_from_tp(logits)
+        return {"logits": broadcast_from_stage(logits, last, topo)}
+
     def forward(self, encoder_input_ids=None, decoder_input_ids=None, encoder_attn_mask=None, decoder_attn_mask=None,
                 encoder_decoder_attn_mask=None, use_cache=False, only_encoder=False):
+        if dutil.get_dist_util().pipeline_parallel_size > 1 and not torch.is_grad_enabled():
+            return self._forward_pipelined(encoder_input_ids, decoder_input_ids, encoder_attn_mask, decoder_attn_mask,
+                                           encoder_decoder_attn_mask, use_cache, only_encoder)
         if use_cache and self.encoder_states is not None:
             encoder_states = self.encoder_states
         else:
@@ -305,7 +398,7 @@ class MT5Model(nn.Module, Generator):
             return None
         if self.encoder_states is not None:
             self.encoder_states = self.encoder_states.index_select(0, beam_idx.to(self.encoder_states.device))
-        return [tuple(t.index_select(0, beam_idx.to(t.device)) for t in layer) for layer in past]
+        return [None if layer is None else tuple(t.index_select(0, beam_idx.to(t.device)) for t in layer) for layer in past]
 
     def prepare_inputs_for_generation(self, input_ids, past=None, encoder_attn_mask=None, encoder_decoder_attn_mask=None,
                                       use_cache=None, encoder_input_ids=None, encoder_outputs=None, **kwargs):
