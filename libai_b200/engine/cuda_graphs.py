@@ -74,6 +74,67 @@ def graph_transformer_blocks(blocks: Sequence[nn.Module], sample_hidden: torch.T
     return [_with_launch_count(g, f, b) for g, (f, b) in zip(graphed, counts)]
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# pipeline parallelism: several micro-batches of one block are in flight (1F1B), so every block gets `n_slots` captured
+# copies — micro-batch i runs (forward, and later backward) on copy i % n_slots, whose saved activations nobody else
+# touches in between (stage s of p keeps at most p - s micro-batches in flight, FIFO).
+# --------------------------------------------------------------------------------------------------------------------
+_CURRENT_SLOT = 0
+
+
+def set_micro_batch_slot(i: int) -> None:
+    """Called by the pipeline schedule before the forward of micro-batch ``i``."""
+    global _CURRENT_SLOT
+    _CURRENT_SLOT = int(i)
+
+
+class _EagerBlock:
+    """Plain callable around a block's original forward: ``make_graphed_callables`` then treats the parameters as
+    captured constants (they live at fixed addresses in the optimizer's flat buffer and their gradients are
+    accumulated into ``main_grad`` by the captured backward kernels themselves)."""
+
+    def __init__(self, block):
+        self.fn = block.forward
+
+    def __call__(self, hidden):
+        return self.fn(hidden)
+
+
+def graph_blocks_multi_slot(blocks: Sequence[nn.Module], sample_hidden: torch.Tensor, n_slots: int, warmup_iters: int = 3
+                            ) -> bool:
+    with torch.no_grad():
+        n0 = ops.launch_count()
+        blocks[0](sample_hidden.detach())
+        fwd_kernels = ops.launch_count() - n0
+    torch.cuda.synchronize()
+    fns = tuple(_EagerBlock(b) for _ in range(n_slots) for b in blocks)
+    samples = tuple((sample_hidden.detach().clone().requires_grad_(True),) for _ in fns)
+    n0 = ops.launch_count()
+    graphed = torch.cuda.make_graphed_callables(fns, samples, num_warmup_iters=warmup_iters, allow_unused_input=True)
+    per_block = (ops.launch_count() - n0) // ((warmup_iters + 1) * len(fns))
+    ops.count_launch(-(ops.launch_count() - n0))
+    bwd_kernels = max(per_block - fwd_kernels, 0)
+    # every parameter gradient of the blocks must have gone into main_grad (captured side effect): a parameter that
+    # still relies on autograd's AccumulateGrad would silently get no gradient from a function-style graphed callable
+    for b in blocks:
+        for p in b.parameters():
+            if p.requires_grad and (p.grad is not None or not getattr(p, "grad_added_to_main_grad", False)):
+                raise RuntimeError("a block parameter gets its gradient through autograd (not main_grad): cannot capture")
+    nb = len(blocks)
+    for k, block in enumerate(blocks):
+        eager = fns[k].fn
+        slots = [graphed[s * nb + k] for s in range(n_slots)]
+
+        def forward(hidden, _eager=eager, _slots=slots, _block=block):
+            if not (torch.is_grad_enabled() and _block.training and hidden.requires_grad):
+                return _eager(hidden)
+            ops.count_launch(fwd_kernels + bwd_kernels)
+            return _slots[_CURRENT_SLOT % len(_slots)](hidden)
+
+        block.forward = forward
+    return True
+
+
 def enable_for_model(model: nn.Module, example_batch: dict) -> bool:
     """Replace the blocks of a ``PipelineStageMixin`` model by graphed versions.  ``example_batch``: one training batch
     (device tensors) used to discover the hidden-state shape.  The gradient buffers must be zeroed afterwards (the
@@ -81,13 +142,15 @@ def enable_for_model(model: nn.Module, example_batch: dict) -> bool:
     from libai_b200.utils import distributed as dutil
 
     topo = dutil.get_dist_util()
-    if (topo.pipeline_parallel_size > 1 or getattr(model, "activation_checkpoint", False)
+    if (getattr(model, "activation_checkpoint", False)
             or (topo.tensor_parallel_size > 1 and not topo.fused_tp_comm)):
-        # (1F1B keeps several micro-batches in flight per block; checkpointing re-runs the forward inside backward;
-        # tensor parallelism is captured only in its fused form — AG→GEMM / GEMM→RS kernels whose handshake state lives
-        # in device memory (ops/comm_gemm.py) — the NCCL form keeps eager launches)
-        logger.warning("cuda graphs: pipeline parallelism / NCCL-form tensor parallelism / activation checkpointing — not captured")
+        # (checkpointing re-runs the forward inside backward; tensor parallelism is captured only in its fused form —
+        # AG→GEMM / GEMM→RS kernels whose handshake state lives in device memory (ops/comm_gemm.py) — the NCCL form
+        # keeps eager launches)
+        logger.warning("cuda graphs: NCCL-form tensor parallelism / activation checkpointing — not captured")
         return False
+    if topo.pipeline_parallel_size > 1:
+        return _enable_for_pipeline_stage(model, example_batch, topo)
     layers = model.stage_layers() if hasattr(model, "stage_layers") else None
     if not isinstance(layers, nn.ModuleList) or len(layers) == 0:
         return False
@@ -123,3 +186,57 @@ def enable_for_model(model: nn.Module, example_batch: dict) -> bool:
     model.train(was_training)
     logger.info("cuda graphs: captured forward+backward of %d blocks (hidden %s)", len(new), tuple(shapes["hidden"].shape))
     return True
+
+
+def _enable_for_pipeline_stage(model: nn.Module, example_batch: dict, topo) -> bool:
+    """Pipeline stage: capture the blocks this stage owns, ``pp - stage`` copies each (see ``graph_blocks_multi_slot``).
+    The hidden-state shape is the stage's p2p payload; it is derived from the batch (token-sharded under sequence
+    parallelism) instead of running the model, because only the first stage can run without a received activation."""
+    layers = model.stage_layers() if hasattr(model, "stage_layers") else None
+    if not isinstance(layers, nn.ModuleList) or len(layers) == 0:
+        return False
+    own = [l for l in layers if topo.owns_layer(getattr(l, "layer_idx", 0))]
+    if not own:
+        return False
+    ids = example_batch.get("input_ids")
+    if ids is None or ids.dim() != 2:
+        logger.warning("cuda graphs: pipeline stage without `input_ids` [b, s] in the batch — not captured")
+        return False
+    p0 = next(own[0].parameters())
+    hidden_size = getattr(own[0], "hidden_size", None)
+    if hidden_size is None:
+        return False
+    b, sq = ids.shape
+    if topo.sequence_parallel:
+        from libai_b200.layers.embedding import set_sp_shape
+
+        set_sp_shape(b, sq)
+        shape = (b * sq // topo.tensor_parallel_size, hidden_size)
+    else:
+        shape = (b, sq, hidden_size)
+    sample = torch.randn(shape, device=p0.device, dtype=p0.dtype) * 0.02
+    n_slots = topo.pipeline_parallel_size - topo.pp_rank
+    was_training = model.training
+    model.train()
+    try:
+        ok = graph_blocks_multi_slot(own, sample, n_slots)
+    except Exception as e:   # capture is an optimisation: never take the run down with it
+        logger.warning("cuda graphs: pipeline-stage capture failed (%s: %s) — staying with eager launches", type(e).__name__, str(e)[:200])
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        ok = False
+    model.train(was_training)
+    if ok:
+        logger.info("cuda graphs: stage %d captured forward+backward of %d blocks x %d micro-batch slots (hidden %s)",
+                    topo.pp_rank, len(own), n_slots, tuple(shape))
+    # all stages must agree (the fused tensor-parallel kernels inside the graphs are collectives)
+    import torch.distributed as dist
+
+    flag = torch.tensor([1 if ok else 0], device=p0.device)
+    if dist.is_initialized():
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0 and ok:
+        logger.warning("cuda graphs: another rank failed to capture — this run cannot mix graphed and eager stages safely")
+    return bool(flag.item())

@@ -255,6 +255,8 @@ class DefaultTrainer(TrainerBase):
     def build_hooks(self):
         cfg = self.cfg
         ret = [hooks.IterationTimer(), hooks.LRScheduler()]
+        if os.environ.get("LIBAI_B200_FAULT_INJECT"):
+            ret.append(hooks.FaultInjectionHook(os.environ["LIBAI_B200_FAULT_INJECT"]))
         if try_get_key(cfg, "train.checkpointer.period", default=0):
             ret.append(
                 hooks.PeriodicCheckpointer(

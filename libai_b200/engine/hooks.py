@@ -375,3 +375,25 @@ class ProfilerHook(HookBase):
         if self._prof is not None:       # training ended inside the window
             self._prof.__exit__(None, None, None)
             self._prof = None
+
+
+class FaultInjectionHook(HookBase):
+    """Test facility for the failure-recovery path: ``LIBAI_B200_FAULT_INJECT="<rank>:<iteration>"`` makes
+    that rank die abruptly (``os._exit``, no cleanup, no checkpoint) right after the given iteration — the launcher
+    (``torchrun``) then tears the job down and a relaunch with ``--resume`` must continue from the last periodic
+    checkpoint (``tests/test_fault_recovery_cpu.py``)."""
+
+    def __init__(self, spec: str):
+        rank, it = spec.split(":")
+        self.rank, self.iteration = int(rank), int(it)
+
+    def after_step(self):
+        from libai_b200.utils import distributed as dutil
+
+        if self.trainer.iter == self.iteration and dutil.get_rank() == self.rank:
+            import os
+            import sys
+
+            sys.stderr.write(f"[fault injection] rank {self.rank} dies after iteration {self.iteration}\n")
+            sys.stderr.flush()
+            os._exit(17)

@@ -86,6 +86,31 @@ def fused_supported(M: int, N: int, K: int, world: int) -> bool:
     return M % (_BM * world) == 0 and N % 8 == 0 and K % 8 == 0 and 2 <= world <= 8
 
 
+# Keep all_gather(x) of the forward for the weight gradient (one device copy of [tokens, h] per column-parallel linear
+# and layer) instead of gathering x a second time inside the wgrad kernel: trades b·s·h·2 bytes of activation memory per
+# column-parallel linear for ~35 us of exposed NVLink synchronisation per wgrad (profiles/r2_06_comm_bench_2gpu.json:
+# AG->wgrad 80 us vs plain wgrad 42 us at 16k tokens).  ``LIBAI_B200_SP_SAVE_GATHERED=0`` restores the re-gather
+# (Megatron's sequence-parallel memory profile).
+import os as _os
+
+_SAVE_GATHERED = _os.environ.get("LIBAI_B200_SP_SAVE_GATHERED", "1") == "1"
+
+
+def set_save_gathered(enabled: bool) -> None:
+    global _SAVE_GATHERED
+    _SAVE_GATHERED = bool(enabled)
+
+
+def _snapshot_gathered(gathered: torch.Tensor, x_shard: torch.Tensor, rank: int) -> torch.Tensor:
+    """Private copy of the gathered operand (the symmetric buffer is reused by the next AG call); the local rows were
+    never written into the buffer (the kernel reads them from ``x_shard``)."""
+    rows = x_shard.shape[0]
+    full = gathered.clone()
+    full[rank * rows : (rank + 1) * rows].copy_(x_shard)
+    count_launch(2)
+    return full
+
+
 def _next(s: dict) -> int:
     """Buffer parity of this call.  Static per call site once captured in a CUDA graph; correctness does not depend on
     strict alternation (the kernels hand out write credits), it only avoids waiting for them."""
@@ -193,15 +218,18 @@ class ColumnParallelLinearFused(torch.autograd.Function):
     def forward(ctx, x_shard, w, bias, act, group):
         has_act = act not in (None, "none")
         need_pre = has_act and (x_shard.requires_grad or w.requires_grad)
-        y, pre, _ = ag_gemm(x_shard, w, bias, act if has_act else None, group, need_pre=need_pre)
-        ctx.save_for_backward(x_shard, w, pre)
+        y, pre, gathered = ag_gemm(x_shard, w, bias, act if has_act else None, group, need_pre=need_pre)
+        x_full = None
+        if _SAVE_GATHERED and ctx.needs_input_grad[1]:
+            x_full = _snapshot_gathered(gathered, x_shard, _state(group).rank)
+        ctx.save_for_backward(x_shard, w, pre, x_full)
         ctx.act, ctx.group, ctx.bias_param = (act if has_act else None), group, bias
         return y
 
     @staticmethod
     def backward(ctx, gy):
         ext = load_ext()
-        x_shard, w, pre = ctx.saved_tensors
+        x_shard, w, pre, x_full = ctx.saved_tensors
         gy = gy.contiguous()
         if ctx.act is not None:
             gy = ext.act_bwd(gy, pre, _ACT_IDS[ctx.act])
@@ -210,7 +238,7 @@ class ColumnParallelLinearFused(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = gemm_rs(gy, w, None, None, ctx.group, layout=1)  # dy [M, N_loc] · W [N_loc, K]
         if ctx.needs_input_grad[1]:
-            gw = _wgrad_ag(gy, x_shard, w, ctx.group)
+            gw = _wgrad_plain(ext, gy, x_full, w) if x_full is not None else _wgrad_ag(gy, x_shard, w, ctx.group)
         if ctx.bias_param is not None and ctx.needs_input_grad[2]:
             gb = _bias_grad(ext, gy, ctx.bias_param)
         return gx, gw, gb, None, None
@@ -249,16 +277,19 @@ class TPMLPFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_shard, w1, b1, w2, b2, residual, act, group):
-        h, pre, _ = ag_gemm(x_shard, w1, b1, act, group, need_pre=True)
+        h, pre, gathered = ag_gemm(x_shard, w1, b1, act, group, need_pre=True)
+        x_full = None
+        if _SAVE_GATHERED and ctx.needs_input_grad[1]:
+            x_full = _snapshot_gathered(gathered, x_shard, _state(group).rank)
         y = gemm_rs(h, w2, b2, residual, group)
-        ctx.save_for_backward(x_shard, w1, w2, pre, h)
+        ctx.save_for_backward(x_shard, w1, w2, pre, h, x_full)
         ctx.act, ctx.group, ctx.b1, ctx.b2, ctx.has_res = act, group, b1, b2, residual is not None
         return y
 
     @staticmethod
     def backward(ctx, gy_shard):
         ext = load_ext()
-        x_shard, w1, w2, pre, h = ctx.saved_tensors
+        x_shard, w1, w2, pre, h, x_full = ctx.saved_tensors
         gy_shard = gy_shard.contiguous()
         b1, b2 = ctx.b1, ctx.b2
         fused_gb1 = None
@@ -273,7 +304,9 @@ class TPMLPFused(torch.autograd.Function):
         gw2 = _wgrad_plain(ext, gy_full, h, w2) if need_w2 else None
         gb2 = _bias_grad(ext, gy_shard, b2) if (b2 is not None and ctx.needs_input_grad[4]) else None
         gx = gemm_rs(dpre, w1, None, None, ctx.group, layout=1) if ctx.needs_input_grad[0] else None
-        gw1 = _wgrad_ag(dpre, x_shard, w1, ctx.group) if ctx.needs_input_grad[1] else None
+        gw1 = None
+        if ctx.needs_input_grad[1]:
+            gw1 = _wgrad_plain(ext, dpre, x_full, w1) if x_full is not None else _wgrad_ag(dpre, x_shard, w1, ctx.group)
         gb1 = None
         if fused_gb1 is not None:
             b1.grad_added_to_main_grad = True

@@ -300,17 +300,27 @@ class PipelineSchedule1F1B:
                 metrics = m if metrics is None else {k: metrics[k] + m[k] for k in m}
 
         it = iter(batches)
+        fwd_index = [0]
+
+        def next_batch():
+            # micro-batch i runs on captured copy i % n_slots of every block (engine/cuda_graphs.py)
+            from libai_b200.engine.cuda_graphs import set_micro_batch_slot
+
+            set_micro_batch_slot(fwd_index[0])
+            fwd_index[0] += 1
+            return next(it)
+
         # ---- warm-up forwards
         for _ in range(warm):
             hidden_in = p2p.recv_forward()
-            out, m = self._forward(next(it), hidden_in, M)
+            out, m = self._forward(next_batch(), hidden_in, M)
             track(m)
             p2p.send_forward(out)
             inflight.append((hidden_in, out))
         # ---- steady 1F1B
         hidden_in = p2p.recv_forward() if steady > 0 else None
         for i in range(steady):
-            out, m = self._forward(next(it), hidden_in, M)
+            out, m = self._forward(next_batch(), hidden_in, M)
             track(m)
             inflight.append((hidden_in, out))
             grads = p2p.send_forward_recv_backward(out)

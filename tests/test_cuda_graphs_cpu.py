@@ -16,14 +16,12 @@ class _Block(nn.Module):
         return self.drop(self.lin(x))
 
 
-def test_dropout_detection_and_cpu_guard():
-    assert not cuda_graphs._block_has_dropout(_Block(0.0))
-    assert cuda_graphs._block_has_dropout(_Block(0.1))
-    blk = _Block(0.0)
-    blk.attention_dropout_prob = 0.1
-    assert cuda_graphs._block_has_dropout(blk)
-    # CPU tensors are never captured
-    assert cuda_graphs.graph_transformer_blocks([_Block()], torch.randn(2, 8)) is None
+def test_cpu_guard_and_micro_batch_slots():
+    # CPU tensors are never captured (dropout no longer excludes a block: the native kernels draw graph-safe Philox state)
+    assert cuda_graphs.graph_transformer_blocks([_Block(0.1)], torch.randn(2, 8)) is None
+    cuda_graphs.set_micro_batch_slot(5)
+    assert cuda_graphs._CURRENT_SLOT == 5
+    cuda_graphs.set_micro_batch_slot(0)
 
 
 def test_launch_count_wrapper_keeps_module_identity():
