@@ -102,12 +102,12 @@ LB_DEVICE uint32_t ld_acquire_gpu_u32(const uint32_t* a) {
   return v;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CTAS = 1>
 struct StageCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BLOCK_N / CTAS) * BLOCK_K * 2;   // CTA pair: each CTA stages half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NUM_STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : (BLOCK_N == 128 ? 6 : 8));
+  static constexpr int NUM_STAGES = CTAS == 2 ? 6 : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : (BLOCK_N == 128 ? 6 : 8)));
   static constexpr int STAGING_BYTES = 8 * 2048;  // one 32x32 bf16 chunk (32 rows x 64 B) per epilogue warp
   static constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STAGING_BYTES;
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
@@ -179,13 +179,16 @@ LB_DEVICE void stg_store_chunk(uint8_t* stg, int lane, const float (&v)[32], __n
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool FP8 = false>
+// CTAS == 2: `cta_group::2` — clusters of two CTAs (one TPC) compute 256 x BLOCK_N tiles; no fused collectives, bf16 only.
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool FP8 = false, int CTAS = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_g /* COMM_AG: the local shard of the gathered operand */, GemmParams p,
             CommParams cp) {
-  using Cfg = StageCfg<BLOCK_N>;
+  using Cfg = StageCfg<BLOCK_N, CTAS>;
   constexpr int NS = Cfg::NUM_STAGES;
+  static_assert(CTAS == 1 || (CTAS == 2 && BLOCK_N == 256 && !FP8), "CTA-pair mode: 256-wide bf16 tiles only");
+  const int cta_rank = CTAS == 2 ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader of the pair
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES);
@@ -198,14 +201,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int warp_idx = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
 
-  const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  // (CTA pair: `m_blocks` counts 256-row blocks = one per pair; this CTA works on rows [256 m + 128 rank, +128))
+  const int m_blocks = (p.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS);
   const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int k_blocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_tiles = m_blocks * n_blocks * p.k_splits;
   // CTAs [0, n_comm) are copy CTAs in COMM_AG mode; the rest run the GEMM roles
   const int n_comm = (cp.mode == COMM_AG) ? cp.n_comm : 0;
-  const int cta = static_cast<int>(blockIdx.x) - n_comm;
-  const int cta_stride = static_cast<int>(gridDim.x) - n_comm;
+  const int cta = (static_cast<int>(blockIdx.x) - n_comm) / CTAS;
+  const int cta_stride = (static_cast<int>(gridDim.x) - n_comm) / CTAS;
   const int mbpr = cp.mode != COMM_NONE ? cp.rows_per_rank / BLOCK_M : m_blocks;
   const bool ag_b = cp.mode == COMM_AG && cp.gathered_is_b != 0;   // TN wgrad: shards along the reduction dimension
   // row blocks are visited owner by owner: AG starts with the local rows (already resident), RS ends with them
@@ -240,21 +244,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (cp.mode == COMM_AG) tma_prefetch_desc(&tmap_g);
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], CTAS);   // pair: the leader's barrier collects one arrival per CTA (+ both CTAs' bytes)
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], NUM_EPI_THREADS);
-    mbar_init(&tmem_empty[1], NUM_EPI_THREADS);
+    // (pair: one arrival per epilogue WARP of both CTAs on the leader's barrier — 256 remote arrivals per tile would
+    // be needless cluster traffic)
+    mbar_init(&tmem_empty[0], CTAS == 2 ? 16 : NUM_EPI_THREADS);
+    mbar_init(&tmem_empty[1], CTAS == 2 ? 16 : NUM_EPI_THREADS);
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp_idx == 1) {
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+    if constexpr (CTAS == 2) tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_ptr_smem);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
   }
   tc_fence_before_sync();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything targets them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -384,7 +392,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           asm volatile("fence.proxy.async.global;\n" ::: "memory");
         }
         const CUtensorMap* map_a = a_local ? &tmap_g : &tmap_a;
-        const int m_row = a_local ? (m_blk - cp.rank * mbpr) * BLOCK_M : m_blk * BLOCK_M;
+        const int m_row = a_local ? (m_blk - cp.rank * mbpr) * BLOCK_M : (m_blk * CTAS + cta_rank) * BLOCK_M;
+        const int n_row = n_blk * BLOCK_N + cta_rank * (BLOCK_N / CTAS);   // pair: this CTA's half of the B tile
         const int kb0 = split * p.k_per_split;
         const int kb1 = min(kb0 + p.k_per_split, k_blocks_total);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -402,6 +411,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          if constexpr (CTAS == 2) {
+            // both CTAs' loads complete on the LEADER's barrier: the leader arms it with the bytes of both, the peer
+            // contributes its arrival remotely
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * 2);
+            else mbar_arrive_cluster(&full_bar[stage], 0);
+            if constexpr (!A_MN) {
+              tma_load_2d_2cta(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_row);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BLOCK_M / 64; ++a)
+                tma_load_2d_2cta(sa + a * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_row + a * 64, kb * BLOCK_K);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d_2cta(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_row);
+            } else {
+#pragma unroll
+              for (int a = 0; a < (BLOCK_N / 2) / 64; ++a)
+                tma_load_2d_2cta(sb + a * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_row + a * 64, kb * BLOCK_K);
+            }
+            if (++stage == NS) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if constexpr (!A_MN) {
             tma_load_2d(sa, map_a, &full_bar[stage], kb * BLOCK_K, m_row);
@@ -429,12 +463,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (warp_idx == 1) {
     // ======================= MMA issuer =======================
     // (FP8 is a template parameter so the bf16 instantiations carry no trace of it)
-    constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(BLOCK_M, BLOCK_N) : make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(BLOCK_M, BLOCK_N) : make_idesc_bf16(BLOCK_M * CTAS, BLOCK_N, A_MN, B_MN);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cta; tile < num_tiles; tile += cta_stride) {
+    for (int tile = cta; tile < num_tiles && cta_rank == 0; tile += cta_stride) {   // (pair: the leader issues for both)
       int split, mn_unused;
       decode_tile(tile, mn_unused, split);
       const int kb0 = split * p.k_per_split;
@@ -458,10 +492,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                      : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 0, 1024);
             if constexpr (FP8) umma_f8_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else if constexpr (CTAS == 2) umma_f16_ss_2cta(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);   // accumulator complete
+          if constexpr (CTAS == 2) {
+            umma_commit_2cta(&empty_bar[stage]);                    // frees the slot in BOTH CTAs
+            if (kb == kb1 - 1) umma_commit_2cta(&tmem_full[acc]);   // both CTAs' epilogues
+          } else {
+            umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
+            if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);   // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == NS) {
@@ -495,7 +535,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     for (int tile = cta; tile < num_tiles; tile += cta_stride) {
       int mn, split_unused;
       decode_tile(tile, mn, split_unused);
-      const int m_blk = map_m(mn / n_blocks), n_blk = mn % n_blocks;
+      const int m_blk = map_m(mn / n_blocks) * CTAS + cta_rank, n_blk = mn % n_blocks;   // this CTA's 128-row block
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const int row = m_blk * BLOCK_M + quad * 32 + lane;
@@ -634,7 +674,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }    // fp32 epilogues
       }      // chunk loop
       tc_fence_before_sync();
-      mbar_arrive(&tmem_empty[acc]);
+      if constexpr (CTAS == 2) {
+        __syncwarp();
+        if (lane == 0) {
+          if (cta_rank == 0) mbar_arrive(&tmem_empty[acc]);
+          else mbar_arrive_cluster(&tmem_empty[acc], 0);   // the leader's MMA thread waits for both epilogues
+        }
+      } else {
+        mbar_arrive(&tmem_empty[acc]);
+      }
       if (cp.mode == COMM_RS) {
         // all 256 epilogue threads have issued their P2P stores -> one release-increment on the owner's counter
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
@@ -722,9 +770,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   tc_fence_before_sync();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();   // nobody may still target the peer's barriers / TMEM
   if (warp_idx == 1) {
     tc_fence_after_sync();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (CTAS == 2) tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
   if (cp.mode != COMM_NONE && threadIdx.x == 0) {
     // retire: the last CTA to get here advances the call counter and tells every peer that this rank is done reading
@@ -829,6 +879,33 @@ bool operand_tmap(CUtensorMap* m, const void* ptr, bool mn_major, int rows_or_co
   uint64_t strides[2] = {2, (uint64_t)ld * 2};
   uint32_t box[2] = {64u, (uint32_t)lb::BLOCK_K};
   return lb_host::make_tmap_bf16(m, ptr, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// CTA-pair (cta_group::2) variant: clusters of 2, 256 x 256 tiles
+template <bool AMN, bool BMN, int EPI>
+cudaError_t launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tg, const lb::GemmParams& p,
+                        const lb::CommParams& cp, int grid, cudaStream_t stream) {
+  using Cfg = lb::StageCfg<256, 2>;
+  auto kern = lb::gemm_kernel<256, AMN, BMN, EPI, false, 2>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(lb::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, tg, p, cp);
 }
 
 template <int BN, bool AMN, bool BMN, int EPI, bool FP8 = false>
@@ -981,9 +1058,17 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   p.deq_a = deq_a;
   p.deq_b = deq_b;
 
+  // CTA pairs (cta_group::2, 256 x 256 tiles, each CTA stages half of B) for the plain bf16 GEMMs whose tile width is
+  // 256 anyway; LIBAI_B200_GEMM_2CTA=0 keeps everything on single-CTA tiles.
+  static int allow_2cta = -1;
+  if (allow_2cta < 0) {
+    const char* e = getenv("LIBAI_B200_GEMM_2CTA");
+    allow_2cta = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const bool two_cta = allow_2cta && bn == 256 && cp.mode == lb::COMM_NONE && !p.fp8 && M > lb::BLOCK_M;
   CUtensorMap ta, tb, tg;
   if (!operand_tmap(&ta, a, a_mn, M, K, lda, lb::BLOCK_M)) return -2;
-  if (!operand_tmap(&tb, b, b_mn, N, K, ldb, bn)) return -2;
+  if (!operand_tmap(&tb, b, b_mn, N, K, ldb, two_cta ? bn / 2 : bn)) return -2;
   tg = ta;
   if (cp.mode == lb::COMM_AG) {
     // tensor map of the local shard of the gathered operand: [rows_per_rank, K] rows of A (NT/NN), or rows_per_rank
@@ -995,14 +1080,35 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   } else if (cp.mode == lb::COMM_RS) {
     cp.arrivals = (uint32_t)(cp.world * n_blocks);
   }
-  const long num_tiles = (long)m_blocks * n_blocks * p.k_splits;
+  long num_tiles = (long)m_blocks * n_blocks * p.k_splits;
   int grid = (int)(num_tiles < sms ? num_tiles : sms);
+  if (two_cta) {
+    num_tiles = (long)((m_blocks + 1) / 2) * n_blocks * p.k_splits;   // 256-row tiles, one per CTA pair
+    const long pairs = sms / 2;
+    grid = 2 * (int)(num_tiles < pairs ? num_tiles : pairs);
+  }
   if (cp.mode == lb::COMM_AG) {
     const long g = num_tiles < (sms - cp.n_comm) ? num_tiles : (sms - cp.n_comm);
     grid = (int)g + cp.n_comm;
   }
 
   cudaError_t e;
+  if (two_cta) {
+    if (layout == 0) {
+      if (epi == 0) e = launch_2cta<false, false, lb::EPI_BF16>(ta, tb, tg, p, cp, grid, stream);
+      else if (epi == 1) e = launch_2cta<false, false, lb::EPI_F32>(ta, tb, tg, p, cp, grid, stream);
+      else e = launch_2cta<false, false, lb::EPI_ATOMIC_F32>(ta, tb, tg, p, cp, grid, stream);
+    } else if (layout == 1) {
+      if (epi == 0) e = launch_2cta<false, true, lb::EPI_BF16>(ta, tb, tg, p, cp, grid, stream);
+      else if (epi == 1) e = launch_2cta<false, true, lb::EPI_F32>(ta, tb, tg, p, cp, grid, stream);
+      else e = launch_2cta<false, true, lb::EPI_ATOMIC_F32>(ta, tb, tg, p, cp, grid, stream);
+    } else {
+      if (epi == 0) e = launch_2cta<true, true, lb::EPI_BF16>(ta, tb, tg, p, cp, grid, stream);
+      else if (epi == 1) e = launch_2cta<true, true, lb::EPI_F32>(ta, tb, tg, p, cp, grid, stream);
+      else e = launch_2cta<true, true, lb::EPI_ATOMIC_F32>(ta, tb, tg, p, cp, grid, stream);
+    }
+    return (int)e;
+  }
   if (p.fp8) {
     if (layout != 0 || epi != 0 || cp.mode != lb::COMM_NONE) return -7;
     e = launch_bn<false, false, lb::EPI_BF16, true>(bn, ta, tb, tg, p, cp, grid, stream);
