@@ -224,12 +224,14 @@ template <uint32_t kCols>
 LB_DEVICE void tmem_dealloc_2cta(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(kCols) : "memory");
 }
-// arrive (count 1) on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+// arrive (count 1) on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster (the form CUTLASS'
+// ClusterBarrier::arrive(cta_id) uses; an explicit `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR per arrival,
+// which throttled the peer's TMA producer to one k-block per fence: profiles/r2_10_ncu_gemm_2cta_first.txt)
 LB_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
 }

@@ -1059,11 +1059,12 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   p.deq_b = deq_b;
 
   // CTA pairs (cta_group::2, 256 x 256 tiles, each CTA stages half of B) for the plain bf16 GEMMs whose tile width is
-  // 256 anyway; LIBAI_B200_GEMM_2CTA=0 keeps everything on single-CTA tiles.
+  // 256 anyway.  OPT-IN (LIBAI_B200_GEMM_2CTA=1): numerically verified on B200, but measured SLOWER than the single-CTA
+  // tiles in its current form (8192^3: 1.58 ms vs 0.81 ms, profiles/r2_09_kernel_check_gemm_2cta.json) — see DESIGN.md.
   static int allow_2cta = -1;
   if (allow_2cta < 0) {
     const char* e = getenv("LIBAI_B200_GEMM_2CTA");
-    allow_2cta = (e != nullptr && e[0] == '0') ? 0 : 1;
+    allow_2cta = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   const bool two_cta = allow_2cta && bn == 256 && cp.mode == lb::COMM_NONE && !p.fp8 && M > lb::BLOCK_M;
   CUtensorMap ta, tb, tg;

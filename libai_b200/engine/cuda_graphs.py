@@ -142,6 +142,9 @@ def enable_for_model(model: nn.Module, example_batch: dict) -> bool:
     from libai_b200.utils import distributed as dutil
 
     topo = dutil.get_dist_util()
+    if getattr(model, "zero_hooks", None) is not None:
+        logger.warning("cuda graphs: ZeRO stage 2/3 (per-block gradient / parameter buckets come and go) — not captured")
+        return False
     if (getattr(model, "activation_checkpoint", False)
             or (topo.tensor_parallel_size > 1 and not topo.fused_tp_comm)):
         # (checkpointing re-runs the forward inside backward; tensor parallelism is captured only in its fused form —

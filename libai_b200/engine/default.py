@@ -388,8 +388,10 @@ class DefaultTrainer(TrainerBase):
             stage = int(zero.stage) if zero is not None and zero.enabled else 0
             names = {id(p): n for n, p in model.named_parameters()}
             opt.configure(zero_stage=stage, param_names=names,
-                          dp_grad_reduce=getattr(model, "dp_grad_reduce", "mean"))
+                          dp_grad_reduce=getattr(model, "dp_grad_reduce", "mean"), model=model)
             opt.setup()
+            if getattr(opt, "bucket_hooks", None) is not None:
+                model.zero_hooks = opt.bucket_hooks    # ZeRO-2/3: forward_stage brackets every block with them
         return opt
 
     @classmethod

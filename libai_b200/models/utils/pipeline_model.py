@@ -45,6 +45,9 @@ class PipelineStageMixin:
     # set by the trainer for the last micro-batch of a step (None = no early gradient reduction)
     grad_ready_callback = None
     grad_ready_layers = ()
+    # ZeRO stage 2 / 3 (optim/zero_buckets.py): brackets every block — parameter all-gather before, gradient
+    # reduce-scatter after its backward; set by DefaultTrainer.build_optimizer
+    zero_hooks = None
 
     # ---- to be provided by the model -------------------------------------------------------
     def stage_pre(self, **batch):
@@ -78,10 +81,16 @@ class PipelineStageMixin:
                 continue
             if cb is not None and torch.is_tensor(hidden) and getattr(layer, "layer_idx", -1) in self.grad_ready_layers:
                 hidden = _GradBoundary.apply(hidden, layer.layer_idx, cb)
+            zh = self.zero_hooks
+            lidx = getattr(layer, "layer_idx", 0)
+            if zh is not None:
+                hidden = zh.wrap_before(hidden, lidx)
             if use_ckpt:
                 hidden = checkpoint(self.stage_layer_call, layer, hidden, batch, use_reentrant=False)
             else:
                 hidden = self.stage_layer_call(layer, hidden, batch)
+            if zh is not None:
+                hidden = zh.wrap_after(hidden, lidx)
         if topo.is_last_stage:
             return self.stage_post(hidden, **batch)
         return hidden

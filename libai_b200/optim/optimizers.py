@@ -88,6 +88,14 @@ class _Group:
     def grad_shard(self) -> torch.Tensor:
         return self.grad_flat[self.lo : self.hi]
 
+    def lp_shard(self) -> torch.Tensor:
+        """Low-precision parameters of the owned range (what the update writes)."""
+        return self.param_flat[self.lo : self.hi]
+
+    def reduced_view(self, lo: int, hi: int) -> torch.Tensor:
+        """Reduced gradients of the flat range ``[lo, hi)`` (inside the owned range)."""
+        return self.grad_flat[lo:hi]
+
 
 class FlatOptimizer(torch.optim.Optimizer):
     """Base class: flat buffers + DP sync + ZeRO + clipping; subclasses implement ``_update``."""
@@ -111,13 +119,20 @@ class FlatOptimizer(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ configuration
     def configure(self, *, zero_stage: int = 0, param_names: Optional[Dict[int, str]] = None,
-                  dp_grad_reduce: str = "mean"):
-        """Called by the trainer before the first step."""
+                  dp_grad_reduce: str = "mean", model=None):
+        """Called by the trainer before the first step.  ``model`` (a ``PipelineStageMixin``) lets ZeRO stage 2 / 3 bucket
+        the parameters per transformer block (``zero_buckets.py``)."""
         self.zero_stage = int(zero_stage)
         self.dp_grad_reduce = dp_grad_reduce
+        self._model = model
         if param_names:
             self._param_names = dict(param_names)
         return self
+
+    @property
+    def bucket_hooks(self):
+        """Hooks ``forward_stage`` has to call around every block (ZeRO stage 2 / 3), else ``None``."""
+        return getattr(self, "_bucket_hooks", None)
 
     def setup(self):
         """Materialise the flat buffers (idempotent). Must run before the first forward so that
@@ -127,14 +142,36 @@ class FlatOptimizer(torch.optim.Optimizer):
         topo = dutil.get_dist_util()
         sharded = self.zero_stage >= 1 and topo.data_parallel_size > 1
         self._groups = []
+        self._hp_index: List[int] = []          # param_groups index of every entry of _groups
+        if sharded and self.zero_stage >= 2:
+            # gradients (stage 2) / parameters too (stage 3) partitioned: per-block buckets, see zero_buckets.py
+            from .zero_buckets import ZeroBucketHooks, build_buckets
+
+            per_group, by_layer = build_buckets(self.param_groups, getattr(self, "_model", None),
+                                                topo.data_parallel_size, topo.dp_rank, self.zero_stage)
+            for gi, buckets in enumerate(per_group):
+                for b in buckets:
+                    for name in self.state_names:
+                        b.state[name] = torch.zeros(b.per, dtype=torch.float32, device=b.device)
+                    self._groups.append(b)
+                    self._hp_index.append(gi)
+            self._bucket_hooks = ZeroBucketHooks(by_layer, self.dp_grad_reduce) if by_layer else None
+            if not by_layer:
+                import logging
+
+                logging.getLogger(__name__).warning(
+                    "ZeRO stage %d: the model exposes no `stage_layers()` blocks — all parameters form one resident "
+                    "bucket (memory profile of stage 1)", self.zero_stage)
+            return self
         for gi, g in enumerate(self.param_groups):
             params = [p for p in g["params"] if p.device.type != "meta" and p.requires_grad]
+            self._hp_index.append(gi)
             if not params:
                 self._groups.append(None)
                 continue
             ws = None
             if (sharded and self.fused_zero_comm and params[0].is_cuda and params[0].dtype == torch.bfloat16
-                    and ops_impl() == "native" and topo.data_parallel_size <= 8):
+                    and ops_impl() == "native" and topo.data_parallel_size <= 8 and self.zero_stage == 1):
                 from libai_b200.parallel.symm_mem import get_workspace
 
                 ws = get_workspace(topo.dp_group)
@@ -149,6 +186,14 @@ class FlatOptimizer(torch.optim.Optimizer):
         self.setup()
         for fg in self._groups:
             if fg is None:
+                continue
+            if hasattr(fg, "red"):           # ZeRO-2/3 bucket: the persistent piece is the reduced-gradient shard
+                fg.red.zero_()
+                if fg.grad_flat is not None:
+                    fg.grad_flat.zero_()
+                for p in fg.params:
+                    p.grad = None
+                    p.grad_added_to_main_grad = False
                 continue
             fg.grad_flat.zero_()
             fg.reduced_from = fg.hi          # nothing of the owned slice has been reduced yet
@@ -257,7 +302,7 @@ class FlatOptimizer(torch.optim.Optimizer):
     def _collect_autograd_grads(self):
         """Fold ``p.grad`` (produced by the PyTorch reference path) into ``main_grad``."""
         for fg in self._groups:
-            if fg is None:
+            if fg is None or hasattr(fg, "red"):
                 continue
             for p in fg.params:
                 if p.grad is not None:
@@ -273,6 +318,14 @@ class FlatOptimizer(torch.optim.Optimizer):
         topo = dutil.get_dist_util()
         for fg in self._groups:
             if fg is None:
+                continue
+            if hasattr(fg, "red"):
+                # ZeRO-2/3: block buckets were reduce-scattered from the backward hooks; what is still open here are
+                # the persistent buckets (embeddings / heads / final norm) and blocks that ran outside forward_stage
+                scale = 1.0 / topo.data_parallel_size if self.dp_grad_reduce == "mean" else 1.0
+                if fg.grad_flat is None and any(p.grad is not None for p in fg.params):
+                    fg.open_grads()
+                fg.reduce_grads(topo, scale)
                 continue
             # (1) parameters replicated over TP whose grads were computed on token shards (LayerNorm γ/β, row-parallel
             # biases): ONE all-reduce over a packed buffer instead of one tiny NCCL call per parameter (≈150 per step
@@ -349,12 +402,13 @@ class FlatOptimizer(torch.optim.Optimizer):
                     lo, hi = max(off, fg.lo), min(off + p.numel(), fg.hi)
                     if lo < hi:
                         skip.append((lo, hi))
+            view = fg.reduced_view
             if math.isinf(norm_type) and skip:
                 acc = torch.zeros((), dtype=torch.float32, device=dev)
                 cur = fg.lo
                 for lo, hi in skip + [(fg.hi, fg.hi)]:
                     if cur < lo:
-                        acc = torch.maximum(acc, _acc(fg.grad_flat[cur:lo]))
+                        acc = torch.maximum(acc, _acc(view(cur, lo)))
                     cur = max(cur, hi)
             else:
                 acc = _acc(fg.grad_shard())
@@ -367,7 +421,7 @@ class FlatOptimizer(torch.optim.Optimizer):
                             merged[-1] = (merged[-1][0], hi)
                         else:
                             merged.append((lo, hi))
-                    dup = torch.cat([fg.grad_flat[lo:hi] for lo, hi in merged]) if len(merged) > 1 else fg.grad_flat[merged[0][0]:merged[0][1]]
+                    dup = torch.cat([view(lo, hi) for lo, hi in merged]) if len(merged) > 1 else view(merged[0][0], merged[0][1])
                     acc = acc - (torch.dot(dup, dup) if norm_type == 2.0 else dup.abs().pow(norm_type).sum())
             total = acc if total is None else (torch.maximum(total, acc) if math.isinf(norm_type) else total + acc)
         if total is None:
@@ -425,14 +479,18 @@ class FlatOptimizer(torch.optim.Optimizer):
         self._step_count += 1
         ops.bump_fp8_weight_epoch()     # parameters are rewritten in place: cached E4M3 weight copies are stale
         topo = dutil.get_dist_util()
-        for g, fg in zip(self.param_groups, self._groups):
+        for gi, fg in zip(self._hp_index, self._groups):
             if fg is None:
                 continue
+            g = self.param_groups[gi]
             scale = coef * self.grad_scale if coef is not None else None
             if fg.symm is not None and hasattr(self, "_fused_zero_update"):
                 self._fused_zero_update(g, fg, self._step_count, scale)
                 continue
             self._update(g, fg, self._step_count, scale)
+            if hasattr(fg, "red"):
+                fg.publish_params(topo.dp_group)      # ZeRO-2 (and resident buckets of ZeRO-3): refresh the full copy
+                continue
             if fg.sharded:
                 shard = fg.param_flat[fg.lo : fg.hi]
                 if fg.device.type == "cuda":
@@ -505,10 +563,42 @@ class FlatOptimizer(torch.optim.Optimizer):
             return self
         with torch.no_grad():
             for fg in self._groups:
-                if fg is not None and fg.master is not None:
+                if fg is None:
+                    continue
+                if hasattr(fg, "red"):
+                    if fg.param_flat is not None:       # (non-resident ZeRO-3 buckets: see params_materialized)
+                        fg.adopt_param_values()
+                elif fg.master is not None:
                     fg.master.copy_(fg.param_flat[fg.lo : fg.hi])
         ops.bump_fp8_weight_epoch()
         return self
+
+    def params_materialized(self, writeback: bool = False):
+        """Context manager: every parameter holds its full, current value while inside (ZeRO stage 3 keeps block
+        parameters as 1/dp shards between uses) — checkpoint save / load, weight loaders and anything else that reads or
+        writes ``model.parameters()`` directly must run inside.  ``writeback``: the values were modified (a checkpoint
+        was loaded): every rank takes its slice back as shard + fp32 master on exit."""
+        from contextlib import contextmanager
+
+        @contextmanager
+        def ctx():
+            self.setup()
+            topo = dutil.get_dist_util()
+            opened = []
+            for fg in self._groups:
+                if fg is not None and hasattr(fg, "red") and fg.param_flat is None:
+                    fg.gather_params(topo.dp_group)
+                    opened.append(fg)
+            try:
+                yield self
+            finally:
+                for fg in self._groups:
+                    if fg is not None and hasattr(fg, "red") and writeback and fg.param_flat is not None:
+                        fg.adopt_param_values()
+                for fg in opened:
+                    fg.release_params()
+
+        return ctx()
 
     def load_state_dict(self, sd):
         self.setup()
@@ -570,7 +660,7 @@ class AdamW(FlatOptimizer):
         if use_native(g):
             ext = load_ext()
             scale_t = scale if scale is not None else torch.ones((), dtype=torch.float32, device=g.device)
-            out_lp = fg.param_flat[fg.lo : fg.hi] if fg.master is not None else None
+            out_lp = fg.lp_shard() if fg.master is not None else None
             ext.fused_adamw(master, g, m, v, out_lp, scale_t.reshape(1).float(), float(lr), float(b1), float(b2),
                             float(eps), float(wd), float(bc1), float(bc2), bool(self.decoupled))
             count_launch()
@@ -587,7 +677,7 @@ class AdamW(FlatOptimizer):
             upd = upd + wd * master
         master.add_(upd, alpha=-lr)
         if fg.master is not None:
-            fg.param_flat[fg.lo : fg.hi].copy_(master)
+            fg.lp_shard().copy_(master)
 
 
     def _fused_zero_update(self, group, fg, step, scale):
@@ -636,7 +726,7 @@ class SGD(FlatOptimizer):
             g = g + mom * buf if nest else buf
         master.add_(g, alpha=-lr)
         if fg.master is not None:
-            fg.param_flat[fg.lo : fg.hi].copy_(master)
+            fg.lp_shard().copy_(master)
 
 
 class LAMB(FlatOptimizer):
@@ -688,4 +778,4 @@ class LAMB(FlatOptimizer):
             if b > a:
                 master[a:b].add_(upd[a:b] * trust[i], alpha=-lr)
         if fg.master is not None:
-            fg.param_flat[fg.lo : fg.hi].copy_(master)
+            fg.lp_shard().copy_(master)

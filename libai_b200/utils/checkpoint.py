@@ -55,7 +55,8 @@ class Checkpointer:
     # ------------------------------------------------------------------ save
     def save(self, name: str, **kwargs: Any) -> None:
         """Collective over all ranks: gathers logical tensors, rank 0 writes."""
-        payload = {"model": pstate.full_state_dict(self.model)}
+        with self._params_materialized():
+            payload = {"model": pstate.full_state_dict(self.model)}
         for key, obj in self.checkpointables.items():
             payload[key] = obj.state_dict()
         payload.update(kwargs)
@@ -81,19 +82,30 @@ class Checkpointer:
             return {}
         self.logger.info(f"Loading checkpoint from {path}")
         ckpt = self._load_file(path)
-        incompatible = self._load_model(ckpt)
-        if incompatible is not None:
-            self._log_incompatible_keys(incompatible)
-        # the optimizer's fp32 master weights were snapshotted from the pre-load parameters: re-derive them (an
-        # optimizer state with ``master`` entries, loaded below, then overrides this with the exact fp32 values)
-        for obj in self.checkpointables.values():
-            if hasattr(obj, "refresh_master"):
-                obj.refresh_master()
+        with self._params_materialized(writeback=True):
+            incompatible = self._load_model(ckpt)
+            if incompatible is not None:
+                self._log_incompatible_keys(incompatible)
+            # the optimizer's fp32 master weights were snapshotted from the pre-load parameters: re-derive them (an
+            # optimizer state with ``master`` entries, loaded below, then overrides this with the exact fp32 values)
+            for obj in self.checkpointables.values():
+                if hasattr(obj, "refresh_master"):
+                    obj.refresh_master()
         for key in list(self.checkpointables if checkpointables is None else checkpointables):
             if key in ckpt:
                 self.logger.info(f"Loading {key} from {path}")
                 self.checkpointables[key].load_state_dict(ckpt.pop(key))
         return ckpt
+
+    def _params_materialized(self, writeback: bool = False):
+        """ZeRO stage 3 keeps block parameters as 1/dp shards between uses: reading / writing the model's tensors needs
+        them gathered (``FlatOptimizer.params_materialized``); a no-op otherwise."""
+        from contextlib import nullcontext
+
+        for obj in self.checkpointables.values():
+            if hasattr(obj, "params_materialized"):
+                return obj.params_materialized(writeback=writeback)
+        return nullcontext()
 
     def has_checkpoint(self) -> bool:
         return os.path.exists(os.path.join(self.save_dir, "last_checkpoint"))
