@@ -952,6 +952,15 @@ static bool wgrad_rmw() {
   return v == 1;
 }
 
+static int gemm_allow_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LIBAI_B200_GEMM_2CTA");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+
 static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldo, int layout,
                      int epi, const void* bias, int act, void* pre_out, const void* pre_in, int force_bn,
                      int force_splits, const lb::CommParams& cp_in, cudaStream_t stream, const float* deq_a = nullptr,
@@ -974,11 +983,18 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
     const int cands[4] = {256, 192, 128, 64};
     for (int c : cands) {
       if (c > 64 && N <= c / 2) continue;
-      const long tiles = (long)m_blocks * ((N + c - 1) / c);
-      const long waves = (tiles + sms - 1) / sms;
+      long tiles = (long)m_blocks * ((N + c - 1) / c);
+      long waves = (tiles + sms - 1) / sms;
       // cost ~ waves * per-tile time (proportional to c, narrower tiles pay more shared-memory traffic per
       // flop, plus a fixed prologue/epilogue overhead per tile)
-      const double eff = c == 256 ? 1.0 : (c == 192 ? 1.03 : (c == 128 ? 1.08 : 1.2));
+      double eff = c == 256 ? 1.0 : (c == 192 ? 1.03 : (c == 128 ? 1.08 : 1.2));
+      if (c == 256 && cp_in.mode == lb::COMM_NONE && deq_a == nullptr && M > lb::BLOCK_M && gemm_allow_2cta()) {
+        // 256-wide tiles run on CTA pairs (256 x 256 per pair, half the B traffic per SM): measured ~12 % faster per
+        // tile row, scheduled over sms / 2 pairs
+        tiles = (long)((m_blocks + 1) / 2) * ((N + c - 1) / c);
+        waves = (tiles + sms / 2 - 1) / (sms / 2);
+        eff = 0.89;
+      }
       const double cost = (double)waves * (c * eff + 24.0);
       if (cost < best - 1e-9) {
         best = cost;
@@ -1059,13 +1075,9 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   p.deq_b = deq_b;
 
   // CTA pairs (cta_group::2, 256 x 256 tiles, each CTA stages half of B) for the plain bf16 GEMMs whose tile width is
-  // 256 anyway.  OPT-IN (LIBAI_B200_GEMM_2CTA=1): numerically verified on B200, but measured SLOWER than the single-CTA
-  // tiles in its current form (8192^3: 1.58 ms vs 0.81 ms, profiles/r2_09_kernel_check_gemm_2cta.json) — see DESIGN.md.
-  static int allow_2cta = -1;
-  if (allow_2cta < 0) {
-    const char* e = getenv("LIBAI_B200_GEMM_2CTA");
-    allow_2cta = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
+  // 256: 10-27 % faster than the single-CTA tiles on the benchmark shapes (8192^3 0.71 vs 0.81 ms, LM head 0.64 vs
+  // 0.81 ms, profiles/r2_11_kernel_check_gemm_2cta.json).  LIBAI_B200_GEMM_2CTA=0 keeps everything on single-CTA tiles.
+  const int allow_2cta = gemm_allow_2cta();
   const bool two_cta = allow_2cta && bn == 256 && cp.mode == lb::COMM_NONE && !p.fp8 && M > lb::BLOCK_M;
   CUtensorMap ta, tb, tg;
   if (!operand_tmap(&ta, a, a_mn, M, K, lda, lb::BLOCK_M)) return -2;
