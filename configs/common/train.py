@@ -44,7 +44,7 @@ train = dict(
     nccl_fusion_threshold_mb=16,
     nccl_fusion_max_ops=24,
     # ZeRO: fp32 master weights + Adam moments partitioned over DP (fused NVLink reduce-scatter/Adam/all-gather);
-    # stages 2 and 3 are accepted (same numerics) but gradients / bf16 parameters stay replicated for now
+    # stage 2 additionally partitions the gradients, stage 3 the parameters too (per-block buckets, optim/zero_buckets.py)
     zero_optimization=dict(enabled=False, stage=1),
     checkpointer=dict(period=5000, max_to_keep=100, save_model_after_n_epoch=None),
     test_micro_batch_size=32,

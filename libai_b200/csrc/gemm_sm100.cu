@@ -213,11 +213,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int mbpr = cp.mode != COMM_NONE ? cp.rows_per_rank / BLOCK_M : m_blocks;
   const bool ag_b = cp.mode == COMM_AG && cp.gathered_is_b != 0;   // TN wgrad: shards along the reduction dimension
   // row blocks are visited owner by owner: AG starts with the local rows (already resident), RS ends with them
+  // (in units of one CTA tile row = BLOCK_M * CTAS rows; a shard holds mbpr / CTAS of them)
   auto map_m = [&](int m_seq) -> int {
     if (cp.mode == COMM_NONE || ag_b) return m_seq;
+    const int upr = mbpr / CTAS;
     const int shift = (cp.mode == COMM_AG) ? 0 : 1;
-    const int owner = (cp.rank + shift + m_seq / mbpr) % cp.world;
-    return owner * mbpr + m_seq % mbpr;
+    const int owner = (cp.rank + shift + m_seq / upr) % cp.world;
+    return owner * upr + m_seq % upr;
   };
   // work item -> (output tile, K partition).  Default: partitions of one tile are neighbours (their red.adds hit L2
   // together).  Gathered-B wgrad: partition-major, starting with the partitions that lie in the local shard (the host
@@ -383,7 +385,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int tile = cta; tile < num_tiles; tile += cta_stride) {
         int split, mn;
         decode_tile(tile, mn, split);
-        const int m_blk = map_m(mn / n_blocks), n_blk = mn % n_blocks;
+        const int m_blk = map_m(mn / n_blocks) * CTAS + cta_rank, n_blk = mn % n_blocks;   // this CTA's 128-row block
         // gathered A: rows of the local shard come straight from the shard's own tensor map, rows owned by a peer
         // from the gathered buffer once that peer's copy CTAs have pushed the row block (arrival counter)
         const bool a_local = cp.mode == COMM_AG && !ag_b && m_blk / mbpr == cp.rank;
@@ -392,7 +394,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           asm volatile("fence.proxy.async.global;\n" ::: "memory");
         }
         const CUtensorMap* map_a = a_local ? &tmap_g : &tmap_a;
-        const int m_row = a_local ? (m_blk - cp.rank * mbpr) * BLOCK_M : (m_blk * CTAS + cta_rank) * BLOCK_M;
+        const int m_row = a_local ? (m_blk - cp.rank * mbpr) * BLOCK_M : m_blk * BLOCK_M;
         const int n_row = n_blk * BLOCK_N + cta_rank * (BLOCK_N / CTAS);   // pair: this CTA's half of the B tile
         const int kb0 = split * p.k_per_split;
         const int kb1 = min(kb0 + p.k_per_split, k_blocks_total);
@@ -411,13 +413,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          const CUtensorMap* map_b = b_local ? &tmap_g : &tmap_b;
+          const int k_row = b_local ? kb * BLOCK_K - cp.rank * cp.rows_per_rank : kb * BLOCK_K;
           if constexpr (CTAS == 2) {
             // both CTAs' loads complete on the LEADER's barrier: the leader arms it with the bytes of both, the peer
             // contributes its arrival remotely
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * 2);
             else mbar_arrive_cluster(&full_bar[stage], 0);
             if constexpr (!A_MN) {
-              tma_load_2d_2cta(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_row);
+              tma_load_2d_2cta(sa, map_a, &full_bar[stage], kb * BLOCK_K, m_row);
             } else {
 #pragma unroll
               for (int a = 0; a < BLOCK_M / 64; ++a)
@@ -428,7 +432,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             } else {
 #pragma unroll
               for (int a = 0; a < (BLOCK_N / 2) / 64; ++a)
-                tma_load_2d_2cta(sb + a * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_row + a * 64, kb * BLOCK_K);
+                tma_load_2d_2cta(sb + a * (BLOCK_K * 128), map_b, &full_bar[stage], n_row + a * 64, k_row);
             }
             if (++stage == NS) {
               stage = 0;
@@ -447,8 +451,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if constexpr (!B_MN) {
             tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
           } else {
-            const CUtensorMap* map_b = b_local ? &tmap_g : &tmap_b;
-            const int k_row = b_local ? kb * BLOCK_K - cp.rank * cp.rows_per_rank : kb * BLOCK_K;
 #pragma unroll
             for (int a = 0; a < BLOCK_N / 64; ++a)
               tma_load_2d(sb + a * (BLOCK_K * 128), map_b, &full_bar[stage], n_blk * BLOCK_N + a * 64, k_row);
@@ -956,7 +958,8 @@ static int gemm_allow_2cta() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("LIBAI_B200_GEMM_2CTA");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    // 0: off; 1 (default): plain GEMMs; 2: also the fused-collective GEMMs (AG->GEMM / GEMM->RS / gathered-B wgrad)
+    v = (e == nullptr) ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
   }
   return v;
 }
@@ -1078,7 +1081,10 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   // 256: 10-27 % faster than the single-CTA tiles on the benchmark shapes (8192^3 0.71 vs 0.81 ms, LM head 0.64 vs
   // 0.81 ms, profiles/r2_11_kernel_check_gemm_2cta.json).  LIBAI_B200_GEMM_2CTA=0 keeps everything on single-CTA tiles.
   const int allow_2cta = gemm_allow_2cta();
-  const bool two_cta = allow_2cta && bn == 256 && cp.mode == lb::COMM_NONE && !p.fp8 && M > lb::BLOCK_M;
+  // (fused collectives: shards must hold whole 256-row pair tiles and the copy CTAs come in pairs)
+  const bool comm_ok = cp.mode == lb::COMM_NONE ||
+                       (cp.rows_per_rank % (2 * lb::BLOCK_M) == 0 && cp.n_comm % 2 == 0 && gemm_allow_2cta() >= 2);
+  const bool two_cta = allow_2cta && bn == 256 && comm_ok && !p.fp8 && M > lb::BLOCK_M;
   CUtensorMap ta, tb, tg;
   if (!operand_tmap(&ta, a, a_mn, M, K, lda, lb::BLOCK_M)) return -2;
   if (!operand_tmap(&tb, b, b_mn, N, K, ldb, two_cta ? bn / 2 : bn)) return -2;
@@ -1097,12 +1103,16 @@ static int gemm_impl(const void* a, const void* b, void* out, int M, int N, int 
   int grid = (int)(num_tiles < sms ? num_tiles : sms);
   if (two_cta) {
     num_tiles = (long)((m_blocks + 1) / 2) * n_blocks * p.k_splits;   // 256-row tiles, one per CTA pair
-    const long pairs = sms / 2;
+    const long pairs = (sms - (cp.mode == lb::COMM_AG ? cp.n_comm : 0)) / 2;
     grid = 2 * (int)(num_tiles < pairs ? num_tiles : pairs);
   }
   if (cp.mode == lb::COMM_AG) {
-    const long g = num_tiles < (sms - cp.n_comm) ? num_tiles : (sms - cp.n_comm);
-    grid = (int)g + cp.n_comm;
+    if (two_cta) {
+      grid += cp.n_comm;
+    } else {
+      const long g = num_tiles < (sms - cp.n_comm) ? num_tiles : (sms - cp.n_comm);
+      grid = (int)g + cp.n_comm;
+    }
   }
 
   cudaError_t e;
