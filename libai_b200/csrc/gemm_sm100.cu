@@ -958,8 +958,8 @@ static int gemm_allow_2cta() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("LIBAI_B200_GEMM_2CTA");
-    // 0: off; 1 (default): plain GEMMs; 2: also the fused-collective GEMMs (AG->GEMM / GEMM->RS / gathered-B wgrad)
-    v = (e == nullptr) ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
+    // 0: off; 1: plain GEMMs only; 2 (default): also the fused-collective GEMMs (AG->GEMM / GEMM->RS / gathered-B wgrad)
+    v = (e == nullptr) ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2));
   }
   return v;
 }
