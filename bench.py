@@ -381,9 +381,13 @@ def measure_native(args, lay, world, rank, local_rank, steps, warmup, with_e2e, 
         "clocks": clocks,
         "final_loss": None,
     }
+    # (under pipeline parallelism only the last stage holds the loss: take it from whoever has it)
+    lv = torch.full((1,), -1e30, dtype=torch.float32, device=dev)
     if loss:
-        lv = sum(v for k, v in loss.items() if "loss" in k)
-        res["final_loss"] = float(lv)
+        lv[0] = sum(v for k, v in loss.items() if "loss" in k).float()
+    if world > 1:
+        dist.all_reduce(lv, op=dist.ReduceOp.MAX)
+    res["final_loss"] = float(lv) if float(lv) > -1e29 else None
 
     # ---- end to end through the trainer API: loader (pinned host) → H2D → step → loss D2H, every step ---------------
     if with_e2e:
@@ -419,7 +423,7 @@ def measure_native(args, lay, world, rank, local_rank, steps, warmup, with_e2e, 
     from libai_b200.parallel import symm_mem
 
     comm_gemm.reset_states()
-    symm_mem._WORKSPACES.clear()
+    symm_mem.release_workspaces()    # collective: unmap the peers' buffers before anyone frees them
     gc.collect()
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
@@ -487,6 +491,64 @@ def measure_pytorch_baseline(args, world, rank, local_rank, steps, warmup):
     return out
 
 
+class _ExtrasWatchdog:
+    """Keeps the headline line safe while the extra layouts run.  One node, so a flag file is the signal: the rank
+    that fails (or sees a layout exceed ``limit_s``) creates it; a polling thread on every rank notices, rank 0 prints
+    the JSON line with what was measured so far, and every rank leaves with exit code 0 (ranks blocked inside a
+    collective cannot be unwound any other way)."""
+
+    def __init__(self, world, emit, layouts, limit_s):
+        import threading
+
+        self.world, self.emit, self.layouts, self.limit_s = world, emit, layouts, limit_s
+        self.flag = os.path.join("/tmp", f"libai_b200_bench_fail_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}")
+        self.current, self.t0, self._stop = None, 0.0, False
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0 and os.path.exists(self.flag):
+            os.remove(self.flag)
+        self.thread = None
+        if world > 1:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+
+    def begin(self, name):
+        self.current, self.t0 = name, time.time()
+
+    def stop(self):
+        self._stop = True
+
+    def _leave(self, why):
+        name = self.current or "extra"
+        self.layouts.setdefault(name, {"error": why})
+        try:
+            self.emit()
+        finally:
+            sys.stdout.flush()
+            os._exit(0)
+
+    def _poll(self):
+        while not self._stop:
+            time.sleep(0.5)
+            if os.path.exists(self.flag):
+                try:
+                    why = open(self.flag).read()[:400] or "a peer rank failed"
+                except OSError:
+                    why = "a peer rank failed"
+                self._leave(why)
+            if self.current is not None and time.time() - self.t0 > self.limit_s:
+                self.fail(self.current, f"layout exceeded {self.limit_s:.0f} s")
+
+    def fail(self, name, why):
+        if self.world == 1:
+            return
+        try:
+            with open(self.flag, "w") as f:
+                f.write(f"{name}: {why}")
+        except OSError:
+            pass
+        time.sleep(1.5)          # let the peers' pollers see the flag before this process goes away
+        self._leave(f"{name}: {why}")
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -513,27 +575,13 @@ def main():
 
     layouts = {main_res["parallelism"]: {k: main_res[k] for k in ("value", "ms_per_step", "cuda_graphs", "gpu_launches",
                                                                   "host_enqueue_ms_per_step", "global_batch")}}
-    if args.extras and args.impl == "native" and args.model == "gpt2" and not args.layout and args.tp == 1 and args.pp == 1:
-        # the model-parallel layouts that fit this GPU count, same global batch, same launch (BASELINE.json configs:
-        # "TP=2 DP=4", "TP=2 PP=2 DP=2 + ZeRO-1")
-        names = {2: ["tp2"], 4: ["tp2", "3d"], 8: ["tp2", "3d"]}.get(world, [])
-        for name in names:
-            lay = layout_of(args, world, name)
-            try:
-                r = measure_native(args, lay, world, rank, local_rank, args.extra_steps, max(3, min(args.warmup, 4)), False)
-                layouts[r["parallelism"]] = {k: r[k] for k in ("value", "ms_per_step", "cuda_graphs", "gpu_launches",
-                                                               "host_enqueue_ms_per_step", "global_batch", "final_loss")}
-                layouts[r["parallelism"]]["steps"] = args.extra_steps
-            except Exception as e:  # an extra layout must never take the headline measurement down
-                layouts[name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
-                if world > 1:
-                    raise      # a rank-local failure would leave the others in a collective: fail loudly instead
-
     ref_same_box = None
     if args.ref_same_box and args.impl == "native" and args.model == "gpt2":
         ref_same_box = measure_pytorch_baseline(args, world, rank, local_rank, min(args.steps, 10), 3)
 
-    if rank == 0:
+    def emit():
+        if rank != 0:
+            return
         base = PUBLISHED_TOKENS_PER_S.get(world) if args.model == "gpt2" else None
         value = main_res["value"]
         spec = MODELS[args.model]
@@ -575,7 +623,31 @@ def main():
             "ref_same_box": ref_same_box,
             "vs_ref_same_box": (value / ref_same_box["value"]) if ref_same_box else None,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+
+    if args.extras and args.impl == "native" and args.model == "gpt2" and not args.layout and args.tp == 1 and args.pp == 1:
+        # the model-parallel layouts that fit this GPU count, same global batch, same launch (BASELINE.json configs:
+        # "TP=2 DP=4", "TP=2 PP=2 DP=2 + ZeRO-1").  They run LAST and under a watchdog: the headline measurement above
+        # is already complete, and a failure (or a hang) in an extra layout on any rank ends every rank cleanly with
+        # the line printed — it must never take the headline down.
+        names = {2: ["tp2"], 4: ["tp2", "3d"], 8: ["tp2", "3d"]}.get(world, [])
+        watch = _ExtrasWatchdog(world, emit, layouts, limit_s=float(os.environ.get("LIBAI_B200_BENCH_EXTRA_LIMIT_S", "420")))
+        for name in names:
+            lay = layout_of(args, world, name)
+            watch.begin(name)
+            try:
+                if os.environ.get("LIBAI_B200_BENCH_INJECT_EXTRA_FAIL", "") == str(rank):   # exercises the watchdog path
+                    raise RuntimeError("injected failure in an extra layout")
+                r = measure_native(args, lay, world, rank, local_rank, args.extra_steps, max(3, min(args.warmup, 4)), False)
+                layouts[r["parallelism"]] = {k: r[k] for k in ("value", "ms_per_step", "cuda_graphs", "gpu_launches",
+                                                               "host_enqueue_ms_per_step", "global_batch", "final_loss")}
+                layouts[r["parallelism"]]["steps"] = args.extra_steps
+            except BaseException as e:  # noqa: BLE001 - incl. KeyboardInterrupt/SystemExit raised inside the trainer
+                watch.fail(name, f"{type(e).__name__}: {str(e)[:300]}")   # does not return when world > 1
+                layouts[name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        watch.stop()
+
+    emit()
     if world > 1:
         dist.destroy_process_group()
     return 0

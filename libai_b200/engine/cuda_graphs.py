@@ -15,8 +15,9 @@ Tensor-parallel blocks are captured too when the collectives are the fused ones 
 AG→GEMM / GEMM→RS kernels keep their call counters, arrival targets and write credits in device memory and advance them
 themselves, so a replay is indistinguishable from a fresh launch.
 
-Not captured: embedding, LM head + loss, optimizer, NCCL collectives.  Restrictions (checked): one tensor argument per
-block, no pipeline parallelism, no activation checkpointing.  Dropout inside captured blocks draws its Philox offset
+Not captured: embedding, LM head + loss, optimizer, NCCL collectives.  Restrictions (checked): besides the hidden state a
+block may take model buffers as keyword tensors (RoPE tables — Llama) and a right-padded ``KeyPaddingMask`` (BERT,
+RoBERTa: its key lengths become a second graph input); no activation checkpointing.  Dropout inside captured blocks draws its Philox offset
 from a device counter that the dropout kernels advance (``ops/functional.py``), so replays produce fresh masks.
 """
 from __future__ import annotations
@@ -88,27 +89,91 @@ def set_micro_batch_slot(i: int) -> None:
     _CURRENT_SLOT = int(i)
 
 
+class BlockCallSpec:
+    """How a model calls its blocks besides the hidden state (discovered from one eager call):
+
+    * ``const_kwargs`` – keyword tensors that are buffers of the model (RoPE cos/sin tables): the same storage on every
+      call, so the captured kernels simply keep reading it;
+    * ``key_lengths`` – the block takes a ``KeyPaddingMask`` as second positional argument (BERT / RoBERTa): its
+      per-sample key lengths (int32 ``[b]``) become a second *graph input*, copied into the static buffer on replay.
+    """
+
+    def __init__(self, const_kwargs=None, key_lengths: Optional[torch.Tensor] = None):
+        self.const_kwargs = dict(const_kwargs or {})
+        self.key_lengths = key_lengths
+
+    @property
+    def trivial(self) -> bool:
+        return not self.const_kwargs and self.key_lengths is None
+
+    def matches(self, args, kwargs) -> bool:
+        """Can this call be served by the captured graph?  (Otherwise the caller runs the eager block.)"""
+        live = {k: v for k, v in kwargs.items() if v is not None}
+        if set(live) != set(self.const_kwargs) or any(live[k] is not self.const_kwargs[k] for k in live):
+            return False
+        if self.key_lengths is None:
+            return len(args) == 0
+        if len(args) != 1:
+            return False
+        from libai_b200.layers.attention import KeyPaddingMask
+
+        m = args[0]
+        return (isinstance(m, KeyPaddingMask) and m.lengths.shape == self.key_lengths.shape and m.is_prefix())
+
+    def graph_inputs(self, args):
+        return (args[0].lengths,) if self.key_lengths is not None else ()
+
+
+def classify_block_call(model: nn.Module, args, kwargs) -> Optional[BlockCallSpec]:
+    """``args`` / ``kwargs``: what the first block received after the hidden state.  ``None`` = not capturable."""
+    from libai_b200.layers.attention import KeyPaddingMask
+
+    buffers = {id(b) for b in model.buffers()}
+    const = {}
+    for k, v in kwargs.items():
+        if v is None:
+            continue
+        if not (torch.is_tensor(v) and id(v) in buffers):
+            return None
+        const[k] = v
+    args = [a for a in args]
+    while args and args[-1] is None:
+        args.pop()
+    if not args:
+        return BlockCallSpec(const)
+    if len(args) == 1 and isinstance(args[0], KeyPaddingMask) and args[0].is_prefix():
+        return BlockCallSpec(const, args[0].lengths)
+    return None
+
+
 class _EagerBlock:
     """Plain callable around a block's original forward: ``make_graphed_callables`` then treats the parameters as
     captured constants (they live at fixed addresses in the optimizer's flat buffer and their gradients are
     accumulated into ``main_grad`` by the captured backward kernels themselves)."""
 
-    def __init__(self, block):
+    def __init__(self, block, spec: Optional[BlockCallSpec] = None):
         self.fn = block.forward
+        self.spec = spec or BlockCallSpec()
 
-    def __call__(self, hidden):
-        return self.fn(hidden)
+    def __call__(self, hidden, lengths=None):
+        if lengths is None:
+            return self.fn(hidden, **self.spec.const_kwargs)
+        from libai_b200.layers.attention import KeyPaddingMask
+
+        return self.fn(hidden, KeyPaddingMask.from_lengths(lengths), **self.spec.const_kwargs)
 
 
-def graph_blocks_multi_slot(blocks: Sequence[nn.Module], sample_hidden: torch.Tensor, n_slots: int, warmup_iters: int = 3
-                            ) -> bool:
+def graph_blocks_multi_slot(blocks: Sequence[nn.Module], sample_hidden: torch.Tensor, n_slots: int, warmup_iters: int = 3,
+                            spec: Optional[BlockCallSpec] = None) -> bool:
+    spec = spec or BlockCallSpec()
+    extra = (spec.key_lengths.detach().clone(),) if spec.key_lengths is not None else ()
     with torch.no_grad():
         n0 = ops.launch_count()
-        blocks[0](sample_hidden.detach())
+        _EagerBlock(blocks[0], spec)(sample_hidden.detach(), *extra)
         fwd_kernels = ops.launch_count() - n0
     torch.cuda.synchronize()
-    fns = tuple(_EagerBlock(b) for _ in range(n_slots) for b in blocks)
-    samples = tuple((sample_hidden.detach().clone().requires_grad_(True),) for _ in fns)
+    fns = tuple(_EagerBlock(b, spec) for _ in range(n_slots) for b in blocks)
+    samples = tuple((sample_hidden.detach().clone().requires_grad_(True),) + tuple(e.clone() for e in extra) for _ in fns)
     n0 = ops.launch_count()
     graphed = torch.cuda.make_graphed_callables(fns, samples, num_warmup_iters=warmup_iters, allow_unused_input=True)
     per_block = (ops.launch_count() - n0) // ((warmup_iters + 1) * len(fns))
@@ -125,11 +190,12 @@ def graph_blocks_multi_slot(blocks: Sequence[nn.Module], sample_hidden: torch.Te
         eager = fns[k].fn
         slots = [graphed[s * nb + k] for s in range(n_slots)]
 
-        def forward(hidden, _eager=eager, _slots=slots, _block=block):
-            if not (torch.is_grad_enabled() and _block.training and hidden.requires_grad):
-                return _eager(hidden)
+        def forward(hidden, *args, _eager=eager, _slots=slots, _block=block, **kwargs):
+            if not (torch.is_grad_enabled() and _block.training and hidden.requires_grad
+                    and hidden.shape == sample_hidden.shape and spec.matches(args, kwargs)):
+                return _eager(hidden, *args, **kwargs)
             ops.count_launch(fwd_kernels + bwd_kernels)
-            return _slots[_CURRENT_SLOT % len(_slots)](hidden)
+            return _slots[_CURRENT_SLOT % len(_slots)](hidden, *spec.graph_inputs(args))
 
         block.forward = forward
     return True
@@ -142,9 +208,22 @@ def enable_for_model(model: nn.Module, example_batch: dict) -> bool:
     from libai_b200.utils import distributed as dutil
 
     topo = dutil.get_dist_util()
-    if getattr(model, "zero_hooks", None) is not None:
-        logger.warning("cuda graphs: ZeRO stage 2/3 (per-block gradient / parameter buckets come and go) — not captured")
+    zero_hooks = getattr(model, "zero_hooks", None)
+    if zero_hooks is not None and not getattr(zero_hooks, "graph_capturable", False):
+        logger.warning("cuda graphs: ZeRO stage 3 (the blocks' parameter storage comes and goes) — not captured")
         return False
+    if zero_hooks is not None:
+        # stage 2: the blocks' gradient buckets live in pooled buffers at fixed addresses; bind them for the capture
+        # (the hooks that open / reduce them sit outside the blocks, in forward_stage)
+        zero_hooks.open_all()
+        try:
+            return _enable_for_model(model, example_batch, topo)
+        finally:
+            zero_hooks.close_all()
+    return _enable_for_model(model, example_batch, topo)
+
+
+def _enable_for_model(model: nn.Module, example_batch: dict, topo) -> bool:
     if (getattr(model, "activation_checkpoint", False)
             or (topo.tensor_parallel_size > 1 and not topo.fused_tp_comm)):
         # (checkpointing re-runs the forward inside backward; tensor parallelism is captured only in its fused form —
@@ -161,7 +240,7 @@ def enable_for_model(model: nn.Module, example_batch: dict) -> bool:
 
     def grab(mod, args, kwargs):
         shapes["hidden"] = args[0]
-        shapes["n_args"] = len(args) + len([v for v in kwargs.values() if v is not None])
+        shapes["args"], shapes["kwargs"] = tuple(args[1:]), dict(kwargs)
 
     h = layers[0].register_forward_pre_hook(grab, with_kwargs=True)
     was_training = model.training
@@ -169,11 +248,16 @@ def enable_for_model(model: nn.Module, example_batch: dict) -> bool:
     with torch.no_grad():
         model(**example_batch)
     h.remove()
-    if shapes.get("n_args", 0) != 1 or not torch.is_tensor(shapes.get("hidden")):
-        logger.warning("cuda graphs: blocks take more than the hidden state — not captured")
+    spec = classify_block_call(model, shapes.get("args", ()), shapes.get("kwargs", {})) if torch.is_tensor(shapes.get("hidden")) else None
+    if spec is None:
+        logger.warning("cuda graphs: blocks take arguments that are neither model buffers nor a right-padded key mask — not captured")
         return False
     try:
-        new = graph_transformer_blocks(list(layers), shapes["hidden"])
+        if spec.trivial:
+            new = graph_transformer_blocks(list(layers), shapes["hidden"])
+        else:
+            # extra inputs: function-style capture (parameters are constants of the graph, their gradients go to main_grad)
+            new = list(layers) if graph_blocks_multi_slot(list(layers), shapes["hidden"], 1, spec=spec) else None
     except Exception as e:   # capture is an optimisation: never take the run down with it
         logger.warning("cuda graphs: capture failed (%s: %s) — staying with eager launches", type(e).__name__, str(e)[:200])
         try:

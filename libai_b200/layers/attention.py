@@ -47,6 +47,17 @@ class KeyPaddingMask:
         self._dense = None
         self._prefix = None
 
+    @classmethod
+    def from_lengths(cls, lengths: torch.Tensor) -> "KeyPaddingMask":
+        """Right-padded mask given directly by its key lengths (int32 ``[b]``) — no host synchronisation, usable while a
+        CUDA graph is being captured (engine/cuda_graphs.py)."""
+        self = cls.__new__(cls)
+        self.mask_2d = None
+        self.lengths = lengths
+        self._dense = None
+        self._prefix = True
+        return self
+
     def is_prefix(self) -> bool:
         """True when every row is a right-padded contiguous prefix (``1…10…0``) — the only shape ``lengths`` can
         express.  Left padding / holes must take the dense ``m_i·m_j`` path.  Checked once per mask (one small sync)."""

@@ -155,7 +155,7 @@ class FlatOptimizer(torch.optim.Optimizer):
                         b.state[name] = torch.zeros(b.per, dtype=torch.float32, device=b.device)
                     self._groups.append(b)
                     self._hp_index.append(gi)
-            self._bucket_hooks = ZeroBucketHooks(by_layer, self.dp_grad_reduce) if by_layer else None
+            self._bucket_hooks = ZeroBucketHooks(by_layer, self.dp_grad_reduce, self.zero_stage) if by_layer else None
             if not by_layer:
                 import logging
 
@@ -316,6 +316,8 @@ class FlatOptimizer(torch.optim.Optimizer):
             return
         self._collect_autograd_grads()
         topo = dutil.get_dist_util()
+        if self.bucket_hooks is not None:
+            self.bucket_hooks.flush()           # the last block's reduce-scatter may still be in flight
         for fg in self._groups:
             if fg is None:
                 continue

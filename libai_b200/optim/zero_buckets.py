@@ -7,10 +7,14 @@ Here it is explicit and bucketed **per transformer block**:
 * every block's parameters form one *bucket* (padded to a multiple of the DP size); rank ``r`` owns slice ``r`` of every
   bucket: fp32 master weights, optimizer moments, the reduced-gradient shard and (stage 3) the low-precision parameter
   shard are the only per-bucket tensors that live for the whole run — ``1/dp`` of the bucket each;
-* **stage 2**: the full fp32 gradient buffer of a block exists only while that block's backward runs: it is allocated
-  (zeroed) when the gradient reaches the block's output, reduce-scattered into the owners' shards as soon as the
-  block's backward has been issued, and freed.  Full low-precision parameters stay resident (all-gathered after the
-  optimizer step, like stage 1);
+* **stage 2**: the full fp32 gradient buffer of a block is live only while that block's backward runs: it is opened
+  (zeroed) when the gradient reaches the block's output and reduce-scattered into the owners' shards as soon as the
+  block's backward has been issued.  The storage comes from a **pool of two buffers per bucket shape** (even / odd
+  blocks): a block's gradients therefore always land at the same addresses — which is what lets the blocks' backward
+  be replayed from CUDA graphs (engine/cuda_graphs.py) — and the reduce-scatter of block ``i`` (asynchronous, on NCCL's
+  stream) overlaps the backward of block ``i-1``, which writes into the other buffer.  Gradient memory is two block
+  buckets instead of the whole model.  Full low-precision parameters stay resident (all-gathered after the optimizer
+  step, like stage 1);
 * **stage 3**: additionally the full parameters of a block exist only around its forward and its backward: all-gathered
   from the shards right before, dropped right after (the autograd nodes keep the ``Parameter`` objects, whose storage is
   simply re-pointed, so nothing stale is ever read);
@@ -19,8 +23,9 @@ Here it is explicit and bucketed **per transformer block**:
   reduce-scattered at the end of the backward pass.
 
 The collectives are ``torch.distributed`` reduce-scatter / all-gather on the DP group (NCCL on GPUs, gloo on CPU), issued
-from autograd hooks in ``PipelineStageMixin.forward_stage``; CUDA-graph capture of the blocks is switched off for these
-stages (the bucket buffers come and go).  Stage 1 keeps its fused NVLink kernels (``optimizers.py``).
+from autograd hooks in ``PipelineStageMixin.forward_stage`` — outside the blocks, so stage 2 keeps the CUDA-graph replay
+of the blocks; stage 3 does not (the parameter storage comes and goes).  Stage 1 keeps its fused NVLink kernels
+(``optimizers.py``).
 """
 from __future__ import annotations
 
@@ -40,8 +45,10 @@ class Bucket:
     sharded = True
     symm = None
 
-    def __init__(self, params: List[torch.nn.Parameter], dp_size: int, dp_rank: int, stage: int, persistent: bool, key):
+    def __init__(self, params: List[torch.nn.Parameter], dp_size: int, dp_rank: int, stage: int, persistent: bool, key,
+                 grad_pool: Optional[Dict] = None, parity: int = 0):
         self.params, self.key, self.stage, self.persistent = params, key, stage, persistent
+        self.pool_buf = None
         self.dtype, self.device = params[0].dtype, params[0].device
         assert all(p.dtype == self.dtype for p in params), "mixed dtypes inside one bucket"
         self.offsets, n = [], 0
@@ -68,6 +75,13 @@ class Bucket:
         self.grad_flat: Optional[torch.Tensor] = None
         self.params_resident = stage < 3 or persistent
         self.grads_resident = persistent
+        if not persistent and grad_pool is not None:
+            # pooled gradient storage: buckets of this shape in even (odd) blocks share one buffer — every block's
+            # gradients always land at the same addresses
+            k = (self.numel, parity, str(self.device))
+            if k not in grad_pool:
+                grad_pool[k] = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+            self.pool_buf = grad_pool[k]
         if self.params_resident:
             self._bind_params(full)
         else:
@@ -97,7 +111,11 @@ class Bucket:
             self._rebind(p, i, torch.empty(1, dtype=self.dtype, device=self.device).expand(p.shape))
 
     def _bind_grads(self):
-        self.grad_flat = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        if self.pool_buf is None:
+            self.grad_flat = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        else:
+            self.pool_buf.zero_()
+            self.grad_flat = self.pool_buf
         for p, off in zip(self.params, self.offsets):
             p.main_grad = self.grad_flat[off : off + p.numel()].view(p.shape)
             p.grad_added_to_main_grad = False
@@ -145,8 +163,10 @@ class Bucket:
         if self.grad_flat is None:
             self._bind_grads()
 
-    def reduce_grads(self, topo, scale: float):
-        """Fold autograd gradients, apply the tensor-parallel fix-ups, reduce-scatter over DP into ``red``."""
+    def reduce_grads(self, topo, scale: float, pending: Optional[list] = None):
+        """Fold autograd gradients, apply the tensor-parallel fix-ups, reduce-scatter over DP into ``red``.  With
+        ``pending`` (a list) the reduce-scatter is left in flight on NCCL's stream: ``(work, bucket, part)`` is appended
+        and ``finish_reduce`` must be called before the bucket's pool buffer is opened again."""
         if self.grad_flat is None:
             return
         for p in self.params:
@@ -167,15 +187,28 @@ class Bucket:
         if scale != 1.0:
             self.grad_flat.mul_(scale)
         part = torch.empty(self.per, dtype=torch.float32, device=self.device)
-        _reduce_scatter(part, self.grad_flat, topo.dp_group, topo.dp_rank)
-        self.red.add_(part)
+        if pending is not None and self.grad_flat.is_cuda and not self.grads_resident:
+            work = dist.reduce_scatter_tensor(part, self.grad_flat, group=topo.dp_group, async_op=True)
+            pending.append((work, self, part))
+        else:
+            _reduce_scatter(part, self.grad_flat, topo.dp_group, topo.dp_rank)
+            self.red.add_(part)
         if self.grads_resident:
             self.grad_flat.zero_()
         else:
+            # closed: eager kernels fall back to autograd's ``p.grad`` until the bucket is opened again (captured
+            # kernels keep the pool address they were recorded with)
             self.grad_flat = None
             for p in self.params:
                 p.main_grad = None
                 p.grad_added_to_main_grad = False
+
+    @staticmethod
+    def finish_reduce(pending: list):
+        while pending:
+            work, bucket, part = pending.pop(0)
+            work.wait()                      # stream-level wait: the current stream continues after the collective
+            bucket.red.add_(part)
 
 
 def _all_gather(full: torch.Tensor, shard: torch.Tensor, group):
@@ -233,10 +266,37 @@ class _After(torch.autograd.Function):
 class ZeroBucketHooks:
     """What ``forward_stage`` calls around every block (``wrap``), see ``_Before`` / ``_After``."""
 
-    def __init__(self, by_layer: Dict[int, List[Bucket]], dp_grad_reduce: str):
+    def __init__(self, by_layer: Dict[int, List[Bucket]], dp_grad_reduce: str, stage: int = 2):
         self.by_layer = by_layer
         self.scale = 1.0
         self.dp_grad_reduce = dp_grad_reduce
+        self.stage = stage
+        self._pending: list = []       # reduce-scatters in flight (at most one block's)
+
+    @property
+    def graph_capturable(self) -> bool:
+        """Stage 2: parameters resident, pooled gradient buffers at fixed addresses → the blocks can be replayed from
+        CUDA graphs.  Stage 3 re-points the parameter storage around every block."""
+        return self.stage == 2
+
+    def open_all(self):
+        """Bind every block's gradient views (capture / warm-up runs the blocks' backward outside ``forward_stage``)."""
+        for buckets in self.by_layer.values():
+            for b in buckets:
+                b.open_grads()
+
+    def close_all(self):
+        for buckets in self.by_layer.values():
+            for b in buckets:
+                if not b.grads_resident and b.grad_flat is not None:
+                    b.grad_flat = None
+                    for p in b.params:
+                        p.main_grad = None
+                        p.grad_added_to_main_grad = False
+
+    def flush(self):
+        """Wait for the reduce-scatter still in flight (end of the backward pass)."""
+        Bucket.finish_reduce(self._pending)
 
     def _topo(self):
         return dutil.get_dist_util()
@@ -273,8 +333,11 @@ class ZeroBucketHooks:
     def post_backward(self, idx):
         topo = self._topo()
         scale = 1.0 / topo.data_parallel_size if self.dp_grad_reduce == "mean" else 1.0
+        # the previous block's reduce-scatter ran under this block's backward; it must be done before ITS pool buffer is
+        # opened again (two blocks further down) — finishing it here keeps at most one in flight
+        self.flush()
         for b in self.by_layer[idx]:
-            b.reduce_grads(topo, scale)
+            b.reduce_grads(topo, scale, pending=self._pending)
             b.release_params()
 
 
@@ -292,14 +355,17 @@ def build_buckets(param_groups, model, dp_size: int, dp_rank: int, stage: int):
         for p in layer.parameters():
             layer_of.setdefault(id(p), idx)
     per_group, by_layer = [], {}
-    for g in param_groups:
+    order = {idx: k for k, idx in enumerate(sorted({v for v in layer_of.values()}))}
+    for gi, g in enumerate(param_groups):
+        pool: Dict = {}
         params = [p for p in g["params"] if p.device.type != "meta" and p.requires_grad]
         split: Dict[object, List] = {}
         for p in params:
             split.setdefault(layer_of.get(id(p), "rest"), []).append(p)
         buckets = []
         for key in sorted(split, key=lambda k: (isinstance(k, str), k)):
-            b = Bucket(split[key], dp_size, dp_rank, stage, persistent=(key == "rest"), key=key)
+            b = Bucket(split[key], dp_size, dp_rank, stage, persistent=(key == "rest"), key=key,
+                       grad_pool=pool, parity=order.get(key, 0) % 2)
             buckets.append(b)
             if key != "rest":
                 by_layer.setdefault(key, []).append(b)

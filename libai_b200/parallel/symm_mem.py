@@ -42,6 +42,23 @@ class SymmetricBuffer:
                 self.ptrs.append(int(ext.symm_open(ht)))
         dist.barrier(group=group)
 
+    def close(self) -> None:
+        """Unmap the peers' allocations and free the local one.  Collective over ``group``: nobody frees memory a
+        peer may still have mapped (a later ``cudaMalloc`` can hand the same range out again, and re-opening its IPC
+        handle while the stale mapping exists fails with "resource already mapped")."""
+        if self.local is None:
+            return
+        ext = load_ext()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)           # every rank's kernels on these buffers have retired
+            for r, p in enumerate(self.ptrs):
+                if r != self.rank:
+                    ext.symm_close(int(p))
+            dist.barrier(group=self.group)           # every mapping is gone before any owner frees
+        self.ptrs = []
+        self.local = None
+
     def view(self, dtype: torch.dtype, shape, offset_bytes: int = 0) -> torch.Tensor:
         """Typed view of the *local* buffer."""
         n = 1
@@ -88,6 +105,14 @@ class CommWorkspace:
             self._bufs[key] = SymmetricBuffer(nbytes, self.group, str(key))
         return self._bufs[key]
 
+    def close(self) -> None:
+        """Release every buffer of this workspace (collective; same order on every rank of the group)."""
+        for key in list(self._bufs):
+            buf = self._bufs.pop(key)
+            if isinstance(buf, SymmetricBuffer):
+                buf.close()
+        self.flags.close()
+
 
 _WORKSPACES: Dict[int, CommWorkspace] = {}
 
@@ -97,3 +122,10 @@ def get_workspace(group) -> CommWorkspace:
     if key not in _WORKSPACES:
         _WORKSPACES[key] = CommWorkspace(group)
     return _WORKSPACES[key]
+
+
+def release_workspaces() -> None:
+    """Tear down every workspace (before the process groups they belong to are destroyed or re-made).  Must be called
+    by all ranks at the same point; objects still holding views of the buffers must be dropped first."""
+    for key in list(_WORKSPACES):
+        _WORKSPACES.pop(key).close()

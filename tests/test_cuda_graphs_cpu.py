@@ -37,3 +37,30 @@ def test_launch_count_wrapper_keeps_module_identity():
     with torch.no_grad():
         blk(torch.randn(2, 8))
     assert ops.launch_count() - n0 == 11
+
+
+def test_block_call_spec_classification():
+    """Blocks may take model buffers (RoPE tables) and a right-padded key mask besides the hidden state."""
+    from libai_b200.layers.attention import KeyPaddingMask
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.register_buffer("cos", torch.ones(4, 2), persistent=False)
+
+    m = M()
+    spec = cuda_graphs.classify_block_call(m, (), {"cos_cached": m.cos, "past": None})
+    assert spec is not None and not spec.trivial and spec.key_lengths is None
+    assert spec.matches((), {"cos_cached": m.cos}) and not spec.matches((), {"cos_cached": m.cos.clone()})
+    assert cuda_graphs.classify_block_call(m, (), {"x": torch.ones(2)}) is None          # not a buffer: varies per call
+    assert cuda_graphs.classify_block_call(m, (None,), {}).trivial
+
+    right = KeyPaddingMask(torch.tensor([[1, 1, 0], [1, 0, 0]]))
+    holes = KeyPaddingMask(torch.tensor([[1, 0, 1], [1, 0, 0]]))
+    spec = cuda_graphs.classify_block_call(m, (right,), {})
+    assert spec is not None and spec.key_lengths.tolist() == [2, 1]
+    assert spec.matches((right,), {}) and not spec.matches((holes,), {}) and not spec.matches((), {})
+    assert spec.graph_inputs((right,))[0] is right.lengths
+    assert cuda_graphs.classify_block_call(m, (holes,), {}) is None
+    again = KeyPaddingMask.from_lengths(right.lengths)
+    assert again.is_prefix() and again.lengths is right.lengths

@@ -11,12 +11,12 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(REPO, "tools"))
 
 TINY = [
-    "model.cfg.hidden_layers=4", "model.cfg.hidden_size=64", "model.cfg.ffn_hidden_size=128",
+    "model.cfg.hidden_layers=8", "model.cfg.hidden_size=64", "model.cfg.ffn_hidden_size=128",
     "model.cfg.num_attention_heads=4", "model.cfg.vocab_size=128", "model.cfg.max_seq_length=16",
     "dataloader.train.dataset.0.vocab_size=128", "dataloader.train.dataset.0.seq_length=16",
     "dataloader.train.dataset.0.num_samples=256", "dataloader.train.num_workers=0",
     "train.train_micro_batch_size=4", "train.log_period=1", "train.amp.enabled=false", "train.warmup_ratio=0.0",
-    "train.dist.pipeline_num_layers=4", "train.dist.data_parallel_size=2", "train.evaluation.enabled=false",
+    "train.dist.pipeline_num_layers=8", "train.dist.data_parallel_size=2", "train.evaluation.enabled=false",
     "optim.lr=1e-2", "train.train_iter=6", "train.checkpointer.period=3",
 ]
 
@@ -37,7 +37,7 @@ def _worker(rank, world, out_dir, stage, acc, resume):
         for fg in opt._groups:
             if fg is None:
                 continue
-            tensors = [getattr(fg, name, None) for name in ("param_flat", "grad_flat", "master", "red", "param_shard")]
+            tensors = [getattr(fg, name, None) for name in ("param_flat", "grad_flat", "pool_buf", "master", "red", "param_shard")]
             tensors += list(fg.state.values())
             for t in tensors:
                 if torch.is_tensor(t):
