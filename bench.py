@@ -491,6 +491,10 @@ def measure_pytorch_baseline(args, world, rank, local_rank, steps, warmup):
     return out
 
 
+def _extras_flag_path():
+    return os.path.join("/tmp", f"libai_b200_bench_fail_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}")
+
+
 class _ExtrasWatchdog:
     """Keeps the headline line safe while the extra layouts run.  One node, so a flag file is the signal: the rank
     that fails (or sees a layout exceed ``limit_s``) creates it; a polling thread on every rank notices, rank 0 prints
@@ -501,10 +505,8 @@ class _ExtrasWatchdog:
         import threading
 
         self.world, self.emit, self.layouts, self.limit_s = world, emit, layouts, limit_s
-        self.flag = os.path.join("/tmp", f"libai_b200_bench_fail_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}")
+        self.flag = _extras_flag_path()     # (a stale file of an earlier launch was removed in main(), before the rendezvous)
         self.current, self.t0, self._stop = None, 0.0, False
-        if int(os.environ.get("LOCAL_RANK", "0")) == 0 and os.path.exists(self.flag):
-            os.remove(self.flag)
         self.thread = None
         if world > 1:
             self.thread = threading.Thread(target=self._poll, daemon=True)
@@ -567,6 +569,8 @@ def main():
     torch.cuda.set_device(local_rank)
     from libai_b200.utils import distributed as _dutil
 
+    if local_rank == 0 and os.path.exists(_extras_flag_path()):
+        os.remove(_extras_flag_path())       # before the rendezvous: no rank can have raised it yet in this launch
     _dutil.init_process_group("cuda")        # torchrun environment → NCCL (+ gloo for host objects)
 
     primary = layout_of(args, world)

@@ -1176,6 +1176,383 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
+// =================================================================================================
+// Backward, pipelined variant (D = 64).  Same maths and the same tiles as attn_bwd_kernel; what changes is who waits
+// for whom.  ncu of the kernel above (profiles/r17_ncu_summary.md): tensor pipe 17 %, issue slots 18 % — the chain
+// S,dP → softmax → dV,dK,dQ → dQ drain → next S,dP ran strictly in sequence.  Here
+//   * 16 softmax warps (4 per TMEM lane quadrant, 32 key columns each): a thread holds its whole share of S and dP in
+//     64 registers, so the S/dP columns are handed back to the MMA warp right after the two tcgen05.ld — the tensor core
+//     computes S,dP of query block i+1 while the softmax of block i is still running;
+//   * dQ is double-buffered in TMEM (S 128 + dP 128 + dV 64 + dK 64 + 2 x dQ 64 = 512 columns) and drained one
+//     iteration late, after the P/dS tiles of the next block have been handed over: neither side waits for the drain;
+//   * P/dS are packed in registers and written to shared memory at the end of the softmax, when the dV/dK/dQ MMAs of
+//     the previous block (which read those tiles) have long retired;
+//   * one mbarrier arrival per warp instead of one per thread; lse/δ of the next block are fetched a block ahead.
+// =================================================================================================
+constexpr int ATT_BWDP_CWARPS = 16;
+constexpr int ATT_BWDP_QST = 3;
+constexpr int ATT_BWDP_SMEM = AttnBwdCfg<64>::SMEM_BYTES + 2 * (ATT_BWDP_QST - AttnBwdCfg<64>::QST) * AttnBwdCfg<64>::TILE_BYTES;
+static_assert(ATT_BWDP_SMEM <= 232448, "pipelined attention backward: shared memory");
+// REGS: rebalance the register file with setmaxnreg.  18 warps leave 5 warps on some SM sub-partitions, i.e. 96 registers
+// per thread — the softmax threads (64 registers of S/dP alone) then spill.  With REGS the CTA is 5 aligned warpgroups:
+// one control group (TMA warp, MMA warp, two idle warps) that shrinks to 64 registers and four softmax groups that grow
+// to 112 (per sub-partition: 5 x 32 x 96 at launch = 15360 of 16384; 64 + 4 x 112 per lane = 16384 afterwards).
+template <bool REGS>
+constexpr int att_bwdp_threads() { return (REGS ? 128 : 64) + ATT_BWDP_CWARPS * 32; }
+
+template <int BIAS, bool DROP, bool REGS>
+__global__ void __launch_bounds__(att_bwdp_threads<REGS>(), 1)
+attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                     const __grid_constant__ CUtensorMap tmap_dq, AttnBwdParams p) {
+  constexpr int D = 64;
+  using Cfg = AttnBwdCfg<D>;
+  // three Q/dO stages: S,dP of block i+1 are issued while block i's softmax runs, i.e. before the dV/dK/dQ MMAs of
+  // block i-1 (the last readers of a two-stage ring's slot) have even been issued
+  constexpr int QST = ATT_BWDP_QST;
+  static_assert(Cfg::DQ_BULK, "pipelined backward: D = 64 configuration");
+  constexpr uint32_t DQ_COL0 = 384;   // two dQ accumulators: columns [384, 448) and [448, 512)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + Cfg::TILE_BYTES;
+  uint8_t* sQ = sV + Cfg::TILE_BYTES;
+  uint8_t* sDO = sQ + QST * Cfg::TILE_BYTES;
+  uint8_t* sP = sDO + QST * Cfg::TILE_BYTES;
+  uint8_t* sDS = sP + Cfg::PS_BYTES;
+  uint8_t* sDQ = sDS + Cfg::PS_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + Cfg::PS_BYTES + Cfg::DQ_STAGE_BYTES);
+  uint64_t* kv_full = bars;          // 1
+  uint64_t* qdo_full = bars + 1;     // 3
+  uint64_t* qdo_empty = bars + 4;    // 3
+  uint64_t* sdp_full = bars + 7;     // 1
+  uint64_t* sdp_free = bars + 8;     // 1  (S/dP are in the softmax warps' registers)
+  uint64_t* pds_full = bars + 9;     // 1
+  uint64_t* pds_empty = bars + 10;   // 1
+  uint64_t* dq_full = bars + 11;     // 2
+  uint64_t* dq_empty = bars + 13;    // 2
+  uint64_t* acc_full = bars + 15;    // 1
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp_idx = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int kv_blk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+  const int k0 = kv_blk * 128;
+  const int kv_len = p.kv_lens != nullptr ? max(1, min(p.S, p.kv_lens[batch])) : p.S;
+  const int nq = (p.S + 127) / 128;
+  const int i_begin = p.causal ? kv_blk : 0;
+  const int iters = nq - i_begin;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_dq);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < QST; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&dq_full[i], 1);
+      mbar_init(&dq_empty[i], ATT_BWDP_CWARPS / 2);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_free, ATT_BWDP_CWARPS);
+    mbar_init(pds_full, ATT_BWDP_CWARPS);
+    mbar_init(pds_empty, 1);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr int CW0 = REGS ? 4 : 2;    // first softmax warp
+  if constexpr (REGS) {
+    if (warp_idx < CW0) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
+  }
+
+  if (warp_idx == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
+      tma_load_4d(sK, &tmap_k, kv_full, 0, k0, head, batch);
+      tma_load_4d(sV, &tmap_v, kv_full, 0, k0, head, batch);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % QST;
+        const int q0 = (i_begin + it) * 128;
+        mbar_wait(&qdo_empty[st], ((it / QST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qdo_full[st], 2 * Cfg::TILE_BYTES);
+        tma_load_4d(sQ + st * Cfg::TILE_BYTES, &tmap_q, &qdo_full[st], 0, q0, head, batch);
+        tma_load_4d(sDO + st * Cfg::TILE_BYTES, &tmap_do, &qdo_full[st], 0, q0, head, batch);
+      }
+    }
+  } else if (warp_idx == 1) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);   // Q·Kᵀ, dO·Vᵀ
+    constexpr uint32_t idesc_t = make_idesc_bf16(128, D, true, true);       // Pᵀ·dO, dSᵀ·Q
+    constexpr uint32_t idesc_q = make_idesc_bf16(128, D, false, true);      // dS·K
+    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+    mbar_wait(kv_full, 0);
+    auto issue_s_dp = [&](int it) {
+      const int st = it % QST;
+      mbar_wait(&qdo_full[st], (it / QST) & 1);
+      tc_fence_after_sync();
+      const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
+      const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16_ss(tmem_base + Cfg::S_COL, make_smem_desc_sw128(q_addr + kk * 32, 0, 1024),
+                      make_smem_desc_sw128(k_addr + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16_ss(tmem_base + Cfg::DP_COL, make_smem_desc_sw128(do_addr + kk * 32, 0, 1024),
+                      make_smem_desc_sw128(v_addr + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+      }
+      __syncwarp();
+    };
+    issue_s_dp(0);
+    for (int it = 0; it < iters; ++it) {
+      const int st = it % QST;
+      const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
+      const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
+      if (it + 1 < iters) {
+        mbar_wait(sdp_free, it & 1);     // S/dP of block `it` sit in registers: the columns are free
+        issue_s_dp(it + 1);              // ... and the tensor core works on the next block under this block's softmax
+      }
+      mbar_wait(pds_full, it & 1);       // P / dS tiles of block `it` written
+      if (it >= 2) mbar_wait(&dq_empty[it & 1], ((it >> 1) & 1) ^ 1);   // dQ accumulator (it & 1): block it-2 drained
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t dq_col = DQ_COL0 + static_cast<uint32_t>(it & 1) * 64u;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {   // dQ first: its drain is the only consumer that is waited for
+          const uint64_t a_ds = make_smem_desc_sw128(ds_addr + (kk / 4) * (128 * 128) + (kk % 4) * 32, 0, 1024);  // dS (K-major A)
+          const uint64_t b_k = make_smem_desc_sw128(k_addr + kk * 2048, 128 * 128, 1024);                          // K  (MN-major B)
+          umma_f16_ss(tmem_base + dq_col, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&dq_full[it & 1]);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t a_pt = make_smem_desc_sw128(p_addr + kk * 2048, 128 * 128, 1024);       // Pᵀ  (MN-major A)
+          const uint64_t b_do = make_smem_desc_sw128(do_addr + kk * 2048, 128 * 128, 1024);      // dO  (MN-major B)
+          umma_f16_ss(tmem_base + Cfg::DV_COL, a_pt, b_do, idesc_t, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t a_dst = make_smem_desc_sw128(ds_addr + kk * 2048, 128 * 128, 1024);     // dSᵀ (MN-major A)
+          const uint64_t b_q = make_smem_desc_sw128(q_addr + kk * 2048, 128 * 128, 1024);        // Q   (MN-major B)
+          umma_f16_ss(tmem_base + Cfg::DK_COL, a_dst, b_q, idesc_t, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&qdo_empty[st]);
+        umma_commit(pds_empty);
+        if (it == iters - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else if (warp_idx >= CW0) {
+    const int quad = warp_idx % 4;            // TMEM lane quadrant this warp may access
+    const int quarter = (warp_idx - CW0) / 4; // 32-column slice of S / dP handled by this warp
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const size_t bh = static_cast<size_t>(batch) * p.A + head;
+    constexpr float LOG2E = 1.4426950408889634f;
+    unsigned long long rng_seed = 0, rng_offset = 0;
+    if constexpr (DROP) {
+      rng_seed = static_cast<unsigned long long>(p.rng_state[0]);
+      rng_offset = static_cast<unsigned long long>(p.rng_state[1]);
+    }
+    float slope2 = 0.f;
+    if constexpr (BIAS == BIAS_ALIBI) slope2 = p.alibi_slopes[head] * LOG2E;
+    const float inv_scale = 1.0f / p.scale;
+    const int c = quarter;
+    uint8_t* prow = sP + r * 128;
+    uint8_t* dsrow = sDS + r * 128;
+    const int half_off = (c / 2) * (128 * 128);
+
+    // dQ of query block `j`: TMEM -> swizzled [32 x 128 B] boxes -> one TMA tensor reduce-add per box (fp32 dq_accum)
+    auto drain_dq = [&](int j) {
+      if (quarter >= 2) return;
+      const int b = j & 1;
+      mbar_wait(&dq_full[b], (j >> 1) & 1);
+      tc_fence_after_sync();
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // this warp's box was consumed
+      __syncwarp();
+      uint8_t* wbox = sDQ + (quad * (D / 32) + quarter) * Cfg::DQ_BOX_BYTES;
+      uint32_t t[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + DQ_COL0 + b * 64 + quarter * 32, t);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      uint8_t* brow = wbox + lane * 128;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<float4*>(brow + ((k ^ (lane & 7)) * 16)) =
+            make_float4(__uint_as_float(t[k * 4]), __uint_as_float(t[k * 4 + 1]), __uint_as_float(t[k * 4 + 2]),
+                        __uint_as_float(t[k * 4 + 3]));
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&dq_empty[b]);      // the accumulator is in shared memory now
+        asm volatile(
+            "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];\n" ::"l"(
+                reinterpret_cast<uint64_t>(&tmap_dq)),
+            "r"(quarter * 32), "r"((i_begin + j) * 128 + quad * 32), "r"(static_cast<int>(bh)), "r"(smem_u32(wbox))
+            : "memory");
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      }
+    };
+
+    auto row_stats = [&](int it, float& lse2, float& delta_s) {
+      const int q_idx = (i_begin + it) * 128 + r;
+      const bool ok = it < iters && q_idx < p.S;
+      lse2 = ok ? p.lse[bh * p.S + q_idx] * LOG2E : 0.f;
+      delta_s = ok ? p.delta[bh * p.S + q_idx] * p.scale : 0.f;
+    };
+    float lse2, delta_s;
+    row_stats(0, lse2, delta_s);
+
+    for (int it = 0; it < iters; ++it) {
+      const int q_blk = i_begin + it;
+      const int q_idx = q_blk * 128 + r;
+      const bool q_ok = q_idx < p.S;
+      const long bias_off = batch * p.bias_strides[0] + head * p.bias_strides[1] +
+                            static_cast<long>(min(q_idx, p.S - 1)) * p.bias_strides[2];
+      const bool need_mask = (p.causal && q_blk == kv_blk) || (k0 + 128 > kv_len) || (q_blk * 128 + 128 > p.S);
+      uint4 bq[4];
+      if constexpr (BIAS == BIAS_DENSE) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int kb = k0 + c * 32 + v * 8;
+          bq[v] = kb < p.S ? *reinterpret_cast<const uint4*>(p.bias + bias_off + kb) : make_uint4(0, 0, 0, 0);
+        }
+      }
+      uint4 rnd[2];
+      if constexpr (DROP) {
+        rnd[0] = attn_dropout_bytes(static_cast<uint32_t>(q_idx), static_cast<uint32_t>((k0 + c * 32) >> 4), static_cast<uint32_t>(bh), rng_seed, rng_offset);
+        rnd[1] = attn_dropout_bytes(static_cast<uint32_t>(q_idx), static_cast<uint32_t>((k0 + c * 32) >> 4) + 1u, static_cast<uint32_t>(bh), rng_seed, rng_offset);
+      }
+      uint32_t ts[32], td[32];
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after_sync();
+      tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::S_COL + c * 32, ts);
+      tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DP_COL + c * 32, td);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_free);
+      const float lse2_cur = lse2, delta_cur = delta_s;
+      row_stats(it + 1, lse2, delta_s);          // next block's row statistics: in flight during this block's softmax
+
+      uint32_t pp[16], dd[16];
+      auto pds = [&](auto mask_tag) {
+        constexpr bool MASK = decltype(mask_tag)::value;
+        float dsv[32];   // only materialised for the dbias path
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0, p1;
+          if constexpr (BIAS == BIAS_DENSE) {
+            const float2 bf = unpack_bf16((&bq[i >> 3].x)[(i & 7) >> 1]);
+            p0 = fast_exp2(fmaf(__uint_as_float(ts[i]), p.scale_log2, bf.x * LOG2E) - lse2_cur);
+            p1 = fast_exp2(fmaf(__uint_as_float(ts[i + 1]), p.scale_log2, bf.y * LOG2E) - lse2_cur);
+          } else if constexpr (BIAS == BIAS_ALIBI) {
+            const int kidx = k0 + c * 32 + i;
+            p0 = fast_exp2(fmaf(__uint_as_float(ts[i]), p.scale_log2, slope2 * static_cast<float>(kidx - q_idx)) - lse2_cur);
+            p1 = fast_exp2(fmaf(__uint_as_float(ts[i + 1]), p.scale_log2, slope2 * static_cast<float>(kidx + 1 - q_idx)) - lse2_cur);
+          } else {
+            p0 = fast_exp2(fmaf(__uint_as_float(ts[i]), p.scale_log2, -lse2_cur));
+            p1 = fast_exp2(fmaf(__uint_as_float(ts[i + 1]), p.scale_log2, -lse2_cur));
+          }
+          if constexpr (MASK) {
+            const int kidx = k0 + c * 32 + i;
+            if (!q_ok || kidx >= kv_len || (p.causal && kidx > q_idx)) p0 = 0.f;
+            if (!q_ok || kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) p1 = 0.f;
+          }
+          float g0 = __uint_as_float(td[i]), g1 = __uint_as_float(td[i + 1]);   // dP w.r.t. the dropped, rescaled P
+          float pd0 = p0, pd1 = p1;                                               // what multiplied V in the forward
+          if constexpr (DROP) {
+            const bool keep0 = rnd_byte(rnd[i >> 4], i & 15) >= p.drop_thresh;
+            const bool keep1 = rnd_byte(rnd[i >> 4], (i & 15) + 1) >= p.drop_thresh;
+            g0 = keep0 ? g0 * p.inv_keep : 0.f;
+            g1 = keep1 ? g1 * p.inv_keep : 0.f;
+            pd0 = keep0 ? p0 * p.inv_keep : 0.f;
+            pd1 = keep1 ? p1 * p.inv_keep : 0.f;
+          }
+          const float d0 = p0 * fmaf(g0, p.scale, -delta_cur);
+          const float d1 = p1 * fmaf(g1, p.scale, -delta_cur);
+          pp[i / 2] = pack_bf16(pd0, pd1);
+          dd[i / 2] = pack_bf16(d0, d1);
+          if constexpr (BIAS == BIAS_DENSE) {
+            dsv[i] = d0 * inv_scale;
+            dsv[i + 1] = d1 * inv_scale;
+          }
+        }
+        if constexpr (BIAS == BIAS_DENSE) {
+          if (p.dbias != nullptr && q_ok) {   // d bias = P ∘ (dP − δ): fp32 reductions (broadcast dims sum over CTAs)
+            float* drow = p.dbias + bias_off + k0 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (k0 + c * 32 + i < p.S)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(drow + i), "f"(dsv[i]), "f"(dsv[i + 1]),
+                             "f"(dsv[i + 2]), "f"(dsv[i + 3])
+                             : "memory");
+            }
+          }
+        }
+      };
+      if (need_mask) pds(std::true_type{}); else pds(std::false_type{});
+      // the dV/dK/dQ MMAs of the previous block read the P/dS tiles: they were issued a whole softmax ago
+      mbar_wait(pds_empty, (it & 1) ^ 1);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int phys = ((c % 2) * 4 + q4) ^ (r & 7);
+        *reinterpret_cast<uint4*>(prow + half_off + phys * 16) = make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
+        *reinterpret_cast<uint4*>(dsrow + half_off + phys * 16) = make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      if (it > 0) drain_dq(it - 1);     // issued behind the previous block's P/dS hand-over: complete by now
+    }
+    drain_dq(iters - 1);
+    if (quarter < 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    // ---- dV / dK accumulators: thread r <-> key row r; warps of quarters 0,1 write dV, quarters 2,3 write dK
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    const int k_idx = k0 + r;
+    {
+      const int which = quarter / 2, cc = quarter % 2;
+      __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
+      __nv_bfloat16* row = base + batch * p.g_strides[0] + head * p.g_strides[1] + static_cast<long>(k_idx) * p.g_strides[2];
+      const uint32_t col = which == 0 ? Cfg::DV_COL : Cfg::DK_COL;
+      uint32_t t[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + col + cc * 32, t);
+      tmem_ld_wait();
+      if (k_idx < p.S) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          *reinterpret_cast<uint4*>(row + cc * 32 + i) = make_uint4(
+              pack_bf16(__uint_as_float(t[i]), __uint_as_float(t[i + 1])),
+              pack_bf16(__uint_as_float(t[i + 2]), __uint_as_float(t[i + 3])),
+              pack_bf16(__uint_as_float(t[i + 4]), __uint_as_float(t[i + 5])),
+              pack_bf16(__uint_as_float(t[i + 6]), __uint_as_float(t[i + 7])));
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // delta[b, a, s] = sum_d dO[b, a, s, d] * O[b, a, s, d]
 // D / 8 lanes per row, 16-byte loads; rows are visited in (b, s, a) order = memory order of the [b, s, a, d] tensors, so
 // a warp reads 32 x 16 contiguous bytes per tensor, and every thread keeps 4 rows (8 loads) in flight.
@@ -1267,11 +1644,47 @@ cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   kern<<<grid, lb::ATT_BWD_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, tdo, tdq, p);
   return cudaGetLastError();
 }
+template <int BIAS, bool DROP, bool REGS>
+cudaError_t launch_bwd_pipe_r(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                              const CUtensorMap& tdq, const lb::AttnBwdParams& p, cudaStream_t s) {
+  auto kern = lb::attn_bwd_pipe_kernel<BIAS, DROP, REGS>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lb::ATT_BWDP_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.S + 127) / 128, p.A, p.B);
+  kern<<<grid, lb::att_bwdp_threads<REGS>(), lb::ATT_BWDP_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
+  return cudaGetLastError();
+}
+// LIBAI_B200_ATTN_BWD_PIPE: 0 = sequential kernel, 1 = pipelined, 2 (default) = pipelined + setmaxnreg
+static int attn_bwd_pipe_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LIBAI_B200_ATTN_BWD_PIPE");
+    v = e == nullptr ? 2 : atoi(e);
+  }
+  return v;
+}
+template <int BIAS, bool DROP>
+cudaError_t launch_bwd_pipe_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                              const CUtensorMap& tdq, const lb::AttnBwdParams& p, cudaStream_t s) {
+  return attn_bwd_pipe_enabled() >= 2 ? launch_bwd_pipe_r<BIAS, DROP, true>(tq, tk, tv, tdo, tdq, p, s)
+                                      : launch_bwd_pipe_r<BIAS, DROP, false>(tq, tk, tv, tdo, tdq, p, s);
+}
 template <int D>
 cudaError_t launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
                        const CUtensorMap& tdq, const lb::AttnBwdParams& p, cudaStream_t s) {
   const int bias = p.bias != nullptr ? lb::BIAS_DENSE : (p.alibi_slopes != nullptr ? lb::BIAS_ALIBI : lb::BIAS_NONE);
   const bool drop = p.drop_thresh > 0;
+  if constexpr (D == 64) {
+    if (attn_bwd_pipe_enabled()) {
+      if (bias == lb::BIAS_NONE) return drop ? launch_bwd_pipe_t<lb::BIAS_NONE, true>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd_pipe_t<lb::BIAS_NONE, false>(tq, tk, tv, tdo, tdq, p, s);
+      if (bias == lb::BIAS_DENSE) return drop ? launch_bwd_pipe_t<lb::BIAS_DENSE, true>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd_pipe_t<lb::BIAS_DENSE, false>(tq, tk, tv, tdo, tdq, p, s);
+      return drop ? launch_bwd_pipe_t<lb::BIAS_ALIBI, true>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd_pipe_t<lb::BIAS_ALIBI, false>(tq, tk, tv, tdo, tdq, p, s);
+    }
+  }
   if (bias == lb::BIAS_NONE) return drop ? launch_bwd_t<D, lb::BIAS_NONE, true>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd_t<D, lb::BIAS_NONE, false>(tq, tk, tv, tdo, tdq, p, s);
   if (bias == lb::BIAS_DENSE) return drop ? launch_bwd_t<D, lb::BIAS_DENSE, true>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd_t<D, lb::BIAS_DENSE, false>(tq, tk, tv, tdo, tdq, p, s);
   return drop ? launch_bwd_t<D, lb::BIAS_ALIBI, true>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd_t<D, lb::BIAS_ALIBI, false>(tq, tk, tv, tdo, tdq, p, s);
