@@ -53,7 +53,7 @@ def main():
         torch.cuda.synchronize()
         return
     out = {"numerics": []}
-    for (B, A, S, D, causal) in [(2, 4, 256, 64, True), (2, 4, 256, 64, False), (2, 3, 200, 64, True), (1, 2, 1024, 64, True),
+    for (B, A, S, D, causal) in [] if "--speed-only" in sys.argv else [(2, 4, 256, 64, True), (2, 4, 256, 64, False), (2, 3, 200, 64, True), (1, 2, 1024, 64, True),
                                  (1, 2, 384, 128, True), (2, 2, 1024, 64, False)]:
         q, k, v = inputs(B, A, S, D)
         scale = 1.0 / math.sqrt(D)

@@ -811,6 +811,7 @@ struct AttnBwdParams {
   uint32_t drop_thresh;
   float inv_keep;
   const long long* rng_state;
+  int debug_skip_dq;    // timing experiments only (LIBAI_B200_ATTN_DEBUG_SKIP_DQ=1): do not issue the dQ reductions
 };
 
 template <int D, int BIAS, bool DROP>
@@ -1196,7 +1197,7 @@ static_assert(ATT_BWDP_SMEM <= 232448, "pipelined attention backward: shared mem
 // REGS: rebalance the register file with setmaxnreg.  18 warps leave 5 warps on some SM sub-partitions, i.e. 96 registers
 // per thread — the softmax threads (64 registers of S/dP alone) then spill.  With REGS the CTA is 5 aligned warpgroups:
 // one control group (TMA warp, MMA warp, two idle warps) that shrinks to 64 registers and four softmax groups that grow
-// to 112 (per sub-partition: 5 x 32 x 96 at launch = 15360 of 16384; 64 + 4 x 112 per lane = 16384 afterwards).
+// to 104 (per sub-partition: 5 x 32 x 96 at launch = 15360 of 16384; 64 + 4 x 112 per lane = 16384 afterwards).
 template <bool REGS>
 constexpr int att_bwdp_threads() { return (REGS ? 128 : 64) + ATT_BWDP_CWARPS * 32; }
 
@@ -1226,13 +1227,14 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* qdo_full = bars + 1;     // 3
   uint64_t* qdo_empty = bars + 4;    // 3
   uint64_t* sdp_full = bars + 7;     // 1
-  uint64_t* sdp_free = bars + 8;     // 1  (S/dP are in the softmax warps' registers)
+  uint64_t* s_free = bars + 8;       // 1  (S is in the softmax warps' registers)
+  uint64_t* dp_free = bars + 16;     // 1  (dP too)
   uint64_t* pds_full = bars + 9;     // 1
   uint64_t* pds_empty = bars + 10;   // 1
   uint64_t* dq_full = bars + 11;     // 2
   uint64_t* dq_empty = bars + 13;    // 2
   uint64_t* acc_full = bars + 15;    // 1
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp_idx = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int kv_blk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
@@ -1258,7 +1260,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_init(&dq_empty[i], ATT_BWDP_CWARPS / 2);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, ATT_BWDP_CWARPS);
+    mbar_init(s_free, ATT_BWDP_CWARPS);
+    mbar_init(dp_free, ATT_BWDP_CWARPS);
     mbar_init(pds_full, ATT_BWDP_CWARPS);
     mbar_init(pds_empty, 1);
     mbar_init(acc_full, 1);
@@ -1273,7 +1276,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   constexpr int CW0 = REGS ? 4 : 2;    // first softmax warp
   if constexpr (REGS) {
     if (warp_idx < CW0) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
   }
 
   if (warp_idx == 0) {
@@ -1297,17 +1300,24 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
     const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
     mbar_wait(kv_full, 0);
+    // S of query block `it` once the softmax warps have read S of block it-1 into registers, dP likewise
     auto issue_s_dp = [&](int it) {
       const int st = it % QST;
       mbar_wait(&qdo_full[st], (it / QST) & 1);
-      tc_fence_after_sync();
       const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
       const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
+      if (it > 0) mbar_wait(s_free, (it - 1) & 1);
+      tc_fence_after_sync();
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
           umma_f16_ss(tmem_base + Cfg::S_COL, make_smem_desc_sw128(q_addr + kk * 32, 0, 1024),
                       make_smem_desc_sw128(k_addr + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
+      }
+      __syncwarp();
+      if (it > 0) mbar_wait(dp_free, (it - 1) & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
           umma_f16_ss(tmem_base + Cfg::DP_COL, make_smem_desc_sw128(do_addr + kk * 32, 0, 1024),
@@ -1321,10 +1331,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int st = it % QST;
       const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
       const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
-      if (it + 1 < iters) {
-        mbar_wait(sdp_free, it & 1);     // S/dP of block `it` sit in registers: the columns are free
-        issue_s_dp(it + 1);              // ... and the tensor core works on the next block under this block's softmax
-      }
+      if (it + 1 < iters) issue_s_dp(it + 1);   // the tensor core works on the next block under this block's softmax
       mbar_wait(pds_full, it & 1);       // P / dS tiles of block `it` written
       if (it >= 2) mbar_wait(&dq_empty[it & 1], ((it >> 1) & 1) ^ 1);   // dQ accumulator (it & 1): block it-2 drained
       tc_fence_after_sync();
@@ -1371,9 +1378,13 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if constexpr (BIAS == BIAS_ALIBI) slope2 = p.alibi_slopes[head] * LOG2E;
     const float inv_scale = 1.0f / p.scale;
     const int c = quarter;
-    uint8_t* prow = sP + r * 128;
-    uint8_t* dsrow = sDS + r * 128;
-    const int half_off = (c / 2) * (128 * 128);
+    // shared-memory addresses as 32-bit shared-window offsets (st.shared, not generic stores)
+    const uint32_t p_row = smem_u32(sP) + static_cast<uint32_t>(r * 128 + (c / 2) * (128 * 128));
+    const uint32_t ds_row = smem_u32(sDS) + static_cast<uint32_t>(r * 128 + (c / 2) * (128 * 128));
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    auto sts128 = [](uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+    };
 
     // dQ of query block `j`: TMEM -> swizzled [32 x 128 B] boxes -> one TMA tensor reduce-add per box (fp32 dq_accum)
     auto drain_dq = [&](int j) {
@@ -1383,108 +1394,129 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tc_fence_after_sync();
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // this warp's box was consumed
       __syncwarp();
-      uint8_t* wbox = sDQ + (quad * (D / 32) + quarter) * Cfg::DQ_BOX_BYTES;
+      const uint32_t wbox = smem_u32(sDQ) + static_cast<uint32_t>((quad * (D / 32) + quarter) * Cfg::DQ_BOX_BYTES);
       uint32_t t[32];
       tmem_ld_32x32b_x32(tmem_base + lane_off + DQ_COL0 + b * 64 + quarter * 32, t);
       tmem_ld_wait();
       tc_fence_before_sync();
-      uint8_t* brow = wbox + lane * 128;
+      const uint32_t brow = wbox + static_cast<uint32_t>(lane * 128);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        *reinterpret_cast<float4*>(brow + ((k ^ (lane & 7)) * 16)) =
-            make_float4(__uint_as_float(t[k * 4]), __uint_as_float(t[k * 4 + 1]), __uint_as_float(t[k * 4 + 2]),
-                        __uint_as_float(t[k * 4 + 3]));
+      for (int k4 = 0; k4 < 8; ++k4)
+        sts128(brow + ((static_cast<uint32_t>(k4) ^ (static_cast<uint32_t>(lane) & 7u)) * 16u), t[k4 * 4], t[k4 * 4 + 1],
+               t[k4 * 4 + 2], t[k4 * 4 + 3]);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&dq_empty[b]);      // the accumulator is in shared memory now
-        asm volatile(
+        if (!p.debug_skip_dq) asm volatile(
             "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];\n" ::"l"(
                 reinterpret_cast<uint64_t>(&tmap_dq)),
-            "r"(quarter * 32), "r"((i_begin + j) * 128 + quad * 32), "r"(static_cast<int>(bh)), "r"(smem_u32(wbox))
+            "r"(quarter * 32), "r"((i_begin + j) * 128 + quad * 32), "r"(static_cast<int>(bh)), "r"(wbox)
             : "memory");
         asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
       }
     };
 
-    auto row_stats = [&](int it, float& lse2, float& delta_s) {
+    // row statistics of block `it` (raw values: they are consumed one block later, nothing may wait for the loads here)
+    auto row_stats = [&](int it, float& lse_raw, float& delta_raw) {
       const int q_idx = (i_begin + it) * 128 + r;
       const bool ok = it < iters && q_idx < p.S;
-      lse2 = ok ? p.lse[bh * p.S + q_idx] * LOG2E : 0.f;
-      delta_s = ok ? p.delta[bh * p.S + q_idx] * p.scale : 0.f;
+      lse_raw = ok ? p.lse[bh * p.S + q_idx] : 0.f;
+      delta_raw = ok ? p.delta[bh * p.S + q_idx] : 0.f;
     };
-    float lse2, delta_s;
-    row_stats(0, lse2, delta_s);
+    float lse_raw, delta_raw;
+    row_stats(0, lse_raw, delta_raw);
 
     for (int it = 0; it < iters; ++it) {
       const int q_blk = i_begin + it;
       const int q_idx = q_blk * 128 + r;
       const bool q_ok = q_idx < p.S;
-      const long bias_off = batch * p.bias_strides[0] + head * p.bias_strides[1] +
-                            static_cast<long>(min(q_idx, p.S - 1)) * p.bias_strides[2];
       const bool need_mask = (p.causal && q_blk == kv_blk) || (k0 + 128 > kv_len) || (q_blk * 128 + 128 > p.S);
-      uint4 bq[4];
+      const float lse2 = lse_raw * LOG2E, delta_s = delta_raw * p.scale;
+      row_stats(it + 1, lse_raw, delta_raw);     // next block's row statistics: in flight during this block's softmax
+      [[maybe_unused]] long bias_off = 0;
+      [[maybe_unused]] uint4 bq[4];
       if constexpr (BIAS == BIAS_DENSE) {
+        bias_off = batch * p.bias_strides[0] + head * p.bias_strides[1] + static_cast<long>(min(q_idx, p.S - 1)) * p.bias_strides[2];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const int kb = k0 + c * 32 + v * 8;
           bq[v] = kb < p.S ? *reinterpret_cast<const uint4*>(p.bias + bias_off + kb) : make_uint4(0, 0, 0, 0);
         }
       }
-      uint4 rnd[2];
+      [[maybe_unused]] uint4 rnd[2];
       if constexpr (DROP) {
         rnd[0] = attn_dropout_bytes(static_cast<uint32_t>(q_idx), static_cast<uint32_t>((k0 + c * 32) >> 4), static_cast<uint32_t>(bh), rng_seed, rng_offset);
         rnd[1] = attn_dropout_bytes(static_cast<uint32_t>(q_idx), static_cast<uint32_t>((k0 + c * 32) >> 4) + 1u, static_cast<uint32_t>(bh), rng_seed, rng_offset);
       }
-      uint32_t ts[32], td[32];
+      // ---- S -> P.  P is kept as packed bf16 pairs (what the dV MMA reads anyway); dS below is formed from these
+      // rounded probabilities, which costs one extra bf16 rounding of a value that is rounded to bf16 again right after
+      uint32_t pp[16];                       // P as it multiplied V in the forward (after dropout)
+      [[maybe_unused]] uint32_t pu[16];      // DROP only: the undropped probabilities
       mbar_wait(sdp_full, it & 1);
       tc_fence_after_sync();
-      tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::S_COL + c * 32, ts);
-      tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DP_COL + c * 32, td);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sdp_free);
-      const float lse2_cur = lse2, delta_cur = delta_s;
-      row_stats(it + 1, lse2, delta_s);          // next block's row statistics: in flight during this block's softmax
-
-      uint32_t pp[16], dd[16];
-      auto pds = [&](auto mask_tag) {
-        constexpr bool MASK = decltype(mask_tag)::value;
-        float dsv[32];   // only materialised for the dbias path
+      {
+        uint32_t ts[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::S_COL + c * 32, ts);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        auto softmax = [&](auto mask_tag) {
+          constexpr bool MASK = decltype(mask_tag)::value;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0, p1;
+            if constexpr (BIAS == BIAS_DENSE) {
+              const float2 bf = unpack_bf16((&bq[i >> 3].x)[(i & 7) >> 1]);
+              p0 = fast_exp2(fmaf(__uint_as_float(ts[i]), p.scale_log2, bf.x * LOG2E) - lse2);
+              p1 = fast_exp2(fmaf(__uint_as_float(ts[i + 1]), p.scale_log2, bf.y * LOG2E) - lse2);
+            } else if constexpr (BIAS == BIAS_ALIBI) {
+              const int kidx = k0 + c * 32 + i;
+              p0 = fast_exp2(fmaf(__uint_as_float(ts[i]), p.scale_log2, slope2 * static_cast<float>(kidx - q_idx)) - lse2);
+              p1 = fast_exp2(fmaf(__uint_as_float(ts[i + 1]), p.scale_log2, slope2 * static_cast<float>(kidx + 1 - q_idx)) - lse2);
+            } else {
+              p0 = fast_exp2(fmaf(__uint_as_float(ts[i]), p.scale_log2, -lse2));
+              p1 = fast_exp2(fmaf(__uint_as_float(ts[i + 1]), p.scale_log2, -lse2));
+            }
+            if constexpr (MASK) {
+              const int kidx = k0 + c * 32 + i;
+              p0 = (!q_ok || kidx >= kv_len || (p.causal && kidx > q_idx)) ? 0.f : p0;
+              p1 = (!q_ok || kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) ? 0.f : p1;
+            }
+            if constexpr (DROP) {
+              const bool keep0 = rnd_byte(rnd[i >> 4], i & 15) >= p.drop_thresh;
+              const bool keep1 = rnd_byte(rnd[i >> 4], (i & 15) + 1) >= p.drop_thresh;
+              pu[i / 2] = pack_bf16(p0, p1);
+              pp[i / 2] = pack_bf16(keep0 ? p0 * p.inv_keep : 0.f, keep1 ? p1 * p.inv_keep : 0.f);
+            } else {
+              pp[i / 2] = pack_bf16(p0, p1);
+            }
+          }
+        };
+        if (need_mask) softmax(std::true_type{}); else softmax(std::false_type{});
+      }
+      // ---- dP -> dS = P ∘ (dP − δ) · scale
+      uint32_t dd[16];
+      {
+        uint32_t td[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + Cfg::DP_COL + c * 32, td);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dp_free);
+        [[maybe_unused]] float dsv[32];   // only materialised for the dbias path
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0, p1;
-          if constexpr (BIAS == BIAS_DENSE) {
-            const float2 bf = unpack_bf16((&bq[i >> 3].x)[(i & 7) >> 1]);
-            p0 = fast_exp2(fmaf(__uint_as_float(ts[i]), p.scale_log2, bf.x * LOG2E) - lse2_cur);
-            p1 = fast_exp2(fmaf(__uint_as_float(ts[i + 1]), p.scale_log2, bf.y * LOG2E) - lse2_cur);
-          } else if constexpr (BIAS == BIAS_ALIBI) {
-            const int kidx = k0 + c * 32 + i;
-            p0 = fast_exp2(fmaf(__uint_as_float(ts[i]), p.scale_log2, slope2 * static_cast<float>(kidx - q_idx)) - lse2_cur);
-            p1 = fast_exp2(fmaf(__uint_as_float(ts[i + 1]), p.scale_log2, slope2 * static_cast<float>(kidx + 1 - q_idx)) - lse2_cur);
-          } else {
-            p0 = fast_exp2(fmaf(__uint_as_float(ts[i]), p.scale_log2, -lse2_cur));
-            p1 = fast_exp2(fmaf(__uint_as_float(ts[i + 1]), p.scale_log2, -lse2_cur));
-          }
-          if constexpr (MASK) {
-            const int kidx = k0 + c * 32 + i;
-            if (!q_ok || kidx >= kv_len || (p.causal && kidx > q_idx)) p0 = 0.f;
-            if (!q_ok || kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) p1 = 0.f;
-          }
+          float2 pr;
+          if constexpr (DROP) pr = unpack_bf16(pu[i / 2]); else pr = unpack_bf16(pp[i / 2]);
           float g0 = __uint_as_float(td[i]), g1 = __uint_as_float(td[i + 1]);   // dP w.r.t. the dropped, rescaled P
-          float pd0 = p0, pd1 = p1;                                               // what multiplied V in the forward
           if constexpr (DROP) {
-            const bool keep0 = rnd_byte(rnd[i >> 4], i & 15) >= p.drop_thresh;
-            const bool keep1 = rnd_byte(rnd[i >> 4], (i & 15) + 1) >= p.drop_thresh;
-            g0 = keep0 ? g0 * p.inv_keep : 0.f;
-            g1 = keep1 ? g1 * p.inv_keep : 0.f;
-            pd0 = keep0 ? p0 * p.inv_keep : 0.f;
-            pd1 = keep1 ? p1 * p.inv_keep : 0.f;
+            g0 = rnd_byte(rnd[i >> 4], i & 15) >= p.drop_thresh ? g0 * p.inv_keep : 0.f;
+            g1 = rnd_byte(rnd[i >> 4], (i & 15) + 1) >= p.drop_thresh ? g1 * p.inv_keep : 0.f;
           }
-          const float d0 = p0 * fmaf(g0, p.scale, -delta_cur);
-          const float d1 = p1 * fmaf(g1, p.scale, -delta_cur);
-          pp[i / 2] = pack_bf16(pd0, pd1);
+          const float d0 = pr.x * fmaf(g0, p.scale, -delta_s);
+          const float d1 = pr.y * fmaf(g1, p.scale, -delta_s);
           dd[i / 2] = pack_bf16(d0, d1);
           if constexpr (BIAS == BIAS_DENSE) {
             dsv[i] = d0 * inv_scale;
@@ -1503,15 +1535,14 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
           }
         }
-      };
-      if (need_mask) pds(std::true_type{}); else pds(std::false_type{});
+      }
       // the dV/dK/dQ MMAs of the previous block read the P/dS tiles: they were issued a whole softmax ago
       mbar_wait(pds_empty, (it & 1) ^ 1);
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
-        const int phys = ((c % 2) * 4 + q4) ^ (r & 7);
-        *reinterpret_cast<uint4*>(prow + half_off + phys * 16) = make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
-        *reinterpret_cast<uint4*>(dsrow + half_off + phys * 16) = make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
+        const uint32_t phys = (static_cast<uint32_t>((c % 2) * 4 + q4) ^ sw) * 16u;
+        sts128(p_row + phys, pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
+        sts128(ds_row + phys, dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -1519,7 +1550,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (it > 0) drain_dq(it - 1);     // issued behind the previous block's P/dS hand-over: complete by now
     }
     drain_dq(iters - 1);
-    if (quarter < 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    // (the CTA may retire while the reductions are still in flight: only their shared-memory reads must be done)
+    if (quarter < 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
     // ---- dV / dK accumulators: thread r <-> key row r; warps of quarters 0,1 write dV, quarters 2,3 write dK
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
@@ -1658,12 +1690,13 @@ cudaError_t launch_bwd_pipe_r(const CUtensorMap& tq, const CUtensorMap& tk, cons
   kern<<<grid, lb::att_bwdp_threads<REGS>(), lb::ATT_BWDP_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
   return cudaGetLastError();
 }
-// LIBAI_B200_ATTN_BWD_PIPE: 0 = sequential kernel, 1 = pipelined, 2 (default) = pipelined + setmaxnreg
+// LIBAI_B200_ATTN_BWD_PIPE: 0 = sequential kernel, 1 (default) = pipelined, 2 = pipelined + setmaxnreg (experimental:
+// the first version, 64/112 registers = the whole register file, never got its TRY_ALLOC granted and hung)
 static int attn_bwd_pipe_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("LIBAI_B200_ATTN_BWD_PIPE");
-    v = e == nullptr ? 2 : atoi(e);
+    v = e == nullptr ? 1 : atoi(e);
   }
   return v;
 }
@@ -1716,7 +1749,12 @@ extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const
       return -2;
   }
   const long rows = (long)B * A * S;
-  {
+  static int skip_helpers = -1;   // timing experiments only: the main kernel alone (results are then meaningless)
+  if (skip_helpers < 0) {
+    const char* e = getenv("LIBAI_B200_ATTN_DEBUG_SKIP_HELPERS");
+    skip_helpers = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
+  if (!skip_helpers) {
     // 4 rows per thread-group and iteration; cap the grid at a few waves
     const long groups = (rows + 3) / 4;
     const long lpr = D / 8;
@@ -1755,8 +1793,17 @@ extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const
   p.drop_thresh = (p_drop > 0.f && rng_state != nullptr) ? (thr == 0 ? 1u : thr) : 0u;
   p.inv_keep = 256.0f / (256.0f - (float)p.drop_thresh);
   p.rng_state = rng_state;
+  {
+    static int skip = -1;
+    if (skip < 0) {
+      const char* e = getenv("LIBAI_B200_ATTN_DEBUG_SKIP_DQ");
+      skip = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    }
+    p.debug_skip_dq = skip;
+  }
   cudaError_t e = (D == 64) ? launch_bwd<64>(tq, tk, tv, tdo, tdq, p, s) : launch_bwd<128>(tq, tk, tv, tdo, tdq, p, s);
   if (e != cudaSuccess) return (int)e;
+  if (skip_helpers) return 0;
   const long nvec = rows * D / 8;
   int blocks = (int)((nvec + 511) / 512);
   if (blocks > 148 * 8) blocks = 148 * 8;
