@@ -6,6 +6,7 @@
 //   bwd : dx = rstd * (g·γ - mean_h(g·γ) - x̂ · mean_h(g·γ·x̂))   (rms: no mean_h(g·γ) term)
 //         dγ = Σ_rows g·x̂ ,  dβ = Σ_rows g        (two-stage: per-CTA partials, then column reduce)
 #include "common.cuh"
+#include <type_traits>
 
 namespace lb {
 
@@ -160,6 +161,105 @@ norm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, const W* __re
   }
 }
 
+// bf16 activations, bandwidth-oriented variant of the kernel above (same maths, same outputs).  The first version kept
+// x̂ and g·γ of a row as 2 x VPL x 8 floats across the two warp reductions and fetched the residual gradient afterwards:
+// 191 registers → one 8-warp block per SM, and three dependent memory phases per row — 19 µs for [8192, 1024] where
+// the 64 MB it moves take 9 µs (profiles/r2_20_step_breakdown.md).  Here a row's x, gy and residual gradient are
+// fetched together as raw 16-byte vectors (3 x VPL x 4 registers), unpacked twice (before and after the reductions:
+// ALU is free here), and blocks are 4 warps at <= 168 registers → 12 warps per SM with 12 loads each in flight.
+constexpr int NORM_BWD_WARPS = 4;
+
+template <typename W, int VPL, bool RMS>
+__global__ void __launch_bounds__(NORM_BWD_WARPS * 32, 3)
+norm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ x, const W* __restrict__ gamma,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ gx,
+                     float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, int rows,
+                     const __nv_bfloat16* __restrict__ gadd) {
+  constexpr int H = VPL * 256;
+  __shared__ float red[NORM_BWD_WARPS][32 * 8 + 8];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  float dg[VPL][8], db[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+  // (γ is re-read from L1 in both passes instead of living in VPL x 8 registers)
+  auto unpack8 = [](const uint4& q, float (&v)[8]) {
+    const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  };
+
+  for (int row = blockIdx.x * NORM_BWD_WARPS + warp; row < rows; row += gridDim.x * NORM_BWD_WARPS) {
+    const size_t base = static_cast<size_t>(row) * H;
+    uint4 xq[VPL], gq[VPL], aq[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      xq[i] = *reinterpret_cast<const uint4*>(x + base + (i * 32 + lane) * 8);
+      gq[i] = *reinterpret_cast<const uint4*>(gy + base + (i * 32 + lane) * 8);
+    }
+    if (gadd != nullptr) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) aq[i] = *reinterpret_cast<const uint4*>(gadd + base + (i * 32 + lane) * 8);
+    }
+    const float mean = RMS ? 0.f : mean_in[row];
+    const float rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float xv[8], gv[8], gm[8];
+      unpack8(xq[i], xv);
+      unpack8(gq[i], gv);
+      Vec8<W>::load(gamma + (i * 32 + lane) * 8, gm);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mean) * rstd;
+        const float gw = gv[j] * gm[j];
+        s1 += gw;
+        s2 += gw * xh;
+        dg[i][j] += gv[j] * xh;
+        db[i][j] += gv[j];
+      }
+    }
+    s1 = RMS ? 0.f : warp_sum(s1) * (1.0f / H);
+    s2 = warp_sum(s2) * (1.0f / H);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float xv[8], gv[8], gm[8], o[8];
+      unpack8(xq[i], xv);
+      unpack8(gq[i], gv);
+      Vec8<W>::load(gamma + (i * 32 + lane) * 8, gm);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mean) * rstd;
+        o[j] = rstd * (gv[j] * gm[j] - s1 - xh * s2);
+      }
+      if (gadd != nullptr) {  // the skip connection's gradient rides along: saves autograd's separate add kernel
+        float a[8];
+        unpack8(aq[i], a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += a[j];
+      }
+      Vec8<__nv_bfloat16>::store(gx + base + (i * 32 + lane) * 8, o);
+    }
+  }
+  // block-level reduction of the per-warp column partials, one vector slot at a time
+  for (int i = 0; i < VPL; ++i) {
+    for (int which = 0; which < (part_dbeta != nullptr ? 2 : 1); ++which) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = which == 0 ? dg[i][j] : db[i][j];
+      __syncthreads();
+      for (int c = threadIdx.x; c < 256; c += NORM_BWD_WARPS * 32) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < NORM_BWD_WARPS; ++w) acc += red[w][c];
+        float* dst = (which == 0 ? part_dgamma : part_dbeta) + static_cast<size_t>(blockIdx.x) * H + i * 256 + c;
+        *dst = acc;
+      }
+    }
+  }
+}
+
 // out[c] = sum_r part[r, c]   (block = 32 columns x 8 row stripes, smem tree over the stripes)
 // blockIdx.y selects (part0 -> out0) / (part1 -> out1): dgamma and dbeta in one launch; `accumulate` adds into `out`
 // (each column is owned by exactly one thread, so the fp32 main-grad buffer is updated with a plain read-modify-write)
@@ -255,19 +355,37 @@ __global__ void norm_bwd_generic(const T* __restrict__ gy, const T* __restrict__
 }  // namespace lb
 
 namespace {
+int norm_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
 int norm_grid(int rows) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int need = (rows + lb::NORM_WARPS - 1) / lb::NORM_WARPS;
-  const int cap = sms * 2;
+  const int cap = norm_sms() * 2;
+  return need < cap ? need : cap;
+}
+// forward: 64 registers → four 8-warp blocks per SM
+int norm_fwd_grid(int rows) {
+  const int need = (rows + lb::NORM_WARPS - 1) / lb::NORM_WARPS;
+  const int cap = norm_sms() * 4;
+  return need < cap ? need : cap;
+}
+// bf16 backward: three 4-warp blocks per SM (one wave; every block leaves one row of column partials)
+int norm_bwd_bf16_grid(int rows) {
+  const int need = (rows + lb::NORM_BWD_WARPS - 1) / lb::NORM_BWD_WARPS;
+  const int cap = norm_sms() * 3;
   return need < cap ? need : cap;
 }
 
 template <typename T, typename W, bool RMS>
 bool fwd_dispatch(int vpl, const T* x, const W* g, const W* b, T* y, float* mean, float* rstd, int rows, float eps,
                   cudaStream_t s) {
-  const int grid = norm_grid(rows);
+  const int grid = norm_fwd_grid(rows);
 #define LB_CASE(V)                                                                                             \
   case V:                                                                                                      \
     lb::norm_fwd_kernel<T, W, V, RMS><<<grid, lb::NORM_WARPS * 32, 0, s>>>(x, g, b, y, mean, rstd, rows, eps); \
@@ -281,9 +399,30 @@ bool fwd_dispatch(int vpl, const T* x, const W* g, const W* b, T* y, float* mean
 #undef LB_CASE
 }
 
+template <typename W, bool RMS>
+bool bwd_dispatch_bf16(int vpl, const __nv_bfloat16* gy, const __nv_bfloat16* x, const W* g, const float* mean,
+                       const float* rstd, __nv_bfloat16* gx, float* pdg, float* pdb, int rows, int grid, cudaStream_t s,
+                       const __nv_bfloat16* gadd) {
+#define LB_CASE(V)                                                                                                        \
+  case V:                                                                                                                 \
+    lb::norm_bwd_bf16_kernel<W, V, RMS><<<grid, lb::NORM_BWD_WARPS * 32, 0, s>>>(gy, x, g, mean, rstd, gx, pdg, pdb, rows, gadd); \
+    return true;
+  switch (vpl) {
+    LB_CASE(1) LB_CASE(2) LB_CASE(3) LB_CASE(4)
+    default:
+      return false;
+  }
+#undef LB_CASE
+}
+// H <= 1024 with bf16 activations takes the bandwidth-oriented kernel (wider rows would spill at 168 registers)
+bool norm_bwd_uses_bf16_kernel(int H, int dtype) { return dtype == 0 && H % 256 == 0 && H / 256 <= 4; }
+
 template <typename T, typename W, bool RMS>
 bool bwd_dispatch(int vpl, const T* gy, const T* x, const W* g, const float* mean, const float* rstd, T* gx, float* pdg,
                   float* pdb, int rows, int grid, cudaStream_t s, const T* gadd) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (norm_bwd_uses_bf16_kernel(vpl * 256, 0)) return bwd_dispatch_bf16<W, RMS>(vpl, gy, x, g, mean, rstd, gx, pdg, pdb, rows, grid, s, gadd);
+  }
 #define LB_CASE(V)                                                                                                   \
   case V:                                                                                                            \
     lb::norm_bwd_kernel<T, W, V, RMS><<<grid, lb::NORM_WARPS * 32, 0, s>>>(gy, x, g, mean, rstd, gx, pdg, pdb, rows, gadd); \
@@ -331,7 +470,10 @@ extern "C" int lb_norm_fwd(const void* x, const void* gamma, const void* beta, v
 }
 
 // workspace: float[2 * grid_cap * H] where grid_cap = lb_norm_bwd_workspace_rows(); dgamma/dbeta fp32 [H]
-extern "C" int lb_norm_bwd_workspace_rows(int rows) { return norm_grid(rows); }
+extern "C" int lb_norm_bwd_workspace_rows(int rows) {
+  const int a = norm_grid(rows), b = norm_bwd_bf16_grid(rows);
+  return a > b ? a : b;
+}
 // the fused "+ residual gradient" is implemented by the register-cached kernel only (H = 256 * {1..6, 8, 10, 12, 16})
 extern "C" int lb_norm_bwd_supports_gadd(int H) {
   if (H % 256 != 0) return 0;
@@ -345,7 +487,7 @@ extern "C" int lb_norm_bwd(const void* gy, const void* x, const void* gamma, con
   if (rows == 0) return 0;
   const bool fast = (H % 256 == 0) && (H / 256 <= 16);
   if (gadd != nullptr && !lb_norm_bwd_supports_gadd(H)) return -3;  // caller adds the residual gradient itself
-  const int grid = norm_grid(rows);
+  const int grid = norm_bwd_uses_bf16_kernel(H, dtype) ? norm_bwd_bf16_grid(rows) : norm_grid(rows);
   bool done = false;
   float* pdg = workspace;
   float* pdb = dbeta != nullptr ? workspace + static_cast<size_t>(grid) * H : nullptr;
