@@ -337,6 +337,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // =================================================================================================
 namespace lb {
 
+// named barrier of the two warps that own the same TMEM lane quadrant (immediate ids: a register id would make ptxas
+// reserve all 16 barriers of the CTA)
+LB_DEVICE void pair_sync(int quad) {
+  if (quad == 0) asm volatile("bar.sync 1, 64;\n" ::: "memory");
+  else if (quad == 1) asm volatile("bar.sync 2, 64;\n" ::: "memory");
+  else if (quad == 2) asm volatile("bar.sync 3, 64;\n" ::: "memory");
+  else asm volatile("bar.sync 4, 64;\n" ::: "memory");
+}
+
 template <int D>
 struct AttnCfg2 {
   static constexpr int QK_CHUNKS = D / 64;
@@ -370,7 +379,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* s_full = bars + 9;
   uint64_t* p_full = bars + 10;
   uint64_t* o_full = bars + 11;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_free = bars + 12;      // the softmax warps hold S(j) in registers: Q·Kᵀ(j+1) may overwrite the columns
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp_idx = threadIdx.x / 32, lane = threadIdx.x % 32;
   // heavy (late) query blocks first: better tail behaviour under the causal mask
@@ -393,8 +403,9 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
+    mbar_init(p_full, 8);        // one arrival per softmax warp
     mbar_init(o_full, 1);
+    mbar_init(s_free, 8);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -430,10 +441,13 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, D, false, true);
     const uint32_t q_addr = smem_u32(sQ);
     mbar_wait(q_full, 0);
-    for (int j = 0; j < nkv; ++j) {
+    // S(j+1) = Q·K(j+1)ᵀ is issued as soon as the softmax warps have read S(j) for the last time (s_free), i.e. under the
+    // exponentials / P store of block j and ahead of P(j)·V(j): the next block's scores are ready when the softmax warps
+    // come back for them
+    auto issue_qk = [&](int j) {
       const int b = j & 1;
       mbar_wait(&k_full[b], (j >> 1) & 1);
-      // (S is free: P·V(j-1) was only issued after the softmax warps finished reading S(j-1))
+      if (j > 0) mbar_wait(s_free, (j - 1) & 1);
       tc_fence_after_sync();
       if (elect_one()) {
         const uint32_t k_addr = smem_u32(sK + b * Cfg::TILE_BYTES);
@@ -447,6 +461,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         umma_commit(&k_empty[b]);
       }
       __syncwarp();
+    };
+    issue_qk(0);
+    for (int j = 0; j < nkv; ++j) {
+      const int b = j & 1;
+      if (j + 1 < nkv) issue_qk(j + 1);
       mbar_wait(p_full, j & 1);
       mbar_wait(&v_full[b], (j >> 1) & 1);
       tc_fence_after_sync();
@@ -545,7 +564,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       if (need_mask) pass1(std::true_type{}); else pass1(std::false_type{});
       float* xch = sXchg + (j & 1) * 256;
       xch[half * 128 + r] = mx;
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      pair_sync(quad);   // only the two warps that share these 32 rows
       mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);
       // ---- lazy rescale: only move the reference max when it grows by more than 2^8
       const float m_cand = fmaxf(m_run, BIAS != BIAS_NONE ? mx : mx * p.scale_log2);
@@ -574,6 +593,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             rnd[1] = attn_dropout_bytes(static_cast<uint32_t>(q_idx), static_cast<uint32_t>((k0 + c * 32) >> 4) + 1u, bh, rng_seed, rng_offset);
           }
           tmem_ld_wait();
+          if (c == 1) {   // S(j) has been read for the last time
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free);
+          }
           uint32_t packed[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -620,12 +644,13 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       }
       tmem_st_wait();
       tc_fence_before_sync();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
     }
     // ---- epilogue: combine the two partial row sums, O / l  →  [B, S, A, D]
     float* xch = sXchg + (nkv & 1) * 256;
     xch[half * 128 + r] = l_run;
-    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    pair_sync(quad);
     l_run += xch[(half ^ 1) * 128 + r];
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after_sync();

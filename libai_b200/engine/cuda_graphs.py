@@ -234,7 +234,7 @@ def _enable_for_model(model: nn.Module, example_batch: dict, topo) -> bool:
     if topo.pipeline_parallel_size > 1:
         return _enable_for_pipeline_stage(model, example_batch, topo)
     layers = model.stage_layers() if hasattr(model, "stage_layers") else None
-    if not isinstance(layers, nn.ModuleList) or len(layers) == 0:
+    if not isinstance(layers, (nn.ModuleList, nn.Sequential)) or len(layers) == 0:
         return False
     shapes = {}
 
@@ -280,7 +280,7 @@ def _enable_for_pipeline_stage(model: nn.Module, example_batch: dict, topo) -> b
     The hidden-state shape is the stage's p2p payload; it is derived from the batch (token-sharded under sequence
     parallelism) instead of running the model, because only the first stage can run without a received activation."""
     layers = model.stage_layers() if hasattr(model, "stage_layers") else None
-    if not isinstance(layers, nn.ModuleList) or len(layers) == 0:
+    if not isinstance(layers, (nn.ModuleList, nn.Sequential)) or len(layers) == 0:
         return False
     own = [l for l in layers if topo.owns_layer(getattr(l, "layer_idx", 0))]
     if not own:
