@@ -54,11 +54,11 @@ int lb_gemm_bf16_comm(const void* a, const void* b, void* out, int M, int N, int
                       void* state, const void* local_shard, int fill_local, const void* residual, void* rs_out,
                       long staging_parity_off, int n_comm, cudaStream_t stream);
 int lb_zero_reduce_scatter(const long* grad_ptrs, const long* flag_ptrs, float* red, float* sqnorm, long lo, long n,
-                           float scale, int world, int rank, unsigned epoch, cudaStream_t s);
+                           float scale, int world, int rank, unsigned epoch, long mc_grad, cudaStream_t s);
 int lb_zero_adam_allgather(float* master, const float* red, float* m, float* v, const long* param_ptrs,
                            const long* flag_ptrs, unsigned* done_counter, const float* clip, long lo, long n, float lr,
                            float b1, float b2, float eps, float wd, float bc1, float bc2, int decoupled, int world,
-                           int rank, unsigned epoch, cudaStream_t s);
+                           int rank, unsigned epoch, long mc_param, cudaStream_t s);
 int lb_device_barrier(const long* flag_ptrs, int world, int rank, int slot, unsigned epoch, cudaStream_t s);
 int lb_p2p_allgather(const void* shard, const long* out_ptrs, const long* flag_ptrs, unsigned* done_counter,
                      long nbytes, int world, int rank, unsigned epoch, cudaStream_t s);
@@ -716,25 +716,25 @@ Tensor gemm_rs(const Tensor& x, const Tensor& w, int64_t layout, const c10::opti
 }
 
 void zero_reduce_scatter(at::IntArrayRef grad_ptrs, at::IntArrayRef flag_ptrs, Tensor red, Tensor sqnorm, int64_t lo,
-                         int64_t n, double scale, int64_t world, int64_t rank, int64_t epoch) {
+                         int64_t n, double scale, int64_t world, int64_t rank, int64_t epoch, int64_t mc_grad) {
   c10::cuda::CUDAGuard guard(red.device());
   auto g = to_longs(grad_ptrs), f = to_longs(flag_ptrs);
   check(lb_zero_reduce_scatter(g.data(), f.data(), red.data_ptr<float>(), sqnorm.data_ptr<float>(), (long)lo, (long)n,
-                               (float)scale, (int)world, (int)rank, (unsigned)epoch, cur_stream()),
+                               (float)scale, (int)world, (int)rank, (unsigned)epoch, (long)mc_grad, cur_stream()),
         "zero_reduce_scatter");
 }
 
 void zero_adam_allgather(Tensor master, const Tensor& red, Tensor m, Tensor v, at::IntArrayRef param_ptrs,
                          at::IntArrayRef flag_ptrs, Tensor done_counter, const Tensor& clip, int64_t lo, int64_t n,
                          double lr, double b1, double b2, double eps, double wd, double bc1, double bc2, bool decoupled,
-                         int64_t world, int64_t rank, int64_t epoch) {
+                         int64_t world, int64_t rank, int64_t epoch, int64_t mc_param) {
   c10::cuda::CUDAGuard guard(master.device());
   auto pp = to_longs(param_ptrs), f = to_longs(flag_ptrs);
   check(lb_zero_adam_allgather(master.data_ptr<float>(), red.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
                                pp.data(), f.data(), reinterpret_cast<unsigned*>(done_counter.data_ptr()),
                                clip.data_ptr<float>(), (long)lo, (long)n, (float)lr, (float)b1, (float)b2, (float)eps,
                                (float)wd, (float)bc1, (float)bc2, decoupled ? 1 : 0, (int)world, (int)rank,
-                               (unsigned)epoch, cur_stream()),
+                               (unsigned)epoch, (long)mc_param, cur_stream()),
         "zero_adam_allgather");
 }
 
@@ -759,8 +759,8 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("ag_gemm(Tensor gathered, Tensor shard, Tensor w, int layout, Tensor? bias, int act, bool need_pre, Tensor? pre_in, Tensor(a!)? colsum, bool fill_local, int world, int rank, int[] peer_buf, int[] peer_flags, int[] peer_done, Tensor(b!) state, int n_comm) -> (Tensor, Tensor)", &ag_gemm);
   m.def("ag_wgrad(Tensor gy, Tensor gathered, Tensor shard, Tensor(a!) out, bool accumulate, int world, int rank, int[] peer_buf, int[] peer_flags, int[] peer_done, Tensor(b!) state, int n_comm) -> ()", &ag_wgrad);
   m.def("gemm_rs(Tensor x, Tensor w, int layout, Tensor? bias, Tensor? residual, int world, int rank, int[] peer_buf, int[] peer_flags, int[] peer_done, Tensor(a!) state, int staging_parity_off) -> Tensor", &gemm_rs);
-  m.def("zero_reduce_scatter(int[] grad_ptrs, int[] flag_ptrs, Tensor(a!) red, Tensor(b!) sqnorm, int lo, int n, float scale, int world, int rank, int epoch) -> ()", &zero_reduce_scatter);
-  m.def("zero_adam_allgather(Tensor(a!) master, Tensor red, Tensor(b!) m, Tensor(c!) v, int[] param_ptrs, int[] flag_ptrs, Tensor(d!) done_counter, Tensor clip, int lo, int n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, bool decoupled, int world, int rank, int epoch) -> ()", &zero_adam_allgather);
+  m.def("zero_reduce_scatter(int[] grad_ptrs, int[] flag_ptrs, Tensor(a!) red, Tensor(b!) sqnorm, int lo, int n, float scale, int world, int rank, int epoch, int mc_grad=0) -> ()", &zero_reduce_scatter);
+  m.def("zero_adam_allgather(Tensor(a!) master, Tensor red, Tensor(b!) m, Tensor(c!) v, int[] param_ptrs, int[] flag_ptrs, Tensor(d!) done_counter, Tensor clip, int lo, int n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, bool decoupled, int world, int rank, int epoch, int mc_param=0) -> ()", &zero_adam_allgather);
   m.def("device_barrier(int[] flag_ptrs, int world, int rank, int slot, int epoch) -> ()", &device_barrier);
   m.def("p2p_allgather(Tensor shard, int[] out_ptrs, int[] flag_ptrs, Tensor(a!) done_counter, int world, int rank, int epoch) -> ()", &p2p_allgather);
   m.def("gemm(Tensor a, Tensor b, int layout, Tensor? bias, Tensor? out, bool accumulate, ScalarType out_dtype) -> Tensor", &gemm);

@@ -5,6 +5,10 @@
 //                         partial squared norm (for global-norm clipping)            [K3, first half]
 //   zero_adam_allgather : AdamW on the owned slice (fp32 master, m, v) and the bf16 parameter slice is
 //                         pushed straight into every peer's parameter buffer (P2P stores)  [K3 + K4]
+//   NVLS                : when the buffers are bound to an NVSwitch multicast object (parallel/symm_mem.py), the reduce-
+//                         scatter is ONE `multimem.ld_reduce` per 16 bytes — the switch adds the eight ranks' values and
+//                         returns the sum, 1/8 of the inbound NVLink traffic of the pull form — and the parameter
+//                         all-gather is ONE `multimem.st` per vector, replicated by the switch to every rank
 //   device barrier      : release/acquire flag exchange at .sys scope with monotonically increasing
 //                         epochs (no host synchronisation, survives CUDA-graph replay as long as the
 //                         epoch is advanced per launch)
@@ -30,6 +34,20 @@ LB_DEVICE float4 ld_stream_f4(const float4* p) {
                : "l"(p)
                : "memory");
   return v;
+}
+
+// in-switch reduction of 4 floats over every device bound to the multicast object (NVLS)
+LB_DEVICE float4 multimem_ld_reduce_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+// one store, replicated by the switch into every bound device's memory (4 bf16 values)
+LB_DEVICE void multimem_st_bf16x4(__nv_bfloat16* mc, uint2 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.bf16x2 [%0], {%1, %2};\n" ::"l"(mc), "r"(v.x), "r"(v.y) : "memory");
 }
 
 LB_DEVICE void st_release_sys(uint32_t* addr, uint32_t v) {
@@ -59,7 +77,8 @@ LB_DEVICE void wait_peers(const PeerPtrs& flags, int world, int rank, int slot, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 zero_reduce_scatter_kernel(PeerPtrs grads, PeerPtrs flags, float* __restrict__ red, float* __restrict__ sqnorm,
-                           size_t lo, size_t n, float scale, int world, int rank, uint32_t epoch) {
+                           size_t lo, size_t n, float scale, int world, int rank, uint32_t epoch,
+                           const float* __restrict__ mc_grad /* multicast address of the gradient buffers, or null */) {
   __shared__ float sm[8];
   if (blockIdx.x == 0 && threadIdx.x == 0) signal_peers(flags, world, rank, /*slot=*/0, epoch);
   if (threadIdx.x == 0) wait_peers(flags, world, rank, 0, epoch);
@@ -68,19 +87,23 @@ zero_reduce_scatter_kernel(PeerPtrs grads, PeerPtrs flags, float* __restrict__ r
   float acc_sq = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 part[MAX_RANKS];
+    if (mc_grad != nullptr) {
+      s = multimem_ld_reduce_f4(mc_grad + lo + i * 4);   // the switch returns the sum over all ranks
+    } else {
+      float4 part[MAX_RANKS];
 #pragma unroll
-    for (int q = 0; q < MAX_RANKS; ++q) {
-      if (q < world) {
-        // rotate the start so that the ranks do not all hammer the same peer at the same time
-        const int src = (rank + q) % world;
-        part[q] = ld_stream_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grads.p[src]) + lo) + i);
+      for (int q = 0; q < MAX_RANKS; ++q) {
+        if (q < world) {
+          // rotate the start so that the ranks do not all hammer the same peer at the same time
+          const int src = (rank + q) % world;
+          part[q] = ld_stream_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grads.p[src]) + lo) + i);
+        }
       }
-    }
 #pragma unroll
-    for (int q = 0; q < MAX_RANKS; ++q) {
-      if (q < world) {
-        s.x += part[q].x; s.y += part[q].y; s.z += part[q].z; s.w += part[q].w;
+      for (int q = 0; q < MAX_RANKS; ++q) {
+        if (q < world) {
+          s.x += part[q].x; s.y += part[q].y; s.z += part[q].z; s.w += part[q].w;
+        }
       }
     }
     s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
@@ -105,7 +128,8 @@ zero_adam_allgather_kernel(float* __restrict__ master, const float* __restrict__
                            float* __restrict__ v, PeerPtrs params /* bf16 flat buffers */, PeerPtrs flags,
                            unsigned int* __restrict__ done_counter, const float* __restrict__ clip_ptr, size_t lo,
                            size_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2,
-                           int decoupled, int world, int rank, uint32_t epoch) {
+                           int decoupled, int world, int rank, uint32_t epoch,
+                           __nv_bfloat16* __restrict__ mc_param /* multicast address of the parameter buffers, or null */) {
   const float clip = clip_ptr != nullptr ? *clip_ptr : 1.0f;
   const size_t nvec = n / 4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
@@ -129,10 +153,14 @@ zero_adam_allgather_kernel(float* __restrict__ master, const float* __restrict__
     reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
     reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
     const uint2 lp = make_uint2(pack_bf16(pp[0], pp[1]), pack_bf16(pp[2], pp[3]));
+    if (mc_param != nullptr) {
+      multimem_st_bf16x4(mc_param + lo + i * 4, lp);    // replicated to every rank (this one included) by the switch
+    } else {
 #pragma unroll 8
-    for (int q = 0; q < world; ++q) {
-      const int dst = (rank + q) % world;
-      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(params.p[dst]) + lo)[i] = lp;
+      for (int q = 0; q < world; ++q) {
+        const int dst = (rank + q) % world;
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(params.p[dst]) + lo)[i] = lp;
+      }
     }
   }
   // all CTAs done -> publish completion to every peer, then wait for theirs: when this kernel retires,
@@ -200,22 +228,24 @@ lb::PeerPtrs to_peers(const long* ptrs, int world) {
 }  // namespace
 
 extern "C" int lb_zero_reduce_scatter(const long* grad_ptrs, const long* flag_ptrs, float* red, float* sqnorm, long lo,
-                                      long n, float scale, int world, int rank, unsigned epoch, cudaStream_t s) {
+                                      long n, float scale, int world, int rank, unsigned epoch, long mc_grad,
+                                      cudaStream_t s) {
   if (world > lb::MAX_RANKS || (n % 4) || (lo % 4)) return -1;
   lb::zero_reduce_scatter_kernel<<<comm_grid(n / 4), 256, 0, s>>>(to_peers(grad_ptrs, world), to_peers(flag_ptrs, world),
                                                                  red, sqnorm, (size_t)lo, (size_t)n, scale, world, rank,
-                                                                 epoch);
+                                                                 epoch, reinterpret_cast<const float*>(mc_grad));
   return (int)cudaGetLastError();
 }
 
 extern "C" int lb_zero_adam_allgather(float* master, const float* red, float* m, float* v, const long* param_ptrs,
                                       const long* flag_ptrs, unsigned* done_counter, const float* clip, long lo, long n,
                                       float lr, float b1, float b2, float eps, float wd, float bc1, float bc2,
-                                      int decoupled, int world, int rank, unsigned epoch, cudaStream_t s) {
+                                      int decoupled, int world, int rank, unsigned epoch, long mc_param, cudaStream_t s) {
   if (world > lb::MAX_RANKS || (n % 4) || (lo % 4)) return -1;
   lb::zero_adam_allgather_kernel<<<comm_grid(n / 4), 256, 0, s>>>(
       master, red, m, v, to_peers(param_ptrs, world), to_peers(flag_ptrs, world), done_counter, clip, (size_t)lo,
-      (size_t)n, lr, b1, b2, eps, wd, bc1, bc2, decoupled, world, rank, epoch);
+      (size_t)n, lr, b1, b2, eps, wd, bc1, bc2, decoupled, world, rank, epoch,
+      reinterpret_cast<__nv_bfloat16*>(mc_param));
   return (int)cudaGetLastError();
 }
 

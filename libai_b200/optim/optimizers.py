@@ -20,6 +20,8 @@ gathered) so optimizer checkpoints are layout independent like the reference's.
 """
 from __future__ import annotations
 
+import os
+
 import math
 from collections import OrderedDict
 from typing import Dict, List, Optional
@@ -57,8 +59,12 @@ class _Group:
         if symm_ws is not None:
             # NVLink peer-mapped buffers: the fused ZeRO kernels read peers' gradients and write peers'
             # parameters directly (K3/K4)
-            pbuf = symm_ws.buffer(("zero_param", index, self.numel), self.numel * params[0].element_size())
-            gbuf = symm_ws.buffer(("zero_grad", index, self.numel), self.numel * 4)
+            # LIBAI_B200_NVLS (default 1): bind the buffers to an NVSwitch multicast object when the platform has one —
+            # the reduce-scatter then reads in-switch sums (multimem.ld_reduce), the parameter all-gather is one
+            # multimem.st per vector
+            nvls = os.environ.get("LIBAI_B200_NVLS", "1") != "0" and self.dtype == torch.bfloat16
+            pbuf = symm_ws.buffer(("zero_param", index, self.numel), self.numel * params[0].element_size(), multicast=nvls)
+            gbuf = symm_ws.buffer(("zero_grad", index, self.numel), self.numel * 4, multicast=nvls)
             self.param_flat = pbuf.view(self.dtype, (self.numel,))
             self.grad_flat = gbuf.view(torch.float32, (self.numel,))
             self.symm = dict(ws=symm_ws, param=pbuf, grad=gbuf)
@@ -294,7 +300,8 @@ class FlatOptimizer(torch.optim.Optimizer):
                     fg.sq_partial = torch.zeros(1, dtype=torch.float32, device=fg.device)
                 # (an empty range still takes part in the flag exchange: all ranks issue the same launch sequence)
                 ext.zero_reduce_scatter(fg.symm["grad"].peer_ptrs(0), ws.flags.peer_ptrs(0), fg.grad_flat[a:b],
-                                        fg.sq_partial, a, b - a, scale, ws.world, ws.rank, ws.next_epoch())
+                                        fg.sq_partial, a, b - a, scale, ws.world, ws.rank, ws.next_epoch(),
+                                        fg.symm["grad"].mc_ptr)
                 count_launch()
                 fg.reduced_from = a
         self._early_launched = True
@@ -359,7 +366,8 @@ class FlatOptimizer(torch.optim.Optimizer):
                 if b == fg.hi:
                     fg.sq_partial.zero_()
                 ext.zero_reduce_scatter(fg.symm["grad"].peer_ptrs(0), ws.flags.peer_ptrs(0), fg.grad_flat[fg.lo:b],
-                                        fg.sq_partial, fg.lo, b - fg.lo, scale, ws.world, ws.rank, ws.next_epoch())
+                                        fg.sq_partial, fg.lo, b - fg.lo, scale, ws.world, ws.rank, ws.next_epoch(),
+                                        fg.symm["grad"].mc_ptr)
                 count_launch()
                 fg.reduced_from = fg.lo
             elif topo.dp_group is not None:
@@ -693,7 +701,7 @@ class AdamW(FlatOptimizer):
             fg.master, fg.grad_shard(), fg.state["exp_avg"], fg.state["exp_avg_sq"], fg.symm["param"].peer_ptrs(0),
             ws.flags.peer_ptrs(0), ws.done_counter[0:1], clip.reshape(1).float(), fg.lo, fg.hi - fg.lo, float(lr),
             float(b1), float(b2), float(eps), float(wd), float(bc1), float(bc2), bool(self.decoupled), ws.world, ws.rank,
-            ws.next_epoch(),
+            ws.next_epoch(), fg.symm["param"].mc_ptr,
         )
         count_launch()
 

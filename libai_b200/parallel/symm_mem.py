@@ -18,14 +18,18 @@ from libai_b200.ops import load_ext
 class SymmetricBuffer:
     """``nbytes`` of zero-initialised device memory mapped by every rank of ``group``."""
 
-    def __init__(self, nbytes: int, group=None, tag: str = ""):
+    def __init__(self, nbytes: int, group=None, tag: str = "", multicast: bool = False):
         ext = load_ext()
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.nbytes = int((nbytes + 255) // 256 * 256)
-        self.local = ext.symm_alloc(self.nbytes)  # uint8 tensor owning the allocation
         self.tag = tag
+        self.mc_ptr = 0          # NVSwitch multicast address of the buffer (0 = none: unicast peer pointers only)
+        self._torch_handle = None
+        if multicast and self.world > 1 and self._init_multicast():
+            return
+        self.local = ext.symm_alloc(self.nbytes)  # uint8 tensor owning the allocation
         if self.world == 1:
             self.ptrs = [self.local.data_ptr()]
             return
@@ -42,6 +46,47 @@ class SymmetricBuffer:
                 self.ptrs.append(int(ext.symm_open(ht)))
         dist.barrier(group=group)
 
+    def _init_multicast(self) -> bool:
+        """Allocate through PyTorch's symmetric-memory allocator (CUDA VMM: ``cuMemCreate`` + file-descriptor exchange +
+        ``cuMulticastBindMem``), which hands back the peers' unicast addresses AND the multicast address of the NVSwitch
+        multicast object the buffers are bound to.  Only the plumbing is PyTorch's; the kernels that use the addresses
+        (``multimem.ld_reduce`` / ``multimem.st``, csrc/comm_kernels.cu) are ours.  Every rank takes the same decision:
+        the outcome is agreed with a MIN all-reduce, a rank-local failure falls back to the CUDA-IPC path everywhere."""
+        ok, t, hdl = 1, None, None
+        try:
+            import torch.distributed._symmetric_memory as tsm
+
+            dev = torch.device("cuda", torch.cuda.current_device())
+            group = self.group if self.group is not None else dist.group.WORLD
+            try:
+                tsm.enable_symm_mem_for_group(group.group_name)
+            except Exception:   # noqa: BLE001 - newer releases enable groups implicitly
+                pass
+            t = tsm.empty(self.nbytes, dtype=torch.uint8, device=dev)
+            hdl = tsm.rendezvous(t, group)
+            if not (getattr(hdl, "has_multicast_support", False) or int(getattr(hdl, "multicast_ptr", 0)) != 0):
+                ok = 0
+            if int(getattr(hdl, "multicast_ptr", 0)) == 0:
+                ok = 0
+        except Exception as e:   # noqa: BLE001
+            import logging
+
+            logging.getLogger(__name__).info("NVLS multicast unavailable for %s (%s: %s)", self.tag, type(e).__name__, str(e)[:200])
+            ok = 0
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            return False
+        t.zero_()
+        torch.cuda.synchronize()
+        self.local = t
+        self._torch_handle = hdl
+        self.ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self.ptrs[self.rank] = t.data_ptr()
+        self.mc_ptr = int(hdl.multicast_ptr)
+        dist.barrier(group=self.group)
+        return True
+
     def close(self) -> None:
         """Unmap the peers' allocations and free the local one.  Collective over ``group``: nobody frees memory a
         peer may still have mapped (a later ``cudaMalloc`` can hand the same range out again, and re-opening its IPC
@@ -52,12 +97,15 @@ class SymmetricBuffer:
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier(group=self.group)           # every rank's kernels on these buffers have retired
-            for r, p in enumerate(self.ptrs):
-                if r != self.rank:
-                    ext.symm_close(int(p))
+            if self._torch_handle is None:
+                for r, p in enumerate(self.ptrs):
+                    if r != self.rank:
+                        ext.symm_close(int(p))
             dist.barrier(group=self.group)           # every mapping is gone before any owner frees
         self.ptrs = []
         self.local = None
+        self._torch_handle = None
+        self.mc_ptr = 0
 
     def view(self, dtype: torch.dtype, shape, offset_bytes: int = 0) -> torch.Tensor:
         """Typed view of the *local* buffer."""
@@ -100,9 +148,9 @@ class CommWorkspace:
         assert self._flag_cursor <= self.FLAG_BYTES, "symmetric flag buffer exhausted"
         return off
 
-    def buffer(self, key: Tuple, nbytes: int) -> SymmetricBuffer:
+    def buffer(self, key: Tuple, nbytes: int, multicast: bool = False) -> SymmetricBuffer:
         if key not in self._bufs:
-            self._bufs[key] = SymmetricBuffer(nbytes, self.group, str(key))
+            self._bufs[key] = SymmetricBuffer(nbytes, self.group, str(key), multicast=multicast)
         return self._bufs[key]
 
     def close(self) -> None:

@@ -315,6 +315,8 @@ def main():
             torch.cuda.synchronize()
             finals.append([p.detach().float().clone() for p in params])
             times.append(timeit(lambda: opt.step(), iters=10, warmup=2))
+            if fused:
+                nvls = bool(opt._groups[0].symm is not None and opt._groups[0].symm["grad"].mc_ptr)
         errs = [rel_err(a, b) for a, b in zip(finals[0], finals[1])]
         # third opinion: the same three AdamW steps computed locally in fp32 from every rank's (seeded) gradients,
         # so a mismatch can be attributed to one arm
@@ -334,7 +336,8 @@ def main():
             p0 -= 1e-2 * upd
         ref_errs = [rel_err(finals[0][0], p0), rel_err(finals[1][0], p0)]
         return {"ok": max(errs) < 1e-2 and max(ref_errs) < 2e-2, "errs": errs, "fused_vs_local_ref": ref_errs[0],
-                "nccl_vs_local_ref": ref_errs[1], "fused_step_ms": times[0], "nccl_step_ms": times[1]}
+                "nccl_vs_local_ref": ref_errs[1], "fused_step_ms": times[0], "nccl_step_ms": times[1],
+                "nvls_multicast": nvls}
 
     record("ZeRO fused RS+Adam+AG vs NCCL", zero)
 
