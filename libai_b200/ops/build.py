@@ -102,11 +102,14 @@ def dump_sass():
         text = subprocess.run([os.path.join(CUDA_HOME, "bin", "cuobjdump"), "-sass", obj], stdout=subprocess.PIPE,
                               text=True).stdout
         counts = {}
-        for key in ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "HMMA",
-                    "RED.E", "REDG", "MULTIMEM", "LDG.E", "STG.E"):
+        # UTCHMMA / UTCQMMA = tcgen05.mma (bf16 / fp8), .2CTA = cta_group::2 pairs; LDTM/STTM = tcgen05.ld/st; UTMALDG /
+        # UTMASTG / UTMAREDG / UBLKCP = TMA tensor + bulk copies and reductions; LDGMC = multimem.ld_reduce (NVLS in-switch
+        # reduction; multimem.st is a STG.*.STRONG.SYS on a multicast address); USETMAXREG = setmaxnreg
+        for key in ("UTCHMMA", "UTCHMMA.2CTA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMALDG.2D.2CTA", "UTMASTG",
+                    "UTMAREDG", "UBLKCP", "SYNCS", "LDGMC", "USETMAXREG", "RED.E", "REDG", "LDG.E", "STG.E"):
             counts[key] = text.count(key)
         summary.append((s, counts))
-        keep = [ln for ln in text.splitlines() if "Function :" in ln or any(k in ln for k in ("UTC", "LDTM", "STTM", "UTMA", "UBLKCP", "MULTIMEM"))]
+        keep = [ln for ln in text.splitlines() if "Function :" in ln or any(k in ln for k in ("UTC", "LDTM", "STTM", "UTMA", "UBLKCP", "LDGMC", "USETMAXREG"))]
         with open(os.path.join(out_dir, s + ".sass.txt"), "w") as f:
             f.write("\n".join(keep) + "\n")
     with open(os.path.join(out_dir, "SUMMARY.md"), "w") as f:

@@ -59,12 +59,14 @@ class _Group:
         if symm_ws is not None:
             # NVLink peer-mapped buffers: the fused ZeRO kernels read peers' gradients and write peers'
             # parameters directly (K3/K4)
-            # LIBAI_B200_NVLS (default 1): bind the buffers to an NVSwitch multicast object when the platform has one —
-            # the reduce-scatter then reads in-switch sums (multimem.ld_reduce), the parameter all-gather is one
-            # multimem.st per vector
-            nvls = os.environ.get("LIBAI_B200_NVLS", "1") != "0" and self.dtype == torch.bfloat16
-            pbuf = symm_ws.buffer(("zero_param", index, self.numel), self.numel * params[0].element_size(), multicast=nvls)
-            gbuf = symm_ws.buffer(("zero_grad", index, self.numel), self.numel * 4, multicast=nvls)
+            # LIBAI_B200_NVLS=1 (opt-in): bind the buffers to an NVSwitch multicast object — the reduce-scatter then reads
+            # in-switch sums (multimem.ld_reduce), the parameter all-gather is one multimem.st per vector.  Off by default:
+            # a reduce-SCATTER through the switch still has every GPU send its whole buffer (only the inbound side
+            # shrinks), so it cannot beat the unicast pull on full-duplex links; measured on 2 GPUs 26.9 vs 26.2 ms per
+            # step (profiles/r2_26_*), bit-identical results.
+            nvls = os.environ.get("LIBAI_B200_NVLS", "0") == "1" and self.dtype == torch.bfloat16
+            pbuf = symm_ws.buffer(("zero_param", index, self.numel, nvls), self.numel * params[0].element_size(), multicast=nvls)
+            gbuf = symm_ws.buffer(("zero_grad", index, self.numel, nvls), self.numel * 4, multicast=nvls)
             self.param_flat = pbuf.view(self.dtype, (self.numel,))
             self.grad_flat = gbuf.view(torch.float32, (self.numel,))
             self.symm = dict(ws=symm_ws, param=pbuf, grad=gbuf)

@@ -294,7 +294,10 @@ def main():
         dutil.setup_dist_util(DictConfig(dict(data_parallel_size=world, tensor_parallel_size=1, pipeline_parallel_size=1)))
         finals = []
         times = []
-        for fused in (True, False):
+        nvls = False
+        for arm in ("fused", "fused_nvls", "nccl"):
+            fused = arm != "nccl"
+            os.environ["LIBAI_B200_NVLS"] = "1" if arm == "fused_nvls" else "0"
             torch.manual_seed(5)
             params = [torch.nn.Parameter((torch.randn(1 << 22, device="cuda") * 0.02).bfloat16()),
                       torch.nn.Parameter((torch.randn(1000, 333, device="cuda") * 0.02).bfloat16())]
@@ -315,9 +318,10 @@ def main():
             torch.cuda.synchronize()
             finals.append([p.detach().float().clone() for p in params])
             times.append(timeit(lambda: opt.step(), iters=10, warmup=2))
-            if fused:
+            if arm == "fused_nvls":
                 nvls = bool(opt._groups[0].symm is not None and opt._groups[0].symm["grad"].mc_ptr)
-        errs = [rel_err(a, b) for a, b in zip(finals[0], finals[1])]
+        os.environ["LIBAI_B200_NVLS"] = "0"
+        errs = [rel_err(a, b) for a, b in zip(finals[0], finals[2])] + [rel_err(a, b) for a, b in zip(finals[1], finals[2])]
         # third opinion: the same three AdamW steps computed locally in fp32 from every rank's (seeded) gradients,
         # so a mismatch can be attributed to one arm
         torch.manual_seed(5)
@@ -334,10 +338,10 @@ def main():
             v.mul_(0.999).addcmul_(g, g, value=0.001)
             upd = (m / (1 - 0.9 ** (i + 1))) / ((v / (1 - 0.999 ** (i + 1))).sqrt() + 1e-8) + 0.01 * p0
             p0 -= 1e-2 * upd
-        ref_errs = [rel_err(finals[0][0], p0), rel_err(finals[1][0], p0)]
+        ref_errs = [rel_err(finals[0][0], p0), rel_err(finals[2][0], p0), rel_err(finals[1][0], p0)]
         return {"ok": max(errs) < 1e-2 and max(ref_errs) < 2e-2, "errs": errs, "fused_vs_local_ref": ref_errs[0],
-                "nccl_vs_local_ref": ref_errs[1], "fused_step_ms": times[0], "nccl_step_ms": times[1],
-                "nvls_multicast": nvls}
+                "nccl_vs_local_ref": ref_errs[1], "nvls_vs_local_ref": ref_errs[2], "fused_step_ms": times[0],
+                "fused_nvls_step_ms": times[1], "nccl_step_ms": times[2], "nvls_multicast_available": nvls}
 
     record("ZeRO fused RS+Adam+AG vs NCCL", zero)
 
