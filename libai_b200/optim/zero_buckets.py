@@ -49,6 +49,7 @@ class Bucket:
                  grad_pool: Optional[Dict] = None, parity: int = 0):
         self.params, self.key, self.stage, self.persistent = params, key, stage, persistent
         self.pool_buf = None
+        self.pool_part = None
         self.dtype, self.device = params[0].dtype, params[0].device
         assert all(p.dtype == self.dtype for p in params), "mixed dtypes inside one bucket"
         self.offsets, n = [], 0
@@ -81,7 +82,12 @@ class Bucket:
             k = (self.numel, parity, str(self.device))
             if k not in grad_pool:
                 grad_pool[k] = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+                # the reduce-scatter output of the same parity: persistent too — a fresh `torch.empty` per block would be
+                # handed to NCCL's stream (record_stream) and could not be reused by the caching allocator until that
+                # stream caught up: with 7B-sized buckets (hundreds of MB) that means cudaMalloc / cudaFree in the step
+                grad_pool[("part",) + k] = torch.empty(self.per, dtype=torch.float32, device=self.device)
             self.pool_buf = grad_pool[k]
+            self.pool_part = grad_pool[("part",) + k]
         if self.params_resident:
             self._bind_params(full)
         else:
@@ -186,7 +192,7 @@ class Bucket:
                     dist.all_reduce(p.main_grad, group=topo.embedding_group)
         if scale != 1.0:
             self.grad_flat.mul_(scale)
-        part = torch.empty(self.per, dtype=torch.float32, device=self.device)
+        part = self.pool_part if self.pool_part is not None else torch.empty(self.per, dtype=torch.float32, device=self.device)
         if pending is not None and self.grad_flat.is_cuda and not self.grads_resident:
             work = dist.reduce_scatter_tensor(part, self.grad_flat, group=topo.dp_group, async_op=True)
             pending.append((work, self, part))

@@ -37,7 +37,7 @@ def _worker(rank, world, out_dir, stage, acc, resume):
         for fg in opt._groups:
             if fg is None:
                 continue
-            tensors = [getattr(fg, name, None) for name in ("param_flat", "grad_flat", "pool_buf", "master", "red", "param_shard")]
+            tensors = [getattr(fg, name, None) for name in ("param_flat", "grad_flat", "pool_buf", "pool_part", "master", "red", "param_shard")]
             tensors += list(fg.state.values())
             for t in tensors:
                 if torch.is_tensor(t):
