@@ -20,8 +20,8 @@ def main():
     ap.add_argument("--layout", default="tp2")
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--device", type=int, default=0, help="1: torch.profiler (CUPTI) kernel table of the timed steps instead of cProfile")
-    a = ap.parse_args()
-    sys.argv = [sys.argv[0], "--gpus", os.environ.get("WORLD_SIZE", "1"), "--layout", a.layout]
+    a, rest = ap.parse_known_args()      # everything else goes to bench.py (e.g. --model llama7b --layers 8 --zero 2)
+    sys.argv = [sys.argv[0], "--gpus", os.environ.get("WORLD_SIZE", "1"), "--layout", a.layout] + rest
     args = bench.parse_args()
     import torch
 
