@@ -1616,10 +1616,12 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 template <int D>
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o, float* __restrict__ delta,
-                  int B, int A, int S, long sb, long sa, long ss) {
+                  int B, int A, int S, long sb, long sa, long ss, float4* __restrict__ zero_fill, long zero_n4) {
   constexpr int LPR = D / 8;  // lanes per row
   const long total = static_cast<long>(B) * A * S;
   const long gid = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  // the fp32 dQ accumulator of the main kernel is cleared here (one launch and one pass less than a memset in front)
+  for (long z = gid; z < zero_n4; z += static_cast<long>(gridDim.x) * blockDim.x) zero_fill[z] = make_float4(0.f, 0.f, 0.f, 0.f);
   const long gstride = static_cast<long>(gridDim.x) * blockDim.x / LPR;
   const int sub = static_cast<int>(gid % LPR);
   const long warp_r0 = (gid - (threadIdx.x % 32)) / LPR;  // loop bound is warp-uniform (the shuffles below need all lanes)
@@ -1779,6 +1781,7 @@ extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const
     const char* e = getenv("LIBAI_B200_ATTN_DEBUG_SKIP_HELPERS");
     skip_helpers = (e != nullptr && atoi(e) != 0) ? 1 : 0;
   }
+  if (skip_helpers) cudaMemsetAsync(dq_accum, 0, sizeof(float) * rows * D, s);
   if (!skip_helpers) {
     // 4 rows per thread-group and iteration; cap the grid at a few waves
     const long groups = (rows + 3) / 4;
@@ -1787,10 +1790,12 @@ extern "C" int lb_attn_bwd(const void* dout, const void* q, const void* k, const
     if (blocks > 148L * 16) blocks = 148L * 16;
     if (D == 64)
       lb::attn_delta_kernel<64><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta, B,
-                                                                   A, S, do_strides[0], do_strides[1], do_strides[2]);
+                                                                   A, S, do_strides[0], do_strides[1], do_strides[2],
+                                                                   reinterpret_cast<float4*>(dq_accum), rows * D / 4);
     else
       lb::attn_delta_kernel<128><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)o, delta, B,
-                                                                    A, S, do_strides[0], do_strides[1], do_strides[2]);
+                                                                    A, S, do_strides[0], do_strides[1], do_strides[2],
+                                                                    reinterpret_cast<float4*>(dq_accum), rows * D / 4);
   }
   lb::AttnBwdParams p;
   p.lse = lse;

@@ -614,7 +614,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> attn_bwd(const Tensor& dout, const Te
   Tensor dk = dqkv.select(3, 1).permute({0, 2, 1, 3});
   Tensor dv = dqkv.select(3, 2).permute({0, 2, 1, 3});
   Tensor delta = at::empty({B, A, S}, q.options().dtype(at::kFloat));
-  Tensor dq_acc = at::zeros({B, A, S, D}, q.options().dtype(at::kFloat));
+  Tensor dq_acc = at::empty({B, A, S, D}, q.options().dtype(at::kFloat));   // cleared by the delta kernel
   TORCH_CHECK(o.stride(3) == 1, "attn_bwd: o must have contiguous D");
   Tensor dout_c = dout;
   if (dout.strides() != o.strides()) {  // bring dout into the [B, S, A, D]-backed layout of o

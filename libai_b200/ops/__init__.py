@@ -136,7 +136,7 @@ def bump_fp8_weight_epoch() -> None:
 # --------------------------------------------------------------------------------------
 # bias gradient of the MLP's first linear inside the dgrad epilogue (GEMM column sums via red.add)
 # --------------------------------------------------------------------------------------
-_FUSED_BIAS_GRAD = os.environ.get("LIBAI_B200_FUSED_BIAS_GRAD", "0") == "1"
+_FUSED_BIAS_GRAD = os.environ.get("LIBAI_B200_FUSED_BIAS_GRAD", "1") == "1"   # +0.8 % on the step in a same-box A/B (profiles/r2_28_*)
 
 
 def fused_bias_grad() -> bool:
