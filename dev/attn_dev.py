@@ -81,6 +81,20 @@ def main():
     od, lsed, std = ext.attn_fwd(q, k, v, True, 0.125, None, None, None, 0.1, 0)
     out["speed"]["fwd_ms_dropout0.1"] = timeit(lambda: ext.attn_fwd(q, k, v, True, 0.125, None, None, None, 0.1, 0))
     out["speed"]["bwd_ms_dropout0.1"] = timeit(lambda: ext.attn_bwd(go, q, k, v, od, lsed, True, 0.125, None, None, None, None, 0.1, std))
+    # Llama-like shape (head dim 128: the sequential backward kernel)
+    q, k, v = inputs(2, 8, 2048, 128)
+    go = torch.randn(2, 2048, 8, 128, device="cuda").bfloat16().permute(0, 2, 1, 3)
+    sc = 1.0 / math.sqrt(128)
+    o, lse, _ = ext.attn_fwd(q, k, v, True, sc, None)
+    qc, kc, vc = (t.contiguous().detach().requires_grad_(True) for t in (q, k, v))
+    og = torch.nn.functional.scaled_dot_product_attention(qc, kc, vc, is_causal=True)
+    gog = torch.randn_like(og)
+    out["speed_B2_H8_S2048_D128"] = {
+        "fwd_ms": timeit(lambda: ext.attn_fwd(q, k, v, True, sc, None)),
+        "bwd_ms": timeit(lambda: ext.attn_bwd(go, q, k, v, o, lse, True, sc, None)),
+        "sdpa_fwd_ms": timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qc, kc, vc, is_causal=True)),
+        "sdpa_bwd_ms": timeit(lambda: torch.autograd.grad(og, (qc, kc, vc), gog, retain_graph=True)),
+    }
     out["ok"] = all(x["ok"] for x in out["numerics"])
     print(json.dumps(out))
 

@@ -493,6 +493,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint32_t p_addr = tmem_base + lane_off + Cfg::P_COL + half * 32;
     const uint32_t o_addr = tmem_base + lane_off + Cfg::O_COL + half * (D / 2);
     float m_run = -INFINITY, l_run = 0.f;       // l_run: partial row sum over this half's columns
+    const int key_lim = p.causal ? min(kv_len, q_idx + 1) : kv_len;   // keys [0, key_lim) are visible to this query row
     constexpr float LOG2E = 1.4426950408889634f;
     unsigned long long rng_seed = 0, rng_offset = 0;
     if constexpr (DROP) {
@@ -554,8 +555,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
             if constexpr (MASK) {
               const int kidx = k0 + c * 32 + i;
-              if (kidx >= kv_len || (p.causal && kidx > q_idx)) x0 = -INFINITY;
-              if (kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) x1 = -INFINITY;
+              x0 = kidx < key_lim ? x0 : -INFINITY;       // branch-free: one compare + select per element
+              x1 = kidx + 1 < key_lim ? x1 : -INFINITY;
             }
             mx = fmaxf(mx, fmaxf(x0, x1));
           }
@@ -611,8 +612,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
             if constexpr (MASK) {
               const int kidx = k0 + c * 32 + i;
-              if (kidx >= kv_len || (p.causal && kidx > q_idx)) e0 = 0.f;
-              if (kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) e1 = 0.f;
+              e0 = kidx < key_lim ? e0 : 0.f;
+              e1 = kidx + 1 < key_lim ? e1 : 0.f;
             }
             rs0 += e0;   // the softmax normaliser is the sum of the UNdropped probabilities
             rs1 += e1;
@@ -886,10 +887,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&qdo_empty[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 256);
+    mbar_init(pds_full, 8);     // one arrival per softmax warp
     mbar_init(pds_empty, 1);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 256);
+    mbar_init(dq_empty, 8);
     mbar_init(acc_full, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -1013,6 +1014,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const float lse2 = q_ok ? p.lse[bh * p.S + q_idx] * 1.4426950408889634f : 0.f;
       const float delta = q_ok ? p.delta[bh * p.S + q_idx] : 0.f;
       const bool need_mask = (p.causal && q_blk == kv_blk) || (k0 + 128 > kv_len) || (q_blk * 128 + 128 > p.S);
+      const int key_lim = !q_ok ? 0 : (p.causal ? min(kv_len, q_idx + 1) : kv_len);   // keys [0, key_lim) are visible
       mbar_wait(sdp_full, it & 1);
       tc_fence_after_sync();
       mbar_wait(pds_empty, (it & 1) ^ 1);
@@ -1059,8 +1061,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             }
             if constexpr (MASK) {
               const int kidx = k0 + c * 32 + i;
-              if (!q_ok || kidx >= kv_len || (p.causal && kidx > q_idx)) p0 = 0.f;
-              if (!q_ok || kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) p1 = 0.f;
+              p0 = kidx < key_lim ? p0 : 0.f;           // branch-free: one compare + select per element
+              p1 = kidx + 1 < key_lim ? p1 : 0.f;
             }
             float g0 = __uint_as_float(td[i]), g1 = __uint_as_float(td[i + 1]);   // dP w.r.t. the dropped, rescaled P
             float pd0 = p0, pd1 = p1;                                               // what multiplied V in the forward
@@ -1107,7 +1109,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (need_mask) pds(std::true_type{}); else pds(std::false_type{});
       tc_fence_before_sync();
       fence_proxy_async();
-      mbar_arrive(pds_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
       // ---- dQ block: TMEM -> fp32 atomics
       mbar_wait(dq_full, it & 1);
       tc_fence_after_sync();
@@ -1163,7 +1166,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       }
       tc_fence_before_sync();
-      mbar_arrive(dq_empty);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
     }
     if (Cfg::DQ_BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
     // ---- dV / dK accumulators: thread r <-> key row r
@@ -1457,6 +1461,7 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int q_idx = q_blk * 128 + r;
       const bool q_ok = q_idx < p.S;
       const bool need_mask = (p.causal && q_blk == kv_blk) || (k0 + 128 > kv_len) || (q_blk * 128 + 128 > p.S);
+      const int key_lim = !q_ok ? 0 : (p.causal ? min(kv_len, q_idx + 1) : kv_len);   // keys [0, key_lim) are visible
       const float lse2 = lse_raw * LOG2E, delta_s = delta_raw * p.scale;
       row_stats(it + 1, lse_raw, delta_raw);     // next block's row statistics: in flight during this block's softmax
       [[maybe_unused]] long bias_off = 0;
@@ -1506,8 +1511,8 @@ attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             if constexpr (MASK) {
               const int kidx = k0 + c * 32 + i;
-              p0 = (!q_ok || kidx >= kv_len || (p.causal && kidx > q_idx)) ? 0.f : p0;
-              p1 = (!q_ok || kidx + 1 >= kv_len || (p.causal && kidx + 1 > q_idx)) ? 0.f : p1;
+              p0 = kidx < key_lim ? p0 : 0.f;             // branch-free: one compare + select per element
+              p1 = kidx + 1 < key_lim ? p1 : 0.f;
             }
             if constexpr (DROP) {
               const bool keep0 = rnd_byte(rnd[i >> 4], i & 15) >= p.drop_thresh;
