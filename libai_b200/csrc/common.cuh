@@ -373,8 +373,9 @@ LB_DEVICE uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 LB_DEVICE float2 unpack_bf16(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+  // a bf16 is the upper half of an fp32: one shift for the low element, one mask for the high one (the intrinsic
+  // compiled to PRMT + IMAD for the high half)
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_GELU_TANH = 2, ACT_RELU = 3, ACT_SILU = 4, ACT_QUICK_GELU = 5,
