@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NORM_BWD_WARPS * 32, 3)
 norm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ x, const W* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ gx,
                      float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, int rows,
-                     const __nv_bfloat16* __restrict__ gadd) {
+                     const __nv_bfloat16* __restrict__ gadd, float* __restrict__ acc_dgamma, float* __restrict__ acc_dbeta) {
   constexpr int H = VPL * 256;
   __shared__ float red[NORM_BWD_WARPS][32 * 8 + 8];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -253,8 +253,14 @@ norm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* 
         float acc = 0.f;
 #pragma unroll
         for (int w = 0; w < NORM_BWD_WARPS; ++w) acc += red[w][c];
-        float* dst = (which == 0 ? part_dgamma : part_dbeta) + static_cast<size_t>(blockIdx.x) * H + i * 256 + c;
-        *dst = acc;
+        if (acc_dgamma != nullptr) {
+          // accumulate mode (training: dγ/dβ live in the fp32 main_grad buffer): one red.add per block and column
+          // straight into the gradient instead of a [blocks, H] partial matrix + a second reduction kernel
+          atomicAdd((which == 0 ? acc_dgamma : acc_dbeta) + i * 256 + c, acc);
+        } else {
+          float* dst = (which == 0 ? part_dgamma : part_dbeta) + static_cast<size_t>(blockIdx.x) * H + i * 256 + c;
+          *dst = acc;
+        }
       }
     }
   }
@@ -402,10 +408,11 @@ bool fwd_dispatch(int vpl, const T* x, const W* g, const W* b, T* y, float* mean
 template <typename W, bool RMS>
 bool bwd_dispatch_bf16(int vpl, const __nv_bfloat16* gy, const __nv_bfloat16* x, const W* g, const float* mean,
                        const float* rstd, __nv_bfloat16* gx, float* pdg, float* pdb, int rows, int grid, cudaStream_t s,
-                       const __nv_bfloat16* gadd) {
+                       const __nv_bfloat16* gadd, float* acc_dg, float* acc_db) {
 #define LB_CASE(V)                                                                                                        \
   case V:                                                                                                                 \
-    lb::norm_bwd_bf16_kernel<W, V, RMS><<<grid, lb::NORM_BWD_WARPS * 32, 0, s>>>(gy, x, g, mean, rstd, gx, pdg, pdb, rows, gadd); \
+    lb::norm_bwd_bf16_kernel<W, V, RMS><<<grid, lb::NORM_BWD_WARPS * 32, 0, s>>>(gy, x, g, mean, rstd, gx, pdg, pdb, rows, gadd, \
+                                                                                 acc_dg, acc_db);                         \
     return true;
   switch (vpl) {
     LB_CASE(1) LB_CASE(2) LB_CASE(3) LB_CASE(4)
@@ -419,9 +426,11 @@ bool norm_bwd_uses_bf16_kernel(int H, int dtype) { return dtype == 0 && H % 256 
 
 template <typename T, typename W, bool RMS>
 bool bwd_dispatch(int vpl, const T* gy, const T* x, const W* g, const float* mean, const float* rstd, T* gx, float* pdg,
-                  float* pdb, int rows, int grid, cudaStream_t s, const T* gadd) {
+                  float* pdb, int rows, int grid, cudaStream_t s, const T* gadd, float* acc_dg = nullptr,
+                  float* acc_db = nullptr) {
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (norm_bwd_uses_bf16_kernel(vpl * 256, 0)) return bwd_dispatch_bf16<W, RMS>(vpl, gy, x, g, mean, rstd, gx, pdg, pdb, rows, grid, s, gadd);
+    if (norm_bwd_uses_bf16_kernel(vpl * 256, 0))
+      return bwd_dispatch_bf16<W, RMS>(vpl, gy, x, g, mean, rstd, gx, pdg, pdb, rows, grid, s, gadd, acc_dg, acc_db);
   }
 #define LB_CASE(V)                                                                                                   \
   case V:                                                                                                            \
@@ -491,14 +500,19 @@ extern "C" int lb_norm_bwd(const void* gy, const void* x, const void* gamma, con
   bool done = false;
   float* pdg = workspace;
   float* pdb = dbeta != nullptr ? workspace + static_cast<size_t>(grid) * H : nullptr;
+  // accumulate mode + bandwidth-oriented bf16 kernel: the blocks add their column partials straight into dgamma / dbeta
+  const bool direct = accumulate && norm_bwd_uses_bf16_kernel(H, dtype);
+  float* direct_dg = direct ? dgamma : nullptr;
+  float* direct_db = (direct && dbeta != nullptr) ? dbeta : nullptr;
+  if (direct && dbeta == nullptr) pdb = nullptr;
 #define LB_GO(T, W)                                                                                                  \
   {                                                                                                                  \
     if (fast) {                                                                                                      \
       done = rms ? bwd_dispatch<T, W, true>(H / 256, (const T*)gy, (const T*)x, (const W*)gamma, mean, rstd, (T*)gx, \
-                                            pdg, pdb, rows, grid, s, (const T*)gadd)                                 \
+                                            pdg, pdb, rows, grid, s, (const T*)gadd, direct_dg, direct_db)           \
                  : bwd_dispatch<T, W, false>(H / 256, (const T*)gy, (const T*)x, (const W*)gamma, mean, rstd,        \
-                                             (T*)gx, pdg, pdb, rows, grid, s, (const T*)gadd);                       \
-      if (done) {                                                                                                    \
+                                             (T*)gx, pdg, pdb, rows, grid, s, (const T*)gadd, direct_dg, direct_db); \
+      if (done && direct_dg == nullptr) {                                                                            \
         lb::colreduce_kernel<<<dim3((H + 31) / 32, dbeta != nullptr ? 2 : 1), 256, 0, s>>>(pdg, dgamma, pdb, dbeta, grid, \
                                                                                            H, accumulate);           \
       }                                                                                                              \
