@@ -818,6 +818,14 @@ bool make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dtype, const void* ba
                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_tiled();
   if (fn == nullptr) return false;
+  // the driver entry point needs a current context: threads that have not touched the runtime yet (the autograd
+  // engine's) bind the primary context once (otherwise the first call returns CUDA_ERROR_INVALID_CONTEXT — handled by
+  // the retry below, but reported as an API error by compute-sanitizer)
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   cuuint64_t gdim[5];
   cuuint64_t gstride[5];
   cuuint32_t gbox[5];
