@@ -34,6 +34,8 @@ int lb_bias_act_bwd(const void* gy, const void* x, const void* bias, void* gx, l
 int lb_bias_residual(const void* x, const void* bias, const void* res, void* y, long rows, int N, cudaStream_t s);
 int lb_swiglu_fwd(const void* gate, const void* up, void* y, long n, cudaStream_t s);
 int lb_swiglu_bwd(const void* gy, const void* gate, const void* up, void* dgate, void* dup, long n, cudaStream_t s);
+int lb_swiglu_packed_fwd(const void* gu, void* y, long rows, long F, cudaStream_t s);
+int lb_swiglu_packed_bwd(const void* gy, const void* gu, void* dgu, long rows, long F, cudaStream_t s);
 int lb_rope_qkv(const void* x, const float* cosv, const float* sinv, void* y, long heads, int S, int A, int D,
                 int pos_offset, int backward, cudaStream_t s);
 int lb_rope(const void* x, const float* cosv, const float* sinv, void* y, long rows, int S, int D, int backward,
@@ -415,6 +417,24 @@ std::tuple<Tensor, Tensor> swiglu_bwd(const Tensor& gy, const Tensor& gate, cons
         "swiglu_bwd");
   return std::make_tuple(dg, du);
 }
+// gu [T, 2F] = [gate | up] (one GEMM against the stacked gate / up weights) -> silu(gate) * up  [T, F]
+Tensor swiglu_packed_fwd(const Tensor& gu) {
+  c10::cuda::CUDAGuard guard(gu.device());
+  TORCH_CHECK(gu.dim() == 2 && gu.is_contiguous() && gu.scalar_type() == at::kBFloat16 && gu.size(1) % 16 == 0,
+              "swiglu_packed_fwd: contiguous bf16 [T, 2F] with F % 8 == 0");
+  Tensor y = at::empty({gu.size(0), gu.size(1) / 2}, gu.options());
+  check(lb_swiglu_packed_fwd(gu.data_ptr(), y.data_ptr(), gu.size(0), gu.size(1) / 2, cur_stream()), "swiglu_packed_fwd");
+  return y;
+}
+Tensor swiglu_packed_bwd(const Tensor& gy, const Tensor& gu) {
+  c10::cuda::CUDAGuard guard(gu.device());
+  TORCH_CHECK(gy.is_contiguous() && gu.is_contiguous() && gy.dim() == 2 && gu.size(1) == 2 * gy.size(1) &&
+                  gy.scalar_type() == at::kBFloat16, "swiglu_packed_bwd: gy [T, F], gu [T, 2F] contiguous bf16");
+  Tensor dgu = at::empty_like(gu);
+  check(lb_swiglu_packed_bwd(gy.data_ptr(), gu.data_ptr(), dgu.data_ptr(), gu.size(0), gy.size(1), cur_stream()),
+        "swiglu_packed_bwd");
+  return dgu;
+}
 // qkv [b, s, a, 3d] packed projection; rotates q and k (v copied).  inplace=true rewrites qkv itself.
 Tensor rope_qkv(const Tensor& qkv, const Tensor& cosv, const Tensor& sinv, int64_t pos_offset, bool backward,
                 bool inplace) {
@@ -780,6 +800,8 @@ TORCH_LIBRARY(libai_b200, m) {
   m.def("bias_residual_fwd(Tensor x, Tensor? bias, Tensor? res) -> Tensor", &bias_residual_fwd);
   m.def("swiglu_fwd(Tensor gate, Tensor up) -> Tensor", &swiglu_fwd);
   m.def("swiglu_bwd(Tensor gy, Tensor gate, Tensor up) -> (Tensor, Tensor)", &swiglu_bwd);
+  m.def("swiglu_packed_fwd(Tensor gu) -> Tensor", &swiglu_packed_fwd);
+  m.def("swiglu_packed_bwd(Tensor gy, Tensor gu) -> Tensor", &swiglu_packed_bwd);
   m.def("dgrad_actgrad(Tensor gy, Tensor w, Tensor pre, int act, Tensor(a!)? bias_grad=None) -> Tensor", &dgrad_actgrad);
   m.def("rope(Tensor x, Tensor cos, Tensor sin, bool backward) -> Tensor", &rope);
   m.def("rope_qkv(Tensor(a!) qkv, Tensor cos, Tensor sin, int pos_offset, bool backward, bool inplace) -> Tensor(a!)", &rope_qkv);

@@ -144,6 +144,41 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gate, const 
   }
 }
 
+// packed form: gu [T, 2F] = [gate | up] (the output of ONE GEMM against the stacked gate/up weights) -> y [T, F]
+__global__ void swiglu_packed_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ y, size_t rows,
+                                         size_t fvec /* F / 8 */) {
+  const size_t total = rows * fvec;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / fvec, c = i % fvec;
+    float g[8], u[8];
+    ld8(gu + (r * 2 * fvec + c) * 8, g);
+    ld8(gu + (r * 2 * fvec + fvec + c) * 8, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = g[j] / (1.0f + __expf(-g[j])) * u[j];
+    st8(y + i * 8, g);
+  }
+}
+// dgu [T, 2F] = [d gate | d up] from gy [T, F] and the saved gu
+__global__ void swiglu_packed_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ gu,
+                                         __nv_bfloat16* __restrict__ dgu, size_t rows, size_t fvec) {
+  const size_t total = rows * fvec;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / fvec, c = i % fvec;
+    float g[8], u[8], d[8], dg[8], du[8];
+    ld8(gu + (r * 2 * fvec + c) * 8, g);
+    ld8(gu + (r * 2 * fvec + fvec + c) * 8, u);
+    ld8(gy + i * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sg = 1.0f / (1.0f + __expf(-g[j]));
+      du[j] = d[j] * g[j] * sg;
+      dg[j] = d[j] * u[j] * sg * (1.0f + g[j] * (1.0f - sg));
+    }
+    st8(dgu + (r * 2 * fvec + c) * 8, dg);
+    st8(dgu + (r * 2 * fvec + fvec + c) * 8, du);
+  }
+}
+
 __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ gate,
                                   const __nv_bfloat16* __restrict__ up, __nv_bfloat16* __restrict__ dgate,
                                   __nv_bfloat16* __restrict__ dup, size_t total_vec) {
@@ -561,6 +596,19 @@ extern "C" int lb_swiglu_bwd(const void* gy, const void* gate, const void* up, v
   if (n == 0) return 0;
   lb::swiglu_bwd_kernel<<<ew_grid(n / 8, 256), 256, 0, s>>>((const bf16*)gy, (const bf16*)gate, (const bf16*)up,
                                                             (bf16*)dgate, (bf16*)dup, n / 8);
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_swiglu_packed_fwd(const void* gu, void* y, long rows, long F, cudaStream_t s) {
+  if (F % 8) return -1;
+  if (rows == 0) return 0;
+  lb::swiglu_packed_fwd_kernel<<<ew_grid(rows * F / 8, 256), 256, 0, s>>>((const bf16*)gu, (bf16*)y, (size_t)rows, (size_t)(F / 8));
+  return (int)cudaGetLastError();
+}
+extern "C" int lb_swiglu_packed_bwd(const void* gy, const void* gu, void* dgu, long rows, long F, cudaStream_t s) {
+  if (F % 8) return -1;
+  if (rows == 0) return 0;
+  lb::swiglu_packed_bwd_kernel<<<ew_grid(rows * F / 8, 256), 256, 0, s>>>((const bf16*)gy, (const bf16*)gu, (bf16*)dgu,
+                                                                         (size_t)rows, (size_t)(F / 8));
   return (int)cudaGetLastError();
 }
 extern "C" int lb_rope(const void* x, const float* cosv, const float* sinv, void* y, long rows, int S, int D,

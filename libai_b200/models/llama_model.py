@@ -77,7 +77,35 @@ class LlamaMLP(nn.Module):
                                 init_method=output_layer_init_method, layer_idx=layer_idx)
 
     def forward(self, hidden_states):
+        y = self._forward_fused_gate_up(hidden_states)
+        if y is not None:
+            return y
         return self.down_proj(OF.swiglu(self.gate_proj(hidden_states), self.up_proj(hidden_states)))
+
+    def _forward_fused_gate_up(self, x):
+        """Gate and up projection as ONE GEMM against the ``[2F, K]`` view over both weights (they are adjacent once the
+        optimizer owns the parameters) — ``ops/gated_mlp.py``; ``None`` = not applicable, take the two-GEMM path."""
+        from libai_b200.ops import gated_mlp, use_native
+
+        if not (gated_mlp.enabled() and x.is_cuda and x.dtype == torch.bfloat16 and use_native(x)):
+            return None
+        wg, wu, wd = self.gate_proj.weight, self.up_proj.weight, self.down_proj.weight
+        if self.gate_proj.bias is not None or self.up_proj.bias is not None or self.down_proj.bias is not None:
+            return None
+        if wg.dtype != torch.bfloat16 or gated_mlp.fused_gate_up_views(wg, wu) is None:
+            return None
+        topo = dutil.get_dist_util()
+        t = topo.tensor_parallel_size
+        if t == 1:
+            return gated_mlp.gated_mlp(x, wg, wu, wd)
+        if not (topo.fused_tp_comm and topo.sequence_parallel and x.dim() == 2):
+            return None
+        from libai_b200.ops import comm_gemm
+
+        M, K = x.shape[0] * t, x.shape[1]
+        if not (comm_gemm.fused_supported(M, 2 * wg.shape[0], K, t) and comm_gemm.fused_supported(M, wd.shape[0], wg.shape[0], t)):
+            return None
+        return gated_mlp.tp_gated_mlp(x.contiguous(), wg, wu, wd, None, topo.tp_group)
 
 
 class LlamaAttention(nn.Module):
