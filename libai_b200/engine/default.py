@@ -314,6 +314,7 @@ class DefaultTrainer(TrainerBase):
     def run_step(self):
         self._trainer.iter = self.iter
         self._trainer.start_iter = self.start_iter
+        self._trainer.max_iter = self.max_iter
         self._trainer.storage = self.storage
         self._trainer.run_step(self.get_batch, try_get_key(self.cfg, "train.input_placement_device", default="cuda"))
 

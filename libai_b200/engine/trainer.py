@@ -164,6 +164,11 @@ class StepTrainer(TrainerBase):
         self.cuda_graphs = False       # set by DefaultTrainer from cfg.train.cuda_graphs.enabled
         self._graphs_tried = False
         self.graphs_enabled = False
+        # inputs of the NEXT step are fetched (loader → pinned host → device) right behind this step's kernels, before
+        # the host blocks on the metrics of a logging step: the device then finds its inputs resident instead of idling
+        # through the loader hand-over and the copy (matters with log_period = 1, e.g. bench.py's end-to-end loop)
+        self.prefetch_inputs = os.environ.get("LIBAI_B200_INPUT_PREFETCH", "1") == "1"
+        self._staged_batches = None
 
     def _arm_grad_overlap(self, last_micro_batch: bool):
         """Opt-in (``LIBAI_B200_OVERLAP_GRAD_SYNC=1``): overlap the data-parallel gradient reduction with the backward
@@ -236,7 +241,9 @@ class StepTrainer(TrainerBase):
         assert self.model.training, "[StepTrainer] model was changed to eval mode!"
         topo = dutil.get_dist_util()
         t0 = time.perf_counter()
-        batches = self._next_batches(get_batch, input_placement_device)
+        batches, self._staged_batches = self._staged_batches, None
+        if batches is None:
+            batches = self._next_batches(get_batch, input_placement_device)
         data_time = time.perf_counter() - t0
         use_events = topo.device_type == "cuda"
         if use_events:
@@ -249,7 +256,15 @@ class StepTrainer(TrainerBase):
         device_time = None
         if use_events:
             self._ev[1].record()
-        if (self.iter + 1) % self.log_period == 0 or self.iter == self.start_iter:
+        logging_step = (self.iter + 1) % self.log_period == 0 or self.iter == self.start_iter
+        if logging_step and self.prefetch_inputs and (self.max_iter <= 0 or self.iter + 1 < self.max_iter):
+            t1 = time.perf_counter()
+            try:
+                self._staged_batches = self._next_batches(get_batch, input_placement_device)
+            except StopIteration:
+                self._staged_batches = None
+            data_time += time.perf_counter() - t1
+        if logging_step:
             if use_events:
                 self._ev[1].synchronize()
                 device_time = self._ev[0].elapsed_time(self._ev[1]) * 1e-3
