@@ -131,3 +131,34 @@ def test_zero2_and_3_with_tensor_and_sequence_parallelism(tmp_path):
     for stage in (2, 3):
         for a, b in zip(res[1], res[stage]):
             assert abs(a - b) < 2e-3 * max(1.0, abs(a)), (stage, res[1], res[stage])
+
+
+def _worker_pp(rank, world, out_dir, stage):
+    import json
+
+    import train_net
+    from libai_b200.config import default_argument_parser
+
+    argv = ["--config-file", os.path.join(REPO, "configs/gpt2_synthetic.py")]
+    tiny = [t for t in TINY if not t.startswith("train.dist.data_parallel_size")]
+    extra = [f"train.output_dir={out_dir}", "train.dist.pipeline_parallel_size=2", "train.dist.data_parallel_size=2",
+             "train.num_accumulation_steps=2", "train.zero_optimization.enabled=true",
+             f"train.zero_optimization.stage={stage}", "train.checkpointer.period=100"]
+    train_net.main(default_argument_parser().parse_args(argv + tiny + extra))
+    path = os.path.join(out_dir, "metrics.json")
+    losses = [json.loads(ln) for ln in open(path)] if os.path.exists(path) else []
+    return [m["total_loss"] for m in losses if "total_loss" in m]
+
+
+def test_zero2_under_pipeline_parallelism(tmp_path):
+    """pp2 x dp2, two 1F1B micro-batches: every micro-batch's backward opens, fills and reduce-scatters the pooled
+    per-block gradient buffers again — same trajectory as stage 1."""
+    from tests.dist_utils import run_distributed
+
+    res = {}
+    for stage in (1, 2):
+        outs = run_distributed(_worker_pp, 4, str(tmp_path / f"pp_s{stage}"), stage, timeout=900)
+        res[stage] = max(outs, key=len)          # the rank that logs the loss
+    assert len(res[1]) >= 6
+    for a, b in zip(res[1], res[2]):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(a)), (res[1], res[2])
