@@ -118,3 +118,31 @@ def test_llama_loader_and_generation_parity(tmp_path):
     ours = model.generate(ids, max_length=16, eos_token_id=None, pad_token_id=0)
     theirs = hf.generate(ids, max_length=16, do_sample=False, eos_token_id=None, pad_token_id=0)
     assert torch.equal(ours, theirs)
+
+
+def test_roberta_loader(tmp_path):
+    """HF RobertaForMaskedLM (random init) → RobertaForPreTraining: masked-LM logits agree, incl. a padded sample
+    (RoBERTa's position ids start after `pad_token_id`)."""
+    from libai_b200.models import RobertaForPreTraining
+    from libai_b200.models.utils.model_loader import RobertaLoaderHuggerFace
+
+    torch.manual_seed(0)
+    hf = transformers.RobertaForMaskedLM(transformers.RobertaConfig(
+        vocab_size=96, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+        max_position_embeddings=40, type_vocab_size=1, pad_token_id=1, hidden_dropout_prob=0,
+        attention_probs_dropout_prob=0)).eval()
+    cfg = DictConfig(dict(vocab_size=1, hidden_size=8, hidden_layers=1, num_attention_heads=1, intermediate_size=8,
+                          hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, max_position_embeddings=8,
+                          num_tokentypes=1, add_pooling_layer=False, initializer_range=0.02, layernorm_eps=1e-5,
+                          pad_token_id=1, bias_gelu_fusion=True, bias_dropout_fusion=True, scale_mask_softmax_fusion=True,
+                          apply_query_key_layer_scaling=False, apply_residual_post_layernorm=False, amp_enabled=False))
+    model = RobertaLoaderHuggerFace(RobertaForPreTraining, cfg, _save(hf, tmp_path, "roberta")).load().eval()
+    ids = torch.randint(2, 96, (2, 16))
+    am = torch.ones(2, 16, dtype=torch.long)
+    am[1, 11:] = 0
+    ids[1, 11:] = 1                      # padded tail
+    with torch.no_grad():
+        a = model(ids, am)
+        b = hf(input_ids=ids, attention_mask=am)
+    valid = am.bool()
+    assert (a["prediction_scores"][valid] - b.logits[valid]).abs().max() < 1e-2
