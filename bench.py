@@ -513,10 +513,16 @@ class _ExtrasWatchdog:
             self.thread.start()
 
     def begin(self, name):
-        self.current, self.t0 = name, time.time()
+        self.t0 = time.time()      # (before `current`: the poller must never pair a new phase with an old start time)
+        self.current = name
+
+    def idle(self):
+        """Between two supervised phases: no time limit is running."""
+        self.current = None
 
     def stop(self):
         self._stop = True
+        self.current = None
 
     def _leave(self, why):
         name = self.current or "extra"
@@ -579,13 +585,12 @@ def main():
 
     layouts = {main_res["parallelism"]: {k: main_res[k] for k in ("value", "ms_per_step", "cuda_graphs", "gpu_launches",
                                                                   "host_enqueue_ms_per_step", "global_batch")}}
-    ref_same_box = None
-    if args.ref_same_box and args.impl == "native" and args.model == "gpt2":
-        ref_same_box = measure_pytorch_baseline(args, world, rank, local_rank, min(args.steps, 10), 3)
+    state = {"ref": None}      # filled in below; `emit` prints whatever has been measured when it is called
 
     def emit():
         if rank != 0:
             return
+        ref_same_box = state["ref"]
         base = PUBLISHED_TOKENS_PER_S.get(world) if args.model == "gpt2" else None
         value = main_res["value"]
         spec = MODELS[args.model]
@@ -629,13 +634,25 @@ def main():
         }
         print(json.dumps(line), flush=True)
 
+    # Everything after the headline measurement runs under a watchdog: a failure or a hang in the comparator or in an
+    # extra layout, on any rank, ends every rank cleanly with the line printed — it must never take the headline down.
+    watch = _ExtrasWatchdog(world, emit, layouts, limit_s=float(os.environ.get("LIBAI_B200_BENCH_EXTRA_LIMIT_S", "420")))
+    if args.ref_same_box and args.impl == "native" and args.model == "gpt2":
+        watch.begin("ref_same_box")
+        try:
+            state["ref"] = measure_pytorch_baseline(args, world, rank, local_rank, min(args.steps, 10), 3)
+        except BaseException as e:  # noqa: BLE001
+            watch.fail("ref_same_box", f"{type(e).__name__}: {str(e)[:300]}")   # does not return when world > 1
+            state["ref"] = None
+            layouts["ref_same_box"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        watch.idle()
+
     if args.extras and args.impl == "native" and args.model == "gpt2" and not args.layout and args.tp == 1 and args.pp == 1:
         # the model-parallel layouts that fit this GPU count, same global batch, same launch (BASELINE.json configs:
         # "TP=2 DP=4", "TP=2 PP=2 DP=2 + ZeRO-1").  They run LAST and under a watchdog: the headline measurement above
         # is already complete, and a failure (or a hang) in an extra layout on any rank ends every rank cleanly with
         # the line printed — it must never take the headline down.
         names = {2: ["tp2"], 4: ["tp2", "3d"], 8: ["tp2", "3d"]}.get(world, [])
-        watch = _ExtrasWatchdog(world, emit, layouts, limit_s=float(os.environ.get("LIBAI_B200_BENCH_EXTRA_LIMIT_S", "420")))
         for name in names:
             lay = layout_of(args, world, name)
             watch.begin(name)
@@ -649,7 +666,8 @@ def main():
             except BaseException as e:  # noqa: BLE001 - incl. KeyboardInterrupt/SystemExit raised inside the trainer
                 watch.fail(name, f"{type(e).__name__}: {str(e)[:300]}")   # does not return when world > 1
                 layouts[name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
-        watch.stop()
+            watch.idle()
+    watch.stop()
 
     emit()
     if world > 1:
